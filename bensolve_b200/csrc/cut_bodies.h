@@ -1,0 +1,373 @@
+// Per-work-item logic of the cut stages (K1..K5), shared between the sm_100a kernels
+// (cut_kernels.cuh) and the host-side test double built with -DB200_EMULATE (tests only; the
+// product library is never built with it and has no CPU path).
+//
+// Reference semantics follow SURVEY App. A; each function cites the bslv_poly.c lines it replaces.
+// Floating point is the reference's operation order with separately rounded multiply and add
+// (gcc -std=c99 => no contraction), so results are bit-identical to the CPU engine.
+#pragma once
+#include "cut_types.h"
+
+#if defined(__CUDA_ARCH__)
+#define B200_MUL(a, b) __dmul_rn((a), (b))
+#define B200_ADD(a, b) __dadd_rn((a), (b))
+#define B200_SUB(a, b) __dsub_rn((a), (b))
+#define B200_DIV(a, b) __ddiv_rn((a), (b))
+#define B200_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define B200_ATOMIC_SUB(p, v) atomicSub((p), (v))
+#define B200_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define B200_ATOMIC_AND(p, v) atomicAnd((p), (v))
+#define B200_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define B200_ATOMIC_EXCH(p, v) atomicExch((p), (v))
+#else // host compilation pass (must be built with -ffp-contract=off)
+#define B200_MUL(a, b) ((a) * (b))
+#define B200_ADD(a, b) ((a) + (b))
+#define B200_SUB(a, b) ((a) - (b))
+#define B200_DIV(a, b) ((a) / (b))
+static inline u32 b200_fetch_add(u32 *p, u32 v) { u32 o = *p; *p = o + v; return o; }
+static inline u32 b200_fetch_sub(u32 *p, u32 v) { u32 o = *p; *p = o - v; return o; }
+static inline u32 b200_fetch_or(u32 *p, u32 v) { u32 o = *p; *p = o | v; return o; }
+static inline u32 b200_fetch_and(u32 *p, u32 v) { u32 o = *p; *p = o & v; return o; }
+static inline u32 b200_fetch_min(u32 *p, u32 v) { u32 o = *p; if (v < o) *p = v; return o; }
+static inline u32 b200_exch(u32 *p, u32 v) { u32 o = *p; *p = v; return o; }
+#define B200_ATOMIC_ADD(p, v) b200_fetch_add((p), (v))
+#define B200_ATOMIC_SUB(p, v) b200_fetch_sub((p), (v))
+#define B200_ATOMIC_OR(p, v) b200_fetch_or((p), (v))
+#define B200_ATOMIC_AND(p, v) b200_fetch_and((p), (v))
+#define B200_ATOMIC_MIN(p, v) b200_fetch_min((p), (v))
+#define B200_ATOMIC_EXCH(p, v) b200_exch((p), (v))
+#endif
+
+B200_HD bool bit_test(const u32 *w, u32 i) { return (w[i >> 5] >> (i & 31)) & 1u; }
+
+// h . x for device row r, strict left-to-right from 0 (bslv_poly.c:123-125, 569-571, 593-595)
+B200_HD double row_dot(const DevState &S, const double *h, u32 r)
+{
+	double s = B200_MUL(h[0], S.coord[r]);
+	for (int j = 1; j < S.d; j++) s = B200_ADD(s, B200_MUL(h[j], S.coord[(size_t)j * S.cap_rows + r]));
+	return s;
+}
+
+// A.2 classes from the three thresholds (bslv_poly.c:596, :666, :573)
+B200_HD u8 class_of(double t, int ideal, const CutParams &P)
+{
+	if (t > P.hi[ideal]) return CLS_PLUS;
+	if (t > P.mid[ideal]) return CLS_ZP;
+	if (t > P.lo[ideal]) return CLS_ZERO;
+	return CLS_MINUS;
+}
+
+// K1 for one row: class byte; bookkeeping of the trigger scan (bslv_poly.c:121-128)
+B200_HD u8 classify_row(const DevState &S, const CutParams &P, u32 r, bool &strict, bool &zp)
+{
+	strict = zp = false;
+	if (!bit_test(S.live, r)) return CLS_DEAD;
+	int id = bit_test(S.ideal, r) ? 1 : 0;
+	double t = row_dot(S, P.h, r);
+	strict = t < P.lo[id];
+	u8 c = class_of(t, id, P);
+	zp = (c == CLS_ZP);
+	return c;
+}
+
+B200_HD bool is_visited_class(u8 c) { return c == CLS_ZERO || c == CLS_MINUS; }
+
+// ZERO+ closure step for visited-list entry i (bslv_poly.c:666-674): a vertex with
+// thr+1e-11 < h.x <= thr+1e-9 that neighbours a visited vertex is projected onto the hyperplane in
+// place and then treated like any other visited vertex.  Returns true if it activated the entry.
+B200_HD bool zp_activate(const DevState &S, const CutParams &P, u32 i)
+{
+	u32 v = S.vis[i];
+	if (S.cls[v] != CLS_ZP) return false;
+	bool touch = false;
+	for (u32 q = 0, off = S.adj_off[v], n = S.adj_len[v]; q < n && !touch; q++)
+		touch = is_visited_class(S.cls[S.adj_pool[off + q]]);
+	if (!touch) return false;
+	int id = bit_test(S.ideal, v) ? 1 : 0;
+	double thr = id ? 0.0 : P.alpha;
+	double mu = B200_DIV(B200_SUB(row_dot(S, P.h, v), thr), P.hh);
+	for (int j = 0; j < S.d; j++) {
+		double *x = S.coord + (size_t)j * S.cap_rows + v;
+		*x = B200_SUB(*x, B200_MUL(mu, P.h[j]));
+	}
+	double t = row_dot(S, P.h, v);
+	S.cls[v] = (t > P.lo[id]) ? CLS_ZERO : CLS_MINUS;   // re-test of bslv_poly.c:573 after :674
+	B200_ATOMIC_ADD(&S.ctl->n_zp_projected, 1u);
+	return true;
+}
+
+// |A n B| of two sorted lists
+B200_HD u32 isect_count(const u32 *a, u32 na, const u32 *b, u32 nb)
+{
+	u32 i = 0, j = 0, n = 0;
+	while (i < na && j < nb) {
+		u32 x = a[i], y = b[j];
+		n += (x == y);
+		i += (x <= y);
+		j += (y <= x);
+	}
+	return n;
+}
+
+// K3a: how many new rows / incidence entries / PLUS neighbours visited entry i produces
+// (sizes of what bslv_poly.c:573-588 and :597-665 append)
+B200_HD void count_outputs(const DevState &S, u32 i)
+{
+	u32 v = S.vis[i];
+	u8 c = S.cls[v];
+	u32 n_out = 0, inc_sz = 0, nplus = 0;
+	if (is_visited_class(c)) {
+		const u32 *iv = S.inc_pool + S.inc_off[v];
+		const u32 niv = S.inc_len[v];
+		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
+		if (c == CLS_ZERO && niv > B200_MAXINC) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
+		for (u32 q = 0, off = S.adj_off[v], n = S.adj_len[v]; q < n; q++) {
+			u32 k = S.adj_pool[off + q];
+			if (S.cls[k] != CLS_PLUS) continue;
+			nplus++;
+			const u32 *ik = S.inc_pool + S.inc_off[k];
+			const u32 nik = S.inc_len[k];
+			if (c == CLS_MINUS)
+				inc_sz += 1 + isect_count(iv, niv, ik, nik);
+			else {
+				u32 a = 0, b = 0;
+				while (a < niv && a < B200_MAXINC && b < nik) {
+					u32 x = iv[a], y = ik[b];
+					if (x == y) mask[a >> 6] |= (u64)1 << (a & 63);
+					a += (x <= y);
+					b += (y <= x);
+				}
+			}
+		}
+		if (c == CLS_ZERO) {
+			n_out = 1;
+			inc_sz = 1;
+			for (int w = 0; w < B200_MAXINC / 64; w++) {
+				u64 m = mask[w];
+				while (m) { m &= m - 1; inc_sz++; }
+			}
+		} else
+			n_out = nplus;
+	}
+	S.cnt3[3 * (size_t)i + 0] = n_out;
+	S.cnt3[3 * (size_t)i + 1] = inc_sz;
+	S.cnt3[3 * (size_t)i + 2] = nplus;
+}
+
+B200_HD void set_bit_atomic(u32 *w, u32 i) { B200_ATOMIC_OR(&w[i >> 5], 1u << (i & 31)); }
+B200_HD void clr_bit_atomic(u32 *w, u32 i) { B200_ATOMIC_AND(&w[i >> 5], ~(1u << (i & 31))); }
+
+// neighbour k of the dying row v now neighbours `nw` instead (bslv_poly.c:628-632)
+B200_HD void rewire(const DevState &S, u32 k, u32 v, u32 nw)
+{
+	u32 off = S.adj_off[k], n = S.adj_len[k];
+	for (u32 q = 0; q < n; q++)
+		if (S.adj_pool[off + q] == v) { S.adj_pool[off + q] = nw; return; }
+}
+
+// K3b + K5 for visited entry i: append its new rows (edge vertices, bslv_poly.c:597-627, or the
+// copy of an on-plane vertex, :573-588), their incidence lists (:634-665), rewire the PLUS
+// neighbours (:628-633) and retire the row itself (:568, :697-705).
+B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
+{
+	u32 v = S.vis[i];
+	u8 c = S.cls[v];
+	if (!is_visited_class(c)) { S.dead_slots[i] = B200_NONE; return; }
+	CutCtl *ctl = S.ctl;
+	const u32 nrows = ctl->nrows, f = P.facet;
+	const size_t cap = S.cap_rows;
+	const int d = S.d;
+	u32 jrow = S.base3[3 * (size_t)i + 0];
+	u32 ipos = ctl->inc_used + S.base3[3 * (size_t)i + 1];
+	u32 ppos = S.base3[3 * (size_t)i + 2];
+	const u32 *iv = S.inc_pool + S.inc_off[v];
+	const u32 niv = S.inc_len[v];
+	const bool v_ideal = bit_test(S.ideal, v);
+	const u32 aoff = S.adj_off[v], an = S.adj_len[v];
+
+	if (c == CLS_ZERO) {
+		const u32 j = jrow, nw = nrows + j;
+		for (int t = 0; t < d; t++) S.coord[t * cap + nw] = S.coord[t * cap + v];
+		if (v_ideal) set_bit_atomic(S.ideal, nw);
+		set_bit_atomic(S.live, nw);
+		S.row_slot[nw] = ctl->slot_cnt + j;
+		S.new_parent[j] = S.row_slot[v];
+		S.deg[j] = 0;
+		S.new_padj_off[j] = ppos;
+		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
+		u32 np = 0;
+		for (u32 q = 0; q < an; q++) {
+			u32 k = S.adj_pool[aoff + q];
+			if (S.cls[k] != CLS_PLUS) continue;
+			S.padj[ppos + np++] = k;
+			rewire(S, k, v, nw);
+			const u32 *ik = S.inc_pool + S.inc_off[k];
+			const u32 nik = S.inc_len[k];
+			u32 a = 0, b = 0;
+			while (a < niv && a < B200_MAXINC && b < nik) {
+				u32 x = iv[a], y = ik[b];
+				if (x == y) mask[a >> 6] |= (u64)1 << (a & 63);
+				a += (x <= y);
+				b += (y <= x);
+			}
+		}
+		S.new_padj_len[j] = np;
+		u32 w = ipos;
+		for (u32 a = 0; a < niv && a < B200_MAXINC; a++)
+			if ((mask[a >> 6] >> (a & 63)) & 1) {
+				S.inc_pool[w++] = iv[a];
+				B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
+			}
+		S.inc_pool[w++] = f;                          // f is the largest facet id: list stays sorted
+		B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
+		S.inc_off[nw] = ipos;
+		S.inc_len[nw] = w - ipos;
+		B200_ATOMIC_ADD(&ctl->n_zero, 1u);
+	} else {
+		u32 np = 0;
+		for (u32 q = 0; q < an; q++) {
+			u32 k = S.adj_pool[aoff + q];
+			if (S.cls[k] != CLS_PLUS) continue;
+			const u32 j = jrow + np, nw = nrows + j;
+			const bool k_ideal = bit_test(S.ideal, k);
+			// A.3: base + mu*dir with (base,dir) chosen by the ideal flags (bslv_poly.c:600-623)
+			const u32 rb = k_ideal ? v : k;           // base
+			const u32 rd = k_ideal ? k : v;           // direction source
+			const bool both = k_ideal && v_ideal, none = !k_ideal && !v_ideal;
+			double base[B200_MAXD], dir[B200_MAXD];
+			for (int t = 0; t < d; t++) {
+				base[t] = S.coord[t * cap + rb];
+				double dv = S.coord[t * cap + rd];
+				if (both) dv = B200_SUB(dv, S.coord[t * cap + v]);
+				else if (none) dv = B200_SUB(dv, S.coord[t * cap + k]);
+				dir[t] = dv;
+			}
+			double hb = B200_MUL(P.h[0], base[0]), hd = B200_MUL(P.h[0], dir[0]);
+			for (int t = 1; t < d; t++) {
+				hb = B200_ADD(hb, B200_MUL(P.h[t], base[t]));
+				hd = B200_ADD(hd, B200_MUL(P.h[t], dir[t]));
+			}
+			double mu = B200_DIV(B200_SUB(both ? 0.0 : P.alpha, hb), hd);
+			for (int t = 0; t < d; t++) S.coord[t * cap + nw] = B200_ADD(base[t], B200_MUL(mu, dir[t]));
+			if (both) set_bit_atomic(S.ideal, nw);
+			set_bit_atomic(S.live, nw);
+			S.row_slot[nw] = ctl->slot_cnt + j;
+			S.new_parent[j] = B200_NONE;
+			S.deg[j] = 0;
+			S.new_padj_off[j] = ppos + np;
+			S.new_padj_len[j] = 1;
+			S.padj[ppos + np] = k;
+			rewire(S, k, v, nw);
+			// incidence {f} u (inc(k) n inc(v)), sorted (bslv_poly.c:625-626, 634-665)
+			const u32 *ik = S.inc_pool + S.inc_off[k];
+			const u32 nik = S.inc_len[k];
+			u32 a = 0, b = 0, w = ipos;
+			while (a < niv && b < nik) {
+				u32 x = iv[a], y = ik[b];
+				if (x == y) {
+					S.inc_pool[w++] = x;
+					B200_ATOMIC_ADD(&S.facet_cnt[x], 1u);
+				}
+				a += (x <= y);
+				b += (y <= x);
+			}
+			S.inc_pool[w++] = f;
+			B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
+			S.inc_off[nw] = ipos;
+			S.inc_len[nw] = w - ipos;
+			ipos = w;
+			np++;
+		}
+		B200_ATOMIC_ADD(&ctl->n_minus, 1u);
+	}
+	// retire v: its facets lose one vertex (bslv_poly.c:679-688, 697-705)
+	clr_bit_atomic(S.live, v);
+	for (u32 a = 0; a < niv; a++) B200_ATOMIC_SUB(&S.facet_cnt[iv[a]], 1u);
+	S.dead_slots[i] = S.row_slot[v];
+}
+
+// after all counts are final: a facet without live vertices dies (clean rule; the reference's
+// variant, bslv_poly.c:686-687/:705, leaves order-dependent ghosts -- SURVEY section 0)
+B200_HD void collect_dead_facets(const DevState &S, u32 i)
+{
+	if (S.dead_slots[i] == B200_NONE) return;
+	u32 v = S.vis[i];
+	const u32 *iv = S.inc_pool + S.inc_off[v];
+	for (u32 a = 0, n = S.inc_len[v]; a < n; a++) {
+		u32 fc = iv[a];
+		if (S.facet_cnt[fc] == 0 && B200_ATOMIC_EXCH(&S.facet_alive[fc], 0u) == 1u)
+			S.dead_facets[B200_ATOMIC_ADD(&S.ctl->n_dead_facets, 1u)] = fc;
+	}
+}
+
+// K4, list form: combinatorial adjacency of new rows a < b on the new facet
+// (edge_test, bslv_poly.c:467-512): |inc(a) n inc(b)| >= d-1 and no third new row contains it.
+B200_HD bool lists_adjacent(const DevState &S, u32 a, u32 b, u32 M)
+{
+	const u32 nrows = S.ctl->nrows;
+	const u32 ra = nrows + a, rb = nrows + b;
+	const u32 *ia = S.inc_pool + S.inc_off[ra], *ib = S.inc_pool + S.inc_off[rb];
+	const u32 na = S.inc_len[ra], nb = S.inc_len[rb];
+	if (S.d == 1) return true;
+	if (isect_count(ia, na, ib, nb) + 1 < (u32)S.d) return false;
+	for (u32 x = 0; x < M; x++) {
+		if (x == a || x == b) continue;
+		const u32 rx = nrows + x;
+		const u32 *ix = S.inc_pool + S.inc_off[rx];
+		const u32 nx = S.inc_len[rx];
+		// does inc(x) contain every element of inc(a) n inc(b)?  3-way sorted merge
+		u32 p = 0, q = 0, r = 0;
+		bool contains = true;
+		while (p < na && q < nb) {
+			u32 u = ia[p], w = ib[q];
+			if (u == w) {
+				while (r < nx && ix[r] < u) r++;
+				if (r == nx || ix[r] != u) { contains = false; break; }
+			}
+			p += (u <= w);
+			q += (w <= u);
+		}
+		if (contains) return false;
+	}
+	return true;
+}
+
+B200_HD void pair_test(const DevState &S, u64 pidx, u32 M)
+{
+	u32 a = (u32)(pidx / M), b = (u32)(pidx % M);
+	if (a >= b) return;
+	if (!lists_adjacent(S, a, b, M)) return;
+	u32 p = B200_ATOMIC_ADD(&S.ctl->n_pairs, 1u);
+	B200_ATOMIC_ADD(&S.deg[a], 1u);
+	B200_ATOMIC_ADD(&S.deg[b], 1u);
+	if (p < S.cap_pairs) { S.pair_a[p] = a; S.pair_b[p] = b; }
+}
+
+// adjacency build: PLUS neighbours first, then the new-facet neighbours in ascending row order
+B200_HD void adj_place(const DevState &S, u32 j)
+{
+	const u32 nw = S.ctl->nrows + j;
+	const u32 off = S.ctl->adj_used + S.adj_base[j];
+	const u32 np = S.new_padj_len[j];
+	S.adj_off[nw] = off;
+	S.adj_len[nw] = np + S.deg[j];
+	for (u32 q = 0; q < np; q++) S.adj_pool[off + q] = S.padj[S.new_padj_off[j] + q];
+	S.adj_fill[j] = np;
+}
+B200_HD void adj_pair_fill(const DevState &S, u32 p)
+{
+	const u32 nrows = S.ctl->nrows, a = S.pair_a[p], b = S.pair_b[p];
+	S.adj_pool[S.adj_off[nrows + a] + B200_ATOMIC_ADD(&S.adj_fill[a], 1u)] = nrows + b;
+	S.adj_pool[S.adj_off[nrows + b] + B200_ATOMIC_ADD(&S.adj_fill[b], 1u)] = nrows + a;
+}
+B200_HD void adj_sort(const DevState &S, u32 j)
+{
+	const u32 nw = S.ctl->nrows + j;
+	u32 *l = S.adj_pool + S.adj_off[nw];
+	const u32 lo = S.new_padj_len[j], n = S.adj_len[nw];
+	for (u32 x = lo + 1; x < n; x++) {
+		u32 key = l[x], y = x;
+		while (y > lo && l[y - 1] > key) { l[y] = l[y - 1]; y--; }
+		l[y] = key;
+	}
+}

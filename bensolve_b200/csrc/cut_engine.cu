@@ -1,0 +1,532 @@
+// CutEngine: device memory management and the stream-ordered kernel pipeline of one cut.
+//
+// Built two ways:
+//   * nvcc, sm_100a  -> the product (libbslv_poly_b200.so).  No CPU path: without a CUDA device
+//                       every entry point fails loudly.
+//   * g++ -DB200_EMULATE -> tests/_emul/libbslv_poly_emul.so, a host-side test double that runs
+//                       the same per-item stage bodies serially so that the data-layout logic
+//                       can be checked on a machine without a GPU.  Never shipped, never loaded
+//                       by the product.
+#include "cut_engine.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <stdexcept>
+
+#ifndef B200_EMULATE
+#include "cut_kernels.cuh"
+#else
+#include "cut_bodies.h"
+#endif
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+void b200_set_error(const std::string &msg) { g_last_error = msg; }
+const char *b200_get_error() { return g_last_error.c_str(); }
+
+[[noreturn]] static void fail(const std::string &msg)
+{
+	b200_set_error(msg);
+	throw std::runtime_error(msg);
+}
+
+// ------------------------------------------------------------------ memory layer
+#ifndef B200_EMULATE
+#define CK(call)                                                                                      \
+	do {                                                                                              \
+		cudaError_t e__ = (call);                                                                     \
+		if (e__ != cudaSuccess)                                                                       \
+			fail(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" +    \
+			     std::to_string(__LINE__) + " in " #call);                                            \
+	} while (0)
+
+static int g_device = -1;
+int b200_num_devices()
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+int b200_select_device(int dev)
+{
+	if (dev < 0 || dev >= b200_num_devices()) { b200_set_error("b200_set_device: no such CUDA device"); return 1; }
+	g_device = dev;
+	return cudaSetDevice(dev) == cudaSuccess ? 0 : 1;
+}
+static void bind_device()
+{
+	if (b200_num_devices() <= 0)
+		fail("bensolve_b200: no CUDA device visible -- the cut step has no CPU fallback");
+	if (g_device < 0) {
+		const char *lr = getenv("LOCAL_RANK");
+		int dev = lr ? atoi(lr) % b200_num_devices() : 0;
+		const char *ov = getenv("B200_DEVICE");
+		if (ov) dev = atoi(ov);
+		g_device = dev;
+	}
+	CK(cudaSetDevice(g_device));
+}
+#define STREAM ((cudaStream_t)stream_)
+static void *dalloc(size_t bytes)
+{
+	void *p = nullptr;
+	CK(cudaMalloc(&p, bytes ? bytes : 16));
+	CK(cudaMemset(p, 0, bytes ? bytes : 16));
+	return p;
+}
+static void dfree(void *p) { if (p) cudaFree(p); }
+static void d2d(void *dst, const void *src, size_t n) { if (n) CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToDevice)); }
+static void h2d(void *dst, const void *src, size_t n) { if (n) CK(cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice)); }
+static void d2h(void *dst, const void *src, size_t n) { if (n) CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost)); }
+#else
+int b200_num_devices() { return 0; }
+int b200_select_device(int) { return 0; }
+static void bind_device() {}
+static void *dalloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
+static void dfree(void *p) { free(p); }
+static void d2d(void *dst, const void *src, size_t n) { if (n) memcpy(dst, src, n); }
+static void h2d(void *dst, const void *src, size_t n) { if (n) memcpy(dst, src, n); }
+static void d2h(void *dst, const void *src, size_t n) { if (n) memcpy(dst, src, n); }
+#endif
+
+template <class T> static void regrow(T *&p, size_t new_n, size_t keep_n)
+{
+	T *q = (T *)dalloc(new_n * sizeof(T));
+	if (p && keep_n) d2d(q, p, keep_n * sizeof(T));
+	dfree(p);
+	p = q;
+}
+
+static u32 round_up(u64 x, u32 m) { return (u32)(((x + m - 1) / m) * m); }
+
+// ------------------------------------------------------------------ construction
+CutEngine::CutEngine(int dim) : d_(dim)
+{
+	if (dim < 1 || dim > B200_MAXD) fail("bensolve_b200: dimension " + std::to_string(dim) + " outside 1.." + std::to_string(B200_MAXD));
+	bind_device();
+	memset(&S_, 0, sizeof S_);
+	S_.d = dim;
+#ifndef B200_EMULATE
+	cudaStream_t st;
+	CK(cudaStreamCreate(&st));   // blocking stream: ordered against the default-stream memset/memcpy of the memory layer
+	stream_ = st;
+	for (int i = 0; i < 4; i++) { cudaEvent_t e; CK(cudaEventCreate(&e)); ev_[i] = e; }
+	CK(cudaMallocHost((void **)&pinned_hdr_, sizeof(CutCtl)));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, g_device));
+	num_sms_ = prop.multiProcessorCount;
+	if (prop.major < 10) fail("bensolve_b200: built for sm_100a (B200); device reports sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+#else
+	pinned_hdr_ = (CutCtl *)calloc(1, sizeof(CutCtl));
+#endif
+	S_.ctl = (CutCtl *)dalloc(sizeof(CutCtl));
+	S_.cur = (CutParams *)dalloc(sizeof(CutParams));
+	ensure_rows(4 * B200_TILE);
+	ensure_inc(1u << 16);
+	ensure_adj(1u << 16);
+	ensure_padj(1u << 14);
+	ensure_pairs(1u << 16);
+	ensure_facets(1024);
+}
+
+CutEngine::~CutEngine()
+{
+#ifndef B200_EMULATE
+	cudaSetDevice(g_device);
+	if (stream_) cudaStreamSynchronize(STREAM);
+#endif
+	void *ptrs[] = {S_.coord, S_.row_slot, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
+	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
+	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	for (void *p : ptrs) dfree(p);
+#ifndef B200_EMULATE
+	for (int i = 0; i < 4; i++) if (ev_[i]) cudaEventDestroy((cudaEvent_t)ev_[i]);
+	if (pinned_hdr_) cudaFreeHost(pinned_hdr_);
+	if (stream_) cudaStreamDestroy(STREAM);
+#else
+	free(pinned_hdr_);
+#endif
+}
+
+// ------------------------------------------------------------------ capacity
+void CutEngine::ensure_rows(u32 need)
+{
+	if (need <= S_.cap_rows) return;
+	const u32 old = S_.cap_rows, keep = hdr_.nrows;
+	const u32 cap = round_up(std::max<u64>(need, (u64)old * 2), B200_TILE);
+#ifndef B200_EMULATE
+	if (stream_) CK(cudaStreamSynchronize(STREAM));
+#endif
+	double *nc = (double *)dalloc((size_t)cap * d_ * sizeof(double));
+	for (int j = 0; j < d_ && S_.coord; j++) d2d(nc + (size_t)j * cap, S_.coord + (size_t)j * old, (size_t)keep * sizeof(double));
+	dfree(S_.coord);
+	S_.coord = nc;
+	regrow(S_.row_slot, cap, keep);
+	regrow(S_.live, cap / 32, old / 32);
+	regrow(S_.ideal, cap / 32, old / 32);
+	regrow(S_.inc_off, cap, keep);
+	regrow(S_.inc_len, cap, keep);
+	regrow(S_.adj_off, cap, keep);
+	regrow(S_.adj_len, cap, keep);
+	regrow(S_.cls, cap, 0);
+	regrow(S_.vis, cap, 0);
+	regrow(S_.cnt3, (size_t)3 * cap, 0);
+	regrow(S_.base3, (size_t)3 * cap, 0);
+	regrow(S_.new_padj_off, cap, 0);
+	regrow(S_.new_padj_len, cap, 0);
+	regrow(S_.new_parent, cap, 0);
+	regrow(S_.deg, cap, 0);
+	regrow(S_.adj_fill, cap, 0);
+	regrow(S_.adj_base, cap, 0);
+	regrow(S_.dead_slots, cap, 0);
+	S_.cap_tiles = cap / B200_TILE;
+	regrow(S_.tile_cnt, S_.cap_tiles, 0);
+	regrow(S_.tile_base, S_.cap_tiles, 0);
+	S_.cap_rows = cap;
+}
+void CutEngine::ensure_inc(u32 need)
+{
+	if (need <= S_.cap_inc) return;
+	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_inc * 2);
+	regrow(S_.inc_pool, cap, hdr_.inc_used);
+	S_.cap_inc = cap;
+}
+void CutEngine::ensure_adj(u32 need)
+{
+	if (need <= S_.cap_adj) return;
+	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_adj * 2);
+	regrow(S_.adj_pool, cap, hdr_.adj_used);
+	S_.cap_adj = cap;
+}
+void CutEngine::ensure_padj(u32 need)
+{
+	if (need <= S_.cap_padj) return;
+	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_padj * 2);
+	regrow(S_.padj, cap, 0);
+	S_.cap_padj = cap;
+}
+void CutEngine::ensure_pairs(u32 need)
+{
+	if (need <= S_.cap_pairs) return;
+	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_pairs * 2);
+	regrow(S_.pair_a, cap, 0);
+	regrow(S_.pair_b, cap, 0);
+	S_.cap_pairs = cap;
+}
+void CutEngine::ensure_facets(u32 need)
+{
+	if (need <= S_.cap_facets) return;
+	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_facets * 2);
+	regrow(S_.facet_cnt, cap, S_.cap_facets);
+	regrow(S_.facet_alive, cap, S_.cap_facets);
+	regrow(S_.dead_facets, cap, 0);
+	S_.cap_facets = cap;
+}
+
+// ------------------------------------------------------------------ initial state
+void CutEngine::upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
+                               const std::vector<std::vector<u32>> &inc, const std::vector<std::vector<u32>> &adj,
+                               u32 n_facets, const std::vector<u32> &facet_counts)
+{
+	ensure_rows(n + B200_TILE);
+	ensure_facets(n_facets + 64);
+	std::vector<double> soa((size_t)n);
+	for (int j = 0; j < d_; j++) {
+		for (u32 r = 0; r < n; r++) soa[r] = coords_aos[(size_t)r * d_ + j];
+		h2d(S_.coord + (size_t)j * S_.cap_rows, soa.data(), n * sizeof(double));
+	}
+	std::vector<u32> slot(n), live((n + 31) / 32, 0), idl((n + 31) / 32, 0), ioff(n), ilen(n), aoff(n), alen(n), ipool, apool;
+	for (u32 r = 0; r < n; r++) {
+		slot[r] = r;
+		live[r >> 5] |= 1u << (r & 31);
+		if (ideal[r]) idl[r >> 5] |= 1u << (r & 31);
+		std::vector<u32> l = inc[r];
+		std::sort(l.begin(), l.end());
+		ioff[r] = (u32)ipool.size();
+		ilen[r] = (u32)l.size();
+		ipool.insert(ipool.end(), l.begin(), l.end());
+		aoff[r] = (u32)apool.size();
+		alen[r] = (u32)adj[r].size();
+		apool.insert(apool.end(), adj[r].begin(), adj[r].end());
+	}
+	ensure_inc((u32)ipool.size() + (1u << 16));
+	ensure_adj((u32)apool.size() + (1u << 16));
+	h2d(S_.row_slot, slot.data(), n * 4);
+	h2d(S_.live, live.data(), live.size() * 4);
+	h2d(S_.ideal, idl.data(), idl.size() * 4);
+	h2d(S_.inc_off, ioff.data(), n * 4);
+	h2d(S_.inc_len, ilen.data(), n * 4);
+	h2d(S_.adj_off, aoff.data(), n * 4);
+	h2d(S_.adj_len, alen.data(), n * 4);
+	h2d(S_.inc_pool, ipool.data(), ipool.size() * 4);
+	h2d(S_.adj_pool, apool.data(), apool.size() * 4);
+	std::vector<u32> fc(facet_counts), fa(n_facets, 0);
+	fc.resize(n_facets, 0);
+	for (u32 f = 0; f < n_facets; f++) fa[f] = fc[f] > 0;
+	h2d(S_.facet_cnt, fc.data(), n_facets * 4);
+	h2d(S_.facet_alive, fa.data(), n_facets * 4);
+	memset(&hdr_, 0, sizeof hdr_);
+	hdr_.nrows = hdr_.slot_cnt = hdr_.n_live = n;
+	hdr_.inc_used = (u32)ipool.size();
+	hdr_.adj_used = (u32)apool.size();
+	h2d(S_.ctl, &hdr_, sizeof hdr_);
+}
+
+// ------------------------------------------------------------------ the pipeline
+#ifndef B200_EMULATE
+template <int D> static void launch_classify(const DevState &S, int grid, cudaStream_t st) { k_classify<D><<<grid, K_THREADS, 0, st>>>(S); }
+
+void CutEngine::launch_part_a(const CutParams &P)
+{
+	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
+	const int gmap = num_sms_ * 4;
+	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
+	k_begin<<<1, 32, 0, STREAM>>>(S_, P);
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
+	switch (d_) {
+	case 2: launch_classify<2>(S_, gcls, STREAM); break;
+	case 3: launch_classify<3>(S_, gcls, STREAM); break;
+	case 4: launch_classify<4>(S_, gcls, STREAM); break;
+	case 5: launch_classify<5>(S_, gcls, STREAM); break;
+	case 6: launch_classify<6>(S_, gcls, STREAM); break;
+	case 7: launch_classify<7>(S_, gcls, STREAM); break;
+	case 8: launch_classify<8>(S_, gcls, STREAM); break;
+	default: launch_classify<0>(S_, gcls, STREAM); break;
+	}
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
+	k_scan_tiles<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
+	k_scatter<<<gcls, K_THREADS, 0, STREAM>>>(S_);
+	k_zp_closure<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
+	k_count<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	k_scan3_plan<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
+	k_emit<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	k_dead_facets<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	stats_.kernel_launches += 9;
+}
+
+void CutEngine::launch_part_b(bool rerun)
+{
+	const int gmap = num_sms_ * 4;
+	if (rerun) { k_pairs_reset<<<gmap, K_THREADS, 0, STREAM>>>(S_); stats_.kernel_launches++; }
+	k_pairs<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_);
+	k_adj_scan<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
+	k_adj_place<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	k_adj_pair_fill<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	k_adj_sort<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	k_finish<<<1, 32, 0, STREAM>>>(S_);
+	stats_.kernel_launches += 6;
+	CK(cudaGetLastError());
+}
+
+void CutEngine::read_header()
+{
+	CK(cudaMemcpyAsync(pinned_hdr_, S_.ctl, sizeof(CutCtl), cudaMemcpyDeviceToHost, STREAM));
+	CK(cudaStreamSynchronize(STREAM));
+	hdr_ = *pinned_hdr_;
+}
+#else // ---- host-side test double: same stage bodies, run serially
+void CutEngine::launch_part_a(const CutParams &P)
+{
+	DevState &S = S_;
+	CutCtl *c = S.ctl;
+	*S.cur = P;
+	c->status = 0;
+	c->n_strict = 0;
+	c->min_strict_row = c->min_strict_slot = B200_NONE;
+	c->n_zp = c->n_zp_projected = c->n_vis = c->n_new = c->inc_new = c->padj_new = 0;
+	c->n_minus = c->n_zero = c->n_pairs = c->adj_new = c->n_dead_facets = c->n_live_scanned = 0;
+	S.facet_cnt[P.facet] = 0;
+	S.facet_alive[P.facet] = 1;
+	for (u32 r = 0; r < c->nrows; r++) {
+		bool strict, zp;
+		u8 cl = classify_row(S, P, r, strict, zp);
+		S.cls[r] = cl;
+		if (cl == CLS_DEAD) continue;
+		c->n_live_scanned++;
+		if (strict) { c->n_strict++; if (r < c->min_strict_row) c->min_strict_row = r; }
+		if (zp) c->n_zp++;
+		if (cl != CLS_PLUS) S.vis[c->n_vis++] = r;
+	}
+	if (c->n_strict == 0) { c->status |= ST_REDUNDANT; S.facet_alive[P.facet] = 0; return; }
+	c->min_strict_slot = S.row_slot[c->min_strict_row];
+	if (c->n_zp) {
+		bool changed;
+		do {
+			changed = false;
+			for (u32 i = 0; i < c->n_vis; i++) changed |= zp_activate(S, P, i);
+		} while (changed);
+	}
+	for (u32 i = 0; i < c->n_vis; i++) count_outputs(S, i);
+	if (c->status & ST_ERR_DEGENERATE) return;
+	u32 carry[3] = {0, 0, 0};
+	for (u32 i = 0; i < c->n_vis; i++)
+		for (int k = 0; k < 3; k++) { S.base3[3 * (size_t)i + k] = carry[k]; carry[k] += S.cnt3[3 * (size_t)i + k]; }
+	c->n_new = carry[0]; c->inc_new = carry[1]; c->padj_new = carry[2];
+	if ((u64)c->nrows + carry[0] > S.cap_rows) c->status |= ST_OVF_ROWS;
+	if ((u64)c->inc_used + carry[1] > S.cap_inc) c->status |= ST_OVF_INC;
+	if (carry[2] > S.cap_padj) c->status |= ST_OVF_PADJ;
+	if (c->status & ST_OVF_A) return;
+	for (u32 i = 0; i < c->n_vis; i++) emit_outputs(S, P, i);
+	for (u32 i = 0; i < c->n_vis; i++) collect_dead_facets(S, i);
+}
+void CutEngine::launch_part_b(bool rerun)
+{
+	DevState &S = S_;
+	CutCtl *c = S.ctl;
+	if (c->status & (ST_REDUNDANT | ST_OVF_A | ST_ERR_DEGENERATE)) return;
+	if (rerun) { c->n_pairs = 0; c->status &= ~(u32)ST_OVF_B; for (u32 j = 0; j < c->n_new; j++) S.deg[j] = 0; }
+	const u32 M = c->n_new;
+	for (u64 p = 0; p < (u64)M * M; p++) pair_test(S, p, M);
+	if (c->n_pairs > S.cap_pairs) { c->status |= ST_OVF_PAIRS; return; }
+	u32 carry = 0;
+	for (u32 j = 0; j < M; j++) { S.adj_base[j] = carry; carry += S.new_padj_len[j] + S.deg[j]; }
+	c->adj_new = carry;
+	if ((u64)c->adj_used + carry > S.cap_adj) { c->status |= ST_OVF_ADJ; return; }
+	for (u32 j = 0; j < M; j++) adj_place(S, j);
+	for (u32 p = 0; p < c->n_pairs; p++) adj_pair_fill(S, p);
+	for (u32 j = 0; j < M; j++) adj_sort(S, j);
+	c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
+	c->nrows += c->n_new;
+	c->slot_cnt += c->n_new;
+	c->inc_used += c->inc_new;
+	c->adj_used += c->adj_new;
+}
+void CutEngine::read_header() { hdr_ = *S_.ctl; }
+#endif
+
+void CutEngine::cut(const CutParams &P, CutDelta &out)
+{
+#ifndef B200_EMULATE
+	CK(cudaSetDevice(g_device));
+#endif
+	out = CutDelta();
+	ensure_facets(P.facet + 1);
+	// head-room for the appends; exact needs are checked on the device before any mutation
+	ensure_rows(hdr_.nrows + std::max<u32>(4096, hdr_.n_live / 2 + 64));
+	const u32 n_live_before = hdr_.n_live, nrows_before = hdr_.nrows;
+#ifndef B200_EMULATE
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[2], STREAM));
+#endif
+	launch_part_a(P);
+	launch_part_b(false);
+	read_header();
+	for (int guard = 0; hdr_.status & (ST_OVF_A | ST_OVF_B); guard++) {
+		if (guard > 8) fail("bensolve_b200: capacity negotiation did not converge");
+		if (hdr_.status & ST_OVF_A) {
+			if (hdr_.status & ST_OVF_ROWS) ensure_rows(hdr_.nrows + hdr_.n_new + B200_TILE);
+			if (hdr_.status & ST_OVF_INC) ensure_inc(hdr_.inc_used + hdr_.inc_new);
+			if (hdr_.status & ST_OVF_PADJ) ensure_padj(hdr_.padj_new);
+			launch_part_a(P);
+			launch_part_b(false);
+		} else {
+			if (hdr_.status & ST_OVF_PAIRS) ensure_pairs(hdr_.n_pairs);
+			if (hdr_.status & ST_OVF_ADJ) ensure_adj(hdr_.adj_used + hdr_.adj_new);
+			launch_part_b(true);
+		}
+		read_header();
+	}
+#ifndef B200_EMULATE
+	if (flags_ & 1) {
+		CK(cudaEventRecord((cudaEvent_t)ev_[3], STREAM));
+		CK(cudaEventSynchronize((cudaEvent_t)ev_[3]));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[0], (cudaEvent_t)ev_[1]));
+		stats_.classify_ms += ms;
+		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[2], (cudaEvent_t)ev_[3]));
+		stats_.cut_ms += ms;
+	}
+#endif
+	if (hdr_.status & ST_ERR_DEGENERATE)
+		fail("bensolve_b200: a vertex on the cutting hyperplane lies on more than " + std::to_string(B200_MAXINC) + " facets");
+	stats_.vertex_evals += hdr_.n_live_scanned;
+	stats_.rows_scanned += nrows_before;
+	if (hdr_.status & ST_REDUNDANT) {
+		out.redundant = 1;
+		stats_.redundant++;
+		stats_.algorithmic_bytes += (u64)n_live_before * (8 * d_ + 1);
+		return;
+	}
+	// ---- delta download (new rows are [first_row, first_row + n_new))
+	const u32 n_new = hdr_.n_new, first_row = hdr_.nrows - n_new;
+	out.trigger_slot = hdr_.min_strict_slot;
+	out.n_new = n_new;
+	out.first_new_slot = hdr_.slot_cnt - n_new;
+	out.coords.resize((size_t)n_new * d_);
+	out.ideal.assign(n_new, 0);
+	out.parent_slot.resize(n_new);
+	if (n_new) {
+		std::vector<double> col(n_new);
+		for (int j = 0; j < d_; j++) {
+			d2h(col.data(), S_.coord + (size_t)j * S_.cap_rows + first_row, (size_t)n_new * sizeof(double));
+			for (u32 r = 0; r < n_new; r++) out.coords[(size_t)r * d_ + j] = col[r];
+		}
+		const u32 w0 = first_row >> 5, w1 = (first_row + n_new - 1) >> 5;
+		std::vector<u32> words(w1 - w0 + 1);
+		d2h(words.data(), S_.ideal + w0, words.size() * 4);
+		for (u32 r = 0; r < n_new; r++) {
+			u32 g = first_row + r;
+			out.ideal[r] = (words[(g >> 5) - w0] >> (g & 31)) & 1u;
+		}
+		d2h(out.parent_slot.data(), S_.new_parent, (size_t)n_new * 4);
+	}
+	std::vector<u32> ds(hdr_.n_vis);
+	d2h(ds.data(), S_.dead_slots, (size_t)hdr_.n_vis * 4);
+	for (u32 s : ds) if (s != B200_NONE) out.dead_slots.push_back(s);
+	out.dead_facets.resize(hdr_.n_dead_facets);
+	d2h(out.dead_facets.data(), S_.dead_facets, (size_t)hdr_.n_dead_facets * 4);
+	// ---- statistics (SURVEY 8(d) algorithmic bytes)
+	const u64 N = n_live_before, nm = hdr_.n_minus, nz = hdr_.n_zero, E = n_new - nz, M = n_new;
+	const u64 W = (P.facet + 64) / 64, A = hdr_.n_pairs;
+	stats_.cuts++;
+	stats_.minus += nm;
+	stats_.zero += nz;
+	stats_.zero_plus_projected += hdr_.n_zp_projected;
+	stats_.edge_vertices += E;
+	stats_.copies += nz;
+	stats_.pair_tests += M * (M - (M ? 1 : 0)) / 2;
+	stats_.new_adjacent_pairs += A;
+	stats_.algorithmic_bytes += N * (8 * d_ + 1) + N + 4 * (nm + nz) + E * (24 * d_ + 24 * W) + nz * (16 * d_ + 16 * W) + 8 * M * W + 8 * A;
+	maybe_compact();
+}
+
+void CutEngine::maybe_compact() {}
+void CutEngine::compact() {}
+
+void CutEngine::reupload_coords(const double *data_aos, size_t n_slots)
+{
+	std::vector<u32> slot(hdr_.nrows);
+	d2h(slot.data(), S_.row_slot, (size_t)hdr_.nrows * 4);
+	std::vector<double> col(hdr_.nrows);
+	for (int j = 0; j < d_; j++) {
+		d2h(col.data(), S_.coord + (size_t)j * S_.cap_rows, (size_t)hdr_.nrows * sizeof(double));
+		for (u32 r = 0; r < hdr_.nrows; r++)
+			if (slot[r] < n_slots) col[r] = data_aos[(size_t)slot[r] * d_ + j];
+		h2d(S_.coord + (size_t)j * S_.cap_rows, col.data(), (size_t)hdr_.nrows * sizeof(double));
+	}
+}
+
+void CutEngine::download_structure(HostStructure &o)
+{
+#ifndef B200_EMULATE
+	CK(cudaSetDevice(g_device));
+	CK(cudaStreamSynchronize(STREAM));
+#endif
+	const u32 n = hdr_.nrows;
+	o.nrows = n;
+	o.row_slot.resize(n); o.inc_off.resize(n); o.inc_len.resize(n); o.adj_off.resize(n); o.adj_len.resize(n);
+	o.live_words.resize((n + 31) / 32);
+	o.inc_pool.resize(hdr_.inc_used);
+	o.adj_pool.resize(hdr_.adj_used);
+	d2h(o.row_slot.data(), S_.row_slot, (size_t)n * 4);
+	d2h(o.live_words.data(), S_.live, o.live_words.size() * 4);
+	d2h(o.inc_off.data(), S_.inc_off, (size_t)n * 4);
+	d2h(o.inc_len.data(), S_.inc_len, (size_t)n * 4);
+	d2h(o.adj_off.data(), S_.adj_off, (size_t)n * 4);
+	d2h(o.adj_len.data(), S_.adj_len, (size_t)n * 4);
+	d2h(o.inc_pool.data(), S_.inc_pool, (size_t)hdr_.inc_used * 4);
+	d2h(o.adj_pool.data(), S_.adj_pool, (size_t)hdr_.adj_used * 4);
+}

@@ -1,0 +1,86 @@
+// Host-side owner of one polytope's device state and of the per-cut kernel pipeline.
+#pragma once
+#include <stddef.h>
+
+#include <string>
+#include <vector>
+
+#include "cut_types.h"
+
+struct CutDelta {             // what one cut changed, in host slot numbers (SURVEY 8(b) coherence rule)
+	int redundant = 0;        // 1 => nothing changed, poly__add_vrtx returns EXIT_FAILURE
+	u32 trigger_slot = 0;     // lowest strictly violated slot: the reference's args->idx (bslv_poly.c:121-131)
+	u32 first_new_slot = 0;
+	u32 n_new = 0;
+	std::vector<double> coords;     // AoS [n_new][d]
+	std::vector<u8> ideal;          // [n_new]
+	std::vector<u32> parent_slot;   // [n_new] slot copied from (ZERO copies) or B200_NONE (edge vertices)
+	std::vector<u32> dead_slots;
+	std::vector<u32> dead_facets;
+};
+
+struct HostStructure {        // snapshot for lazy materialisation of the host poly_lists
+	u32 nrows = 0;
+	std::vector<u32> row_slot, live_words, inc_off, inc_len, adj_off, adj_len, inc_pool, adj_pool;
+};
+
+struct EngineStats {
+	u64 cuts = 0, redundant = 0, vertex_evals = 0, rows_scanned = 0;
+	u64 minus = 0, zero = 0, zero_plus_projected = 0, edge_vertices = 0, copies = 0;
+	u64 pair_tests = 0, new_adjacent_pairs = 0, algorithmic_bytes = 0, kernel_launches = 0, compactions = 0;
+	double classify_ms = 0, cut_ms = 0;
+};
+
+class CutEngine {
+public:
+	explicit CutEngine(int dim);
+	~CutEngine();
+	CutEngine(const CutEngine &) = delete;
+	CutEngine &operator=(const CutEngine &) = delete;
+
+	int dim() const { return d_; }
+	// Load the start polyhedron (poly__poly_initialise, bslv_poly.c:711-787): n rows = slots 0..n-1.
+	void upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
+	                    const std::vector<std::vector<u32>> &inc, const std::vector<std::vector<u32>> &adj,
+	                    u32 n_facets, const std::vector<u32> &facet_counts);
+	// One halfspace; fills `out`.  Throws std::runtime_error on CUDA errors.
+	void cut(const CutParams &P, CutDelta &out);
+	// Overwrite device coordinates of the given live slots from the host mirror (after the caller
+	// edited primal.data in place, bslv_algs.c:193-273).
+	void reupload_coords(const double *data_aos, size_t n_slots);
+	void download_structure(HostStructure &out);
+	void compact();                      // drop dead rows, repack pools
+	void set_flags(unsigned f) { flags_ = f; }
+	const EngineStats &stats() const { return stats_; }
+	u32 live_vertices() const { return hdr_.n_live; }
+	u32 slots() const { return hdr_.slot_cnt; }
+	u32 rows() const { return hdr_.nrows; }
+
+private:
+	void ensure_rows(u32 need);
+	void ensure_inc(u32 need);
+	void ensure_adj(u32 need);
+	void ensure_padj(u32 need);
+	void ensure_pairs(u32 need);
+	void ensure_facets(u32 need);
+	void launch_part_a(const CutParams &P);
+	void launch_part_b(bool rerun);
+	void read_header();
+	void maybe_compact();
+
+	int d_;
+	unsigned flags_ = 0;
+	DevState S_{};
+	CutCtl hdr_{};            // host copy of the control block as of the last sync
+	CutCtl *pinned_hdr_ = nullptr;
+	void *stream_ = nullptr;
+	void *ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+	int num_sms_ = 148;
+	EngineStats stats_;
+};
+
+// library-wide helpers (cut_engine.cu)
+void b200_set_error(const std::string &msg);
+const char *b200_get_error();
+int b200_select_device(int dev);
+int b200_num_devices();

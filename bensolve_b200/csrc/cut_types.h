@@ -1,0 +1,104 @@
+// Device-side data layout of the cut engine (see DESIGN.md "Data layout in HBM").
+//
+// One CutEngine instance mirrors one reference `poly_args` (bslv_poly.h:71-82).  The primal
+// polytope lives in HBM as
+//   * coord    : SoA FP64, coord[j*cap_rows + r]   (coalesced along the vertex axis for K1)
+//   * live/ideal : 32-bit-word bitsets over device rows
+//   * row_slot : device row -> host slot number (rows are compacted, host slots never are)
+//   * inc_pool : per-row SORTED facet-id lists (immutable after creation; bslv_poly.c keeps them
+//                as unsorted malloc'd size_t lists, bslv_poly.h:49-53)
+//   * adj_pool : per-row neighbour rows (entries are rewritten in place when a neighbour is cut off)
+//   * facet_cnt: live vertices per facet (replaces dual.incidence[f].cnt tests, bslv_poly.c:686,698)
+#pragma once
+#include <stdint.h>
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;
+
+#define B200_MAXD 16        // highest supported dimension q of the image space
+#define B200_MAXINC 256     // longest incidence list a ZERO vertex may have (degenerate inputs)
+#define B200_NONE 0xFFFFFFFFu
+
+#if defined(__CUDACC__) && !defined(B200_EMULATE)
+#define B200_HD __host__ __device__ __forceinline__
+#else
+#define B200_HD inline
+#endif
+
+// vertex classes with respect to the current halfspace
+enum : u8 { CLS_PLUS = 0, CLS_ZP = 1, CLS_ZERO = 2, CLS_MINUS = 3, CLS_DEAD = 4 };
+
+// status bits of a cut
+enum : u32 {
+	ST_REDUNDANT = 1u,      // no vertex strictly violates: poly__add_vrtx returns EXIT_FAILURE
+	ST_OVF_ROWS = 2u,       // row capacity too small          (detected before any mutation)
+	ST_OVF_INC = 4u,        // incidence pool too small        (idem)
+	ST_OVF_PADJ = 8u,       // PLUS-neighbour scratch too small (idem)
+	ST_OVF_PAIRS = 16u,     // K4 pair buffer too small        (K4 is re-runnable)
+	ST_OVF_ADJ = 32u,       // adjacency pool too small        (adjacency build is re-runnable)
+	ST_ERR_DEGENERATE = 64u // an incidence list exceeds B200_MAXINC
+};
+#define ST_OVF_A (ST_OVF_ROWS | ST_OVF_INC | ST_OVF_PADJ)
+#define ST_OVF_B (ST_OVF_PAIRS | ST_OVF_ADJ)
+
+// The halfspace of the current cut, h.x >= alpha (alpha replaced by 0 for ideal vertices), with
+// the reference's three thresholds pre-added in FP64 exactly as bslv_poly.c:126,573,596,666 does.
+struct CutParams {
+	double h[B200_MAXD];
+	double alpha;
+	double hi[2];   // thr + 1e-9        index 1 = ideal vertex (thr = 0)
+	double mid[2];  // thr + 1e-2*1e-9
+	double lo[2];   // thr - 1e-9
+	double hh;      // sum h_j^2, left to right (bslv_poly.c:668-670)
+	u32 facet;      // id of the new facet = dual slot of this halfspace
+	u32 pad;
+};
+
+// Counters shared by the kernels of one cut; the host reads it back once per cut.
+struct CutCtl {
+	// persistent
+	u32 nrows;        // device rows in use (live + dead, before this cut's appends)
+	u32 slot_cnt;     // host-visible primal.cnt
+	u32 n_live;       // live vertices
+	u32 inc_used, adj_used;
+	// per cut
+	u32 status;
+	u32 n_strict;       // vertices with h.x < thr - eps (trigger, bslv_poly.c:126)
+	u32 min_strict_row; // lowest such row (its slot is what the reference leaves in args->idx)
+	u32 n_zp;           // ZERO+ candidates seen by K1
+	u32 n_zp_projected;
+	u32 n_vis;          // non-PLUS rows (compact list length)
+	u32 n_new, inc_new, padj_new;
+	u32 n_minus, n_zero;
+	u32 n_pairs;        // adjacent pairs found by K4
+	u32 adj_new;
+	u32 n_dead_facets;
+	u32 n_live_scanned; // live rows classified by K1
+	u32 min_strict_slot;
+	u32 reserved[3];
+};
+
+struct DevState {
+	int d;
+	u32 cap_rows, cap_inc, cap_adj, cap_facets, cap_padj, cap_pairs, cap_tiles;
+	double *coord;
+	u32 *row_slot, *live, *ideal;
+	u32 *inc_off, *inc_len, *adj_off, *adj_len;
+	u32 *inc_pool, *adj_pool;
+	u32 *facet_cnt, *facet_alive;
+	u8 *cls;
+	// per-cut scratch
+	u32 *tile_cnt, *tile_base;
+	u32 *vis;            // [cap_rows] non-PLUS rows, ascending
+	u32 *cnt3, *base3;   // [3*cap_rows] (new rows, incidence entries, PLUS neighbours) per visited row
+	u32 *padj;           // [cap_padj] PLUS neighbours of the new rows
+	u32 *new_padj_off, *new_padj_len, *new_parent, *deg, *adj_fill, *adj_base; // [cap_rows], by new-row index
+	u32 *pair_a, *pair_b; // [cap_pairs]
+	u32 *dead_slots;     // [cap_rows] by visited index
+	u32 *dead_facets;    // [cap_facets]
+	CutCtl *ctl;
+	CutParams *cur;
+};
+
+#define B200_TILE 2048u  // rows per K1/K2 tile

