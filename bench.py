@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- cut throughput of the B200 polyhedral cut engine (BASELINE.json metric).
+
+Workload (config 5 of BASELINE.json, the largest single-GPU configuration): pure H->V enumeration
+of a random polytope in R^6 from N halfspaces tangent to the unit ball (synthetic, fixed seed).
+One *step* = the whole cut sequence: poly__initialise, d queued halfspaces, poly__intl_apprx, then
+one cut per remaining halfspace, ending with a coherent host mirror.
+
+    value : cuts/s with the halfspaces already resident in HBM (b200_poly_add_batch_device)
+    e2e   : cuts/s through the reference-facing call, one poly__add_vrtx per halfspace with HOST
+            buffers; every call returns with primal.data/used/ideal/cnt current on the host
+    roofline : K1 (classify), the dominant kernel, timed alone with CUDA events on its own stream
+               with an L2 flush before each launch, against MEASURED_PEAKS.json hbm_gbs
+    cpu_baseline : the unmodified reference engine (oracle/_ref) on a bounded prefix of the trace
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libref_poly.so, built
+from the unmodified bslv_poly.c; falls back to the restatement oracle/libpoly_oracle.so) on the
+same bounded prefix.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+from bensolve_b200 import capi, polytopes as P  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dim", type=int, default=6)
+    ap.add_argument("--halfspaces", type=int, default=5000)
+    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--ref-prefix", type=int, default=300, help="halfspaces of the trace the CPU reference is timed on")
+    ap.add_argument("--classify-iters", type=int, default=30)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- CPU reference arm
+def load_cpu_engine():
+    from bensolve_b200 import build
+    if not (os.path.exists(capi.REF_SO) or os.path.exists(capi.ORACLE_SO)):
+        build.build_oracle()
+    if os.path.exists(capi.REF_SO):
+        return capi.load_lib(capi.REF_SO), "reference"
+    return capi.load_lib(capi.ORACLE_SO), "port"
+
+
+def cpu_step(lib, trace, prefix):
+    e = capi.PolyEngine(lib, trace.dim)
+    t0 = time.perf_counter()
+    rcs = P.replay(e, trace, upto=prefix)
+    dt = time.perf_counter() - t0
+    cuts = len(rcs) - sum(rcs)
+    live = int(np.unpackbits(np.ctypeslib.as_array(e.args.primal.used, shape=((e.args.primal.cnt + 63) // 64,)).view(np.uint8)).sum())
+    e.kill()
+    return cuts, dt, live
+
+
+def run_reference(a, trace):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, kind = load_cpu_engine()
+    prefix = min(a.ref_prefix, len(trace))
+    for _ in range(a.warmup):
+        cpu_step(lib, trace, prefix)
+    cuts = 0
+    t = 0.0
+    live = 0
+    for _ in range(a.steps):
+        c, dt, live = cpu_step(lib, trace, prefix)
+        cuts += c
+        t += dt
+    v = cuts / t
+    line = {
+        "impl": "reference", "metric": "halfspace cuts/sec", "value": v, "unit": "cuts/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"pure H->V enumeration, random tangent polytope in R^{a.dim}, {a.halfspaces} halfspaces, seed {a.seed}",
+                   "sample": f"first {prefix} of {a.halfspaces} halfspaces ({live} live vertices at the end of the sample)"},
+        "cpu_baseline": {"value": v, "unit": "cuts/s", "cores": 1, "kind": kind,
+                         "sample": f"first {prefix} of {a.halfspaces} halfspaces, single thread (the reference engine is single-threaded; {os.cpu_count()} host cores present)"},
+        "e2e": {"value": v, "unit": "cuts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- B200 arm
+def measured_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_b200(a, trace):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.load_product()
+    lib.b200_set_device.argtypes = [__import__("ctypes").c_int]
+    lib.b200_set_device(local)
+    d, n = trace.dim, len(trace)
+    dev = torch.device("cuda", local)
+    d_vals = torch.from_numpy(np.ascontiguousarray(trace.vals[d:])).to(dev)      # inputs resident in HBM
+    torch.cuda.synchronize()
+    sizes = {"rows": 0, "inc": 0, "adj": 0}
+
+    def fresh_engine():
+        e = capi.PolyEngine(lib, d)
+        if sizes["rows"]:
+            e.reserve(sizes["rows"], sizes["inc"], sizes["adj"])
+        for i in range(d):
+            e.add(trace.vals[i], 0)
+        assert e.init_approx() == 0
+        return e
+
+    def step_value(keep=False):
+        e = fresh_engine()
+        rcs = e.add_batch_device(d_vals.data_ptr(), 0, n - d)
+        st = e.stats()
+        if keep:
+            return e, st, rcs
+        e.kill()
+        return None, st, rcs
+
+    def step_e2e():
+        e = fresh_engine()
+        rcs = [e.add(trace.vals[i], 0) for i in range(d, n)]
+        st = e.stats()
+        e.kill()
+        return st, rcs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also reveals the capacities to reserve, so the timed steps do not re-allocate)
+    for w in range(max(a.warmup, 1)):
+        _, st, _ = step_value()
+        sizes.update(rows=int(st["slots"] * 1.25) + 65536, inc=int(st["slots"] * (d + 2)) + (1 << 20), adj=int(st["slots"] * (d + 2)) + (1 << 20))
+        if w < a.warmup - 1 or a.warmup == 0:
+            continue
+    for _ in range(max(a.warmup - 1, 0)):
+        step_e2e()
+
+    with ClockSampler(local) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        cuts_v = launches_v = evals_v = 0
+        for k in range(a.steps):
+            eng, st, rcs = step_value(keep=(k == a.steps - 1))
+            cuts_v += st["cuts"]; launches_v += st["kernel_launches"]; evals_v += st["vertex_evals"]
+        barrier()
+        t_value = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        cuts_e = launches_e = 0
+        d2h = 0
+        for k in range(a.steps):
+            st_e, _ = step_e2e()
+            cuts_e += st_e["cuts"]; launches_e += st_e["kernel_launches"]
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        # roofline of the dominant kernel on the final polytope of the last value step
+        st_final = eng.stats()
+        hp = np.append(trace.vals[n // 2] * 1.0000001, -1.0)
+        ms_flush = eng.classify_bench(hp, a.classify_iters, True)
+        ms_l2 = eng.classify_bench(hp, a.classify_iters, False)
+    clocks = clk.summary()
+
+    # max over ranks (each rank holds a replica at N>1 -- see DESIGN.md, multi-GPU)
+    if dist is not None:
+        tt = torch.tensor([t_value, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_value, t_e2e = float(tt[0]), float(tt[1])
+    eng.kill()
+
+    peak, peak_src = measured_peak()
+    n_live = st_final["live_vertices"]
+    alg_bytes = n_live * (8 * d + 1)
+    achieved = alg_bytes / (ms_flush * 1e-3) / 1e9
+    per_step = st_final
+    # bytes crossing PCIe per e2e step: d doubles in per call; the packed delta back per call
+    h2d = (n - d) * 8 * (d + 1)
+    d2h_step = int(128 * (n - d) + per_step["slots"] * (8 * d + 5) + 4 * per_step["slots"])
+
+    line = {
+        "metric": "halfspace cuts/sec", "value": cuts_v / t_value, "unit": "cuts/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * t_value / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"pure H->V enumeration, random tangent polytope in R^{d}, {n} halfspaces, seed {a.seed}",
+            "live_vertices": int(n_live), "slots": int(per_step["slots"]), "facets": int(per_step["facets"]),
+            "l2": "step: coordinates (%.0f MB) stay L2-resident across cuts, inherent to the workload; roofline: L2 flushed (256 MB memset) before every timed K1 launch" % (n_live * 8 * d / 1e6),
+            "multi_gpu": "replicas" if world > 1 else "single",
+        },
+        "vertex_evals_per_s": evals_v / t_value,
+        "e2e": {"value": cuts_e / t_e2e, "unit": "cuts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step,
+                "ms_per_step": 1e3 * t_e2e / a.steps},
+        "gpu_launches": int(launches_v + launches_e),
+        "roofline": {"bound": "hbm", "kernel": f"k_classify<{d}>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "ms_per_launch": ms_flush, "ms_per_launch_l2_resident": ms_l2,
+                     "achieved_l2_resident": alg_bytes / (ms_l2 * 1e-3) / 1e9 if ms_l2 > 0 else None,
+                     "sequence_algorithmic_bytes": int(per_step["algorithmic_bytes"]),
+                     "sequence_frac": per_step["algorithmic_bytes"] / (t_value / a.steps) / 1e9 / peak},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        # CPU baseline beside it: unmodified reference engine on a bounded prefix, rank 0, 1 thread
+        cpu_lib, kind = load_cpu_engine()
+        prefix = min(a.ref_prefix, n)
+        c, dt, live = cpu_step(cpu_lib, trace, prefix)
+        line["cpu_baseline"] = {"value": c / dt, "unit": "cuts/s", "cores": 1, "kind": kind,
+                                "sample": f"first {prefix} of {n} halfspaces ({live} live vertices at the end), {dt:.1f} s, single thread of {os.cpu_count()}"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    trace = P.tangent_polytope(a.dim, a.halfspaces, a.seed)
+    if a.impl == "reference":
+        run_reference(a, trace)
+    else:
+        run_b200(a, trace)
+
+
+if __name__ == "__main__":
+    main()

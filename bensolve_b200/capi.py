@@ -89,6 +89,13 @@ class Permutation(C.Structure):  # bslv_poly.h:84-88
     _fields_ = [("cnt", C.c_size_t), ("data", C.POINTER(C.c_size_t)), ("inv", C.POINTER(C.c_size_t))]
 
 
+class Stats(C.Structure):  # b200_stats, include/bensolve_b200.h
+    _fields_ = [(n, C.c_uint64) for n in (
+        "cuts", "redundant", "vertex_evals", "rows_scanned", "minus", "zero", "zero_plus_projected", "edge_vertices",
+        "copies", "pair_tests", "new_adjacent_pairs", "algorithmic_bytes", "kernel_launches", "compactions",
+        "live_vertices", "slots", "facets")] + [("classify_ms", C.c_double), ("cut_ms", C.c_double)]
+
+
 assert C.sizeof(PolyList) == 24 and C.sizeof(Polytope) == 112 and C.sizeof(PolyArgs) == 392
 
 # the 16 entry points bslv_algs.o imports + the exported helpers
@@ -135,6 +142,19 @@ def _bind(lib):
     if hasattr(lib, "b200_poly_materialise"):
         lib.b200_poly_materialise.argtypes = [P(PolyArgs)]
         lib.b200_poly_materialise.restype = C.c_int
+        lib.b200_poly_set_flags.argtypes = [P(PolyArgs), C.c_uint]
+        lib.b200_poly_set_flags.restype = C.c_int
+        lib.b200_poly_add_batch.argtypes = [P(PolyArgs), P(C.c_double), P(C.c_ubyte), C.c_size_t, P(C.c_int)]
+        lib.b200_poly_add_batch.restype = C.c_long
+        lib.b200_poly_add_batch_device.argtypes = [P(PolyArgs), C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_int)]
+        lib.b200_poly_add_batch_device.restype = C.c_long
+        lib.b200_poly_reserve.argtypes = [P(PolyArgs), C.c_size_t, C.c_size_t, C.c_size_t]
+        lib.b200_poly_reserve.restype = C.c_int
+        lib.b200_poly_classify_bench.argtypes = [P(PolyArgs), P(C.c_double), C.c_int, C.c_int]
+        lib.b200_poly_classify_bench.restype = C.c_double
+        lib.b200_poly_get_stats.argtypes = [P(PolyArgs), P(Stats)]
+        lib.b200_poly_get_stats.restype = C.c_int
+        lib.b200_last_error.restype = C.c_char_p
     return lib
 
 
@@ -185,7 +205,7 @@ class PolyState:
 class PolyEngine:
     """Drives one ``poly_args`` through the reference API (same calls as bslv_algs.c:331-350)."""
 
-    def __init__(self, lib, dim: int, callback=None, dim_primg_prml: int = 0, dim_primg_dl: int = 0):
+    def __init__(self, lib, dim: int, callback=None, dim_primg_prml: int = 0, dim_primg_dl: int = 0, flags: int = 0):
         self.lib = lib
         self.dim = dim
         self.args = PolyArgs()
@@ -197,6 +217,8 @@ class PolyEngine:
         self.args.dim_primg_prml = dim_primg_prml
         self.args.dim_primg_dl = dim_primg_dl
         lib.poly__initialise(C.byref(self.args))
+        if flags:
+            lib.b200_poly_set_flags(C.byref(self.args), flags)   # product / emulation double only
         self.alive = True
 
     # -- the calls bslv_algs.c makes -------------------------------------------------------
@@ -206,6 +228,39 @@ class PolyEngine:
             self.args.val[k] = float(val[k])
         self.args.ideal = int(ideal)
         return self.lib.poly__add_vrtx(C.byref(self.args))
+
+    def add_batch(self, vals, ideal=None):
+        """b200_poly_add_batch: host arrays in, one device-resident pass, mirror coherent at return."""
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        n = len(vals)
+        rcs = (C.c_int * n)()
+        idl = None
+        if ideal is not None:
+            ideal = np.ascontiguousarray(ideal, dtype=np.uint8)
+            idl = ideal.ctypes.data_as(C.POINTER(C.c_ubyte))
+        got = self.lib.b200_poly_add_batch(C.byref(self.args), vals.ctypes.data_as(C.POINTER(C.c_double)), idl, n, rcs)
+        if got < 0:
+            raise RuntimeError(self.lib.b200_last_error().decode())
+        return list(rcs)
+
+    def add_batch_device(self, d_vals_ptr: int, d_ideal_ptr: int, n: int):
+        rcs = (C.c_int * n)()
+        got = self.lib.b200_poly_add_batch_device(C.byref(self.args), d_vals_ptr, d_ideal_ptr or None, n, rcs)
+        if got < 0:
+            raise RuntimeError(self.lib.b200_last_error().decode())
+        return list(rcs)
+
+    def reserve(self, vertices: int, inc_entries: int, adj_entries: int):
+        return self.lib.b200_poly_reserve(C.byref(self.args), vertices, inc_entries, adj_entries)
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.lib.b200_poly_get_stats(C.byref(self.args), C.byref(st))
+        return {n: getattr(st, n) for n, _ in Stats._fields_}
+
+    def classify_bench(self, hp, iters: int, flush_l2: bool) -> float:
+        arr = (C.c_double * (self.dim + 1))(*[float(x) for x in hp])
+        return self.lib.b200_poly_classify_bench(C.byref(self.args), arr, iters, 1 if flush_l2 else 0)
 
     def init_approx(self) -> int:
         return self.lib.poly__intl_apprx(C.byref(self.args))

@@ -192,6 +192,7 @@ B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
 		set_bit_atomic(S.live, nw);
 		S.row_slot[nw] = ctl->slot_cnt + j;
 		S.new_parent[j] = S.row_slot[v];
+		S.root[nw] = S.row_slot[v] < P.batch_first ? S.row_slot[v] : S.root[v];
 		S.deg[j] = 0;
 		S.new_padj_off[j] = ppos;
 		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
@@ -253,6 +254,7 @@ B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
 			set_bit_atomic(S.live, nw);
 			S.row_slot[nw] = ctl->slot_cnt + j;
 			S.new_parent[j] = B200_NONE;
+			S.root[nw] = B200_NONE;
 			S.deg[j] = 0;
 			S.new_padj_off[j] = ppos + np;
 			S.new_padj_len[j] = 1;
@@ -332,15 +334,85 @@ B200_HD bool lists_adjacent(const DevState &S, u32 a, u32 b, u32 M)
 	return true;
 }
 
-B200_HD void pair_test(const DevState &S, u64 pidx, u32 M)
+// ---- K4, bitset form (north_star (3)): the incidence lists of the M new rows are re-coded as rows of a
+// bit matrix over the facets they actually touch (the new facet itself is common to all and left
+// out, so the reference's |mutual| >= d-1, bslv_poly.c:484, becomes popcount >= d-2).
+
+// column relabelling: first toucher of a facet in this cut allocates its column
+B200_HD void k4_assign_columns(const DevState &S, u32 j)
 {
-	u32 a = (u32)(pidx / M), b = (u32)(pidx % M);
-	if (a >= b) return;
-	if (!lists_adjacent(S, a, b, M)) return;
-	u32 p = B200_ATOMIC_ADD(&S.ctl->n_pairs, 1u);
+	const u32 r = S.ctl->nrows + j, f = S.cur->facet, epoch = f + 1;
+	const u32 *l = S.inc_pool + S.inc_off[r];
+	for (u32 q = 0, n = S.inc_len[r]; q < n; q++) {
+		const u32 fc = l[q];
+		if (fc == f) continue;
+		if (B200_ATOMIC_EXCH(&S.facet_epoch[fc], epoch) != epoch) S.facet_local[fc] = B200_ATOMIC_ADD(&S.ctl->n_local, 1u);
+	}
+}
+B200_HD void k4_plan(const DevState &S)
+{
+	CutCtl *c = S.ctl;
+	c->wl = (c->n_local + 63) / 64;
+	c->mpad = (c->n_new + 31) & ~31u;
+	if ((u64)c->wl * c->mpad > S.cap_bits) c->status |= ST_OVF_BITS;
+}
+B200_HD void k4_build_row(const DevState &S, u32 j)
+{
+	const CutCtl *c = S.ctl;
+	const u32 r = c->nrows + j, f = S.cur->facet, wl = c->wl, mpad = c->mpad;
+	for (u32 w = 0; w < wl; w++) S.bits[(size_t)w * mpad + j] = 0;
+	const u32 *l = S.inc_pool + S.inc_off[r];
+	for (u32 q = 0, n = S.inc_len[r]; q < n; q++) {
+		const u32 fc = l[q];
+		if (fc == f) continue;
+		const u32 col = S.facet_local[fc];
+		S.bits[(size_t)(col >> 6) * mpad + j] |= (u64)1 << (col & 63);
+	}
+}
+B200_HD u32 popc64(u64 x)
+{
+#if defined(__CUDA_ARCH__)
+	return (u32)__popcll(x);
+#else
+	return (u32)__builtin_popcountll(x);
+#endif
+}
+B200_HD void k4_push_survivor(const DevState &S, u32 a, u32 b)
+{
+	const u32 p = B200_ATOMIC_ADD(&S.ctl->n_surv, 1u);
+	if (p < S.cap_pairs) { S.surv_a[p] = a; S.surv_b[p] = b; }
+}
+B200_HD void k4_push_pair(const DevState &S, u32 a, u32 b)
+{
+	const u32 p = B200_ATOMIC_ADD(&S.ctl->n_pairs, 1u);
 	B200_ATOMIC_ADD(&S.deg[a], 1u);
 	B200_ATOMIC_ADD(&S.deg[b], 1u);
 	if (p < S.cap_pairs) { S.pair_a[p] = a; S.pair_b[p] = b; }
+}
+// scalar forms (host test double; the kernels use the tiled / warp-cooperative forms)
+B200_HD void k4_filter_pair(const DevState &S, u32 a, u32 b)
+{
+	const CutCtl *c = S.ctl;
+	u32 n = 0;
+	for (u32 w = 0; w < c->wl; w++) n += popc64(S.bits[(size_t)w * c->mpad + a] & S.bits[(size_t)w * c->mpad + b]);
+	if (n + 2 >= (u32)S.d) k4_push_survivor(S, a, b);
+}
+B200_HD void k4_contain_pair(const DevState &S, u32 s)
+{
+	const CutCtl *c = S.ctl;
+	const u32 a = S.surv_a[s], b = S.surv_b[s], M = c->n_new;
+	bool adjacent = true;
+	if (S.d != 1)
+		for (u32 x = 0; x < M && adjacent; x++) {
+			if (x == a || x == b) continue;
+			bool contains = true;
+			for (u32 w = 0; w < c->wl && contains; w++) {
+				const u64 m = S.bits[(size_t)w * c->mpad + a] & S.bits[(size_t)w * c->mpad + b];
+				contains = (S.bits[(size_t)w * c->mpad + x] & m) == m;
+			}
+			if (contains) adjacent = false;
+		}
+	if (adjacent) k4_push_pair(S, a, b);
 }
 
 // adjacency build: PLUS neighbours first, then the new-facet neighbours in ascending row order
@@ -370,4 +442,44 @@ B200_HD void adj_sort(const DevState &S, u32 j)
 		while (y > lo && l[y - 1] > key) { l[y] = l[y - 1]; y--; }
 		l[y] = key;
 	}
+}
+
+// ---- delta record for the host mirror (SURVEY 8(b) coherence rule), packed so that one D2H copy
+// brings everything poly__add_vrtx has to apply.  Layout after the B200_STAGE_HDR-byte header:
+//   double coords[n_new][d] | u32 parent_slot[n_new] | u32 dead_slot[n_vis] | u32 dead_facet[n_dead] | u8 ideal[n_new]
+struct StageLayout { u64 coords, parent, dead_slots, dead_facets, ideal, total; };
+B200_HD StageLayout stage_layout(const CutCtl &c, int d)
+{
+	StageLayout L;
+	const bool cutting = !(c.status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE));
+	const u64 n_new = cutting ? c.n_new : 0, n_vis = cutting ? c.n_vis : 0, n_dead = cutting ? c.n_dead_facets : 0;
+	L.coords = B200_STAGE_HDR;
+	L.parent = L.coords + 8 * n_new * (u64)d;
+	L.dead_slots = L.parent + 4 * n_new;
+	L.dead_facets = L.dead_slots + 4 * n_vis;
+	L.ideal = L.dead_facets + 4 * n_dead;
+	L.total = (L.ideal + n_new + 7) & ~(u64)7;
+	return L;
+}
+// item e of the packing pass; n_items = n_new*d + n_new + n_vis + n_dead  (ideal rides with parent)
+B200_HD void pack_delta_item(const DevState &S, const StageLayout &L, u64 e)
+{
+	const CutCtl *c = S.ctl;
+	const u64 n_new = c->n_new, d = (u64)S.d;
+	const u32 first_row = c->nrows - c->n_new;      // k_finish has already advanced nrows
+	if (e < n_new * d) {
+		const u64 r = e / d, j = e % d;
+		((double *)(S.stage + L.coords))[e] = S.coord[j * S.cap_rows + first_row + r];
+		return;
+	}
+	e -= n_new * d;
+	if (e < n_new) {
+		((u32 *)(S.stage + L.parent))[e] = S.new_parent[e];
+		S.stage[L.ideal + e] = bit_test(S.ideal, first_row + (u32)e) ? 1 : 0;
+		return;
+	}
+	e -= n_new;
+	if (e < c->n_vis) { ((u32 *)(S.stage + L.dead_slots))[e] = S.dead_slots[e]; return; }
+	e -= c->n_vis;
+	((u32 *)(S.stage + L.dead_facets))[e] = S.dead_facets[e];
 }

@@ -129,6 +129,8 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	ensure_adj(1u << 16);
 	ensure_padj(1u << 14);
 	ensure_pairs(1u << 16);
+	ensure_bits(1u << 16);
+	ensure_stage(1u << 18);
 	ensure_facets(1024);
 }
 
@@ -138,17 +140,19 @@ CutEngine::~CutEngine()
 	cudaSetDevice(g_device);
 	if (stream_) cudaStreamSynchronize(STREAM);
 #endif
-	void *ptrs[] = {S_.coord, S_.row_slot, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
+	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
 	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 #ifndef B200_EMULATE
 	for (int i = 0; i < 4; i++) if (ev_[i]) cudaEventDestroy((cudaEvent_t)ev_[i]);
 	if (pinned_hdr_) cudaFreeHost(pinned_hdr_);
+	if (pinned_stage_) cudaFreeHost(pinned_stage_);
 	if (stream_) cudaStreamDestroy(STREAM);
 #else
 	free(pinned_hdr_);
+	free(pinned_stage_);
 #endif
 }
 
@@ -166,6 +170,7 @@ void CutEngine::ensure_rows(u32 need)
 	dfree(S_.coord);
 	S_.coord = nc;
 	regrow(S_.row_slot, cap, keep);
+	regrow(S_.root, cap, keep);
 	regrow(S_.live, cap / 32, old / 32);
 	regrow(S_.ideal, cap / 32, old / 32);
 	regrow(S_.inc_off, cap, keep);
@@ -215,7 +220,30 @@ void CutEngine::ensure_pairs(u32 need)
 	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_pairs * 2);
 	regrow(S_.pair_a, cap, 0);
 	regrow(S_.pair_b, cap, 0);
+	regrow(S_.surv_a, cap, 0);
+	regrow(S_.surv_b, cap, 0);
 	S_.cap_pairs = cap;
+}
+void CutEngine::ensure_bits(u64 need)
+{
+	if (need <= S_.cap_bits) return;
+	u64 cap = std::max<u64>(need, S_.cap_bits * 2);
+	regrow(S_.bits, cap, 0);
+	S_.cap_bits = cap;
+}
+void CutEngine::ensure_stage(u64 need)
+{
+	if (need <= S_.cap_stage) return;
+	const u64 cap = std::max<u64>(need, S_.cap_stage * 2);
+	regrow(S_.stage, cap, 0);
+#ifndef B200_EMULATE
+	if (pinned_stage_) CK(cudaFreeHost(pinned_stage_));
+	CK(cudaMallocHost((void **)&pinned_stage_, cap));
+#else
+	free(pinned_stage_);
+	pinned_stage_ = (unsigned char *)calloc(1, cap);
+#endif
+	S_.cap_stage = cap;
 }
 void CutEngine::ensure_facets(u32 need)
 {
@@ -223,6 +251,8 @@ void CutEngine::ensure_facets(u32 need)
 	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_facets * 2);
 	regrow(S_.facet_cnt, cap, S_.cap_facets);
 	regrow(S_.facet_alive, cap, S_.cap_facets);
+	regrow(S_.facet_epoch, cap, S_.cap_facets);
+	regrow(S_.facet_local, cap, S_.cap_facets);
 	regrow(S_.dead_facets, cap, 0);
 	S_.cap_facets = cap;
 }
@@ -280,13 +310,8 @@ void CutEngine::upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
 #ifndef B200_EMULATE
 template <int D> static void launch_classify(const DevState &S, int grid, cudaStream_t st) { k_classify<D><<<grid, K_THREADS, 0, st>>>(S); }
 
-void CutEngine::launch_part_a(const CutParams &P)
+void CutEngine::launch_classify_dim(int gcls)
 {
-	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
-	const int gmap = num_sms_ * 4;
-	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
-	k_begin<<<1, 32, 0, STREAM>>>(S_, P);
-	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
 	switch (d_) {
 	case 2: launch_classify<2>(S_, gcls, STREAM); break;
 	case 3: launch_classify<3>(S_, gcls, STREAM); break;
@@ -297,6 +322,19 @@ void CutEngine::launch_part_a(const CutParams &P)
 	case 8: launch_classify<8>(S_, gcls, STREAM); break;
 	default: launch_classify<0>(S_, gcls, STREAM); break;
 	}
+}
+
+void CutEngine::launch_part_a(const CutParams &P)
+{
+	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
+	const int gmap = num_sms_ * 4;
+	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
+	if (dev_vals_)
+		k_begin_dev<<<1, 32, 0, STREAM>>>(S_, dev_vals_, dev_ideal_, dev_index_, P.facet, P.batch_first);
+	else
+		k_begin<<<1, 32, 0, STREAM>>>(S_, P);
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
+	launch_classify_dim(gcls);
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 	k_scan_tiles<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
 	k_scatter<<<gcls, K_THREADS, 0, STREAM>>>(S_);
@@ -312,33 +350,59 @@ void CutEngine::launch_part_b(bool rerun)
 {
 	const int gmap = num_sms_ * 4;
 	if (rerun) { k_pairs_reset<<<gmap, K_THREADS, 0, STREAM>>>(S_); stats_.kernel_launches++; }
-	k_pairs<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_);
+	k4_assign<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	k4_plan_kernel<<<1, 32, 0, STREAM>>>(S_);
+	k4_build<<<gmap, K_THREADS, 0, STREAM>>>(S_);
+	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
+	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
 	k_adj_scan<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
 	k_adj_place<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k_adj_pair_fill<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k_adj_sort<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k_finish<<<1, 32, 0, STREAM>>>(S_);
-	stats_.kernel_launches += 6;
+	stats_.kernel_launches += 10;
 	CK(cudaGetLastError());
 }
 
-void CutEngine::read_header()
+void CutEngine::launch_part_c(bool header_only)
 {
-	CK(cudaMemcpyAsync(pinned_hdr_, S_.ctl, sizeof(CutCtl), cudaMemcpyDeviceToHost, STREAM));
+	k_pack_delta<<<header_only ? 1 : num_sms_ * 2, K_THREADS, 0, STREAM>>>(S_, header_only ? 1 : 0);
+	stats_.kernel_launches++;
+}
+
+// One D2H copy brings the header and (almost always) the whole delta; a second one only when the
+// record is longer than the speculative first chunk.
+void CutEngine::fetch_delta()
+{
+	const u64 first = header_only_ ? B200_STAGE_HDR : std::min<u64>(S_.cap_stage, 64 * 1024);
+	CK(cudaMemcpyAsync(pinned_stage_, S_.stage, first, cudaMemcpyDeviceToHost, STREAM));
 	CK(cudaStreamSynchronize(STREAM));
-	hdr_ = *pinned_hdr_;
+	memcpy(&hdr_, pinned_stage_, sizeof(CutCtl));
+	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE)) && hdr_.stage_bytes > first) {
+		CK(cudaMemcpyAsync(pinned_stage_ + first, S_.stage + first, hdr_.stage_bytes - first, cudaMemcpyDeviceToHost, STREAM));
+		CK(cudaStreamSynchronize(STREAM));
+	}
 }
 #else // ---- host-side test double: same stage bodies, run serially
-void CutEngine::launch_part_a(const CutParams &P)
+void CutEngine::launch_part_a(const CutParams &Pin)
 {
 	DevState &S = S_;
 	CutCtl *c = S.ctl;
+	CutParams P = Pin;
+	if (dev_vals_) {
+		double hh = 0;
+		for (int j = 0; j < B200_MAXD; j++) { const double v = j < S.d ? dev_vals_[dev_index_ * S.d + j] : 0.0; P.h[j] = v; hh += v * v; }
+		P.alpha = (dev_ideal_ && dev_ideal_[dev_index_]) ? 0.0 : -1.0;
+		for (int id = 0; id < 2; id++) { const double thr = id ? 0.0 : P.alpha; P.hi[id] = thr + 1e-9; P.mid[id] = thr + 1.0e-2 * 1e-9; P.lo[id] = thr - 1e-9; }
+		P.hh = hh;
+	}
 	*S.cur = P;
 	c->status = 0;
 	c->n_strict = 0;
 	c->min_strict_row = c->min_strict_slot = B200_NONE;
 	c->n_zp = c->n_zp_projected = c->n_vis = c->n_new = c->inc_new = c->padj_new = 0;
 	c->n_minus = c->n_zero = c->n_pairs = c->adj_new = c->n_dead_facets = c->n_live_scanned = 0;
+	c->n_local = c->wl = c->mpad = c->n_surv = 0;
 	S.facet_cnt[P.facet] = 0;
 	S.facet_alive[P.facet] = 1;
 	for (u32 r = 0; r < c->nrows; r++) {
@@ -378,9 +442,16 @@ void CutEngine::launch_part_b(bool rerun)
 	DevState &S = S_;
 	CutCtl *c = S.ctl;
 	if (c->status & (ST_REDUNDANT | ST_OVF_A | ST_ERR_DEGENERATE)) return;
-	if (rerun) { c->n_pairs = 0; c->status &= ~(u32)ST_OVF_B; for (u32 j = 0; j < c->n_new; j++) S.deg[j] = 0; }
+	if (rerun) { c->n_pairs = c->n_surv = 0; c->status &= ~(u32)ST_OVF_B; for (u32 j = 0; j < c->n_new; j++) S.deg[j] = 0; }
 	const u32 M = c->n_new;
-	for (u64 p = 0; p < (u64)M * M; p++) pair_test(S, p, M);
+	for (u32 j = 0; j < M; j++) k4_assign_columns(S, j);
+	k4_plan(S);
+	if (c->status & ST_OVF_BITS) return;
+	for (u32 j = 0; j < M; j++) k4_build_row(S, j);
+	for (u32 a = 0; a < M; a++)
+		for (u32 b = a + 1; b < M; b++) k4_filter_pair(S, a, b);
+	if (c->n_surv > S.cap_pairs) { c->status |= ST_OVF_PAIRS; return; }
+	for (u32 s = 0; s < c->n_surv; s++) k4_contain_pair(S, s);
 	if (c->n_pairs > S.cap_pairs) { c->status |= ST_OVF_PAIRS; return; }
 	u32 carry = 0;
 	for (u32 j = 0; j < M; j++) { S.adj_base[j] = carry; carry += S.new_padj_len[j] + S.deg[j]; }
@@ -395,39 +466,58 @@ void CutEngine::launch_part_b(bool rerun)
 	c->inc_used += c->inc_new;
 	c->adj_used += c->adj_new;
 }
-void CutEngine::read_header() { hdr_ = *S_.ctl; }
+void CutEngine::launch_part_c(bool header_only)
+{
+	CutCtl *c = S_.ctl;
+	const StageLayout L = stage_layout(*c, S_.d);
+	CutCtl h = *c;
+	h.stage_bytes = (u32)L.total;
+	if (!header_only && L.total > S_.cap_stage) h.status |= ST_OVF_STAGE;
+	memcpy(S_.stage, &h, sizeof h);
+	if (header_only || (h.status & ST_OVF_STAGE) || (c->status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE))) return;
+	const u64 n = (u64)c->n_new * S_.d + c->n_new + c->n_vis + c->n_dead_facets;
+	for (u64 e = 0; e < n; e++) pack_delta_item(S_, L, e);
+}
+void CutEngine::fetch_delta()
+{
+	memcpy(&hdr_, S_.stage, sizeof(CutCtl));
+	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE))) memcpy(pinned_stage_, S_.stage, hdr_.stage_bytes);
+}
 #endif
 
-void CutEngine::cut(const CutParams &P, CutDelta &out)
+void CutEngine::run_cut(const CutParams &P, bool header_only)
 {
 #ifndef B200_EMULATE
 	CK(cudaSetDevice(g_device));
 #endif
-	out = CutDelta();
+	header_only_ = header_only;
 	ensure_facets(P.facet + 1);
 	// head-room for the appends; exact needs are checked on the device before any mutation
 	ensure_rows(hdr_.nrows + std::max<u32>(4096, hdr_.n_live / 2 + 64));
-	const u32 n_live_before = hdr_.n_live, nrows_before = hdr_.nrows;
 #ifndef B200_EMULATE
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[2], STREAM));
 #endif
 	launch_part_a(P);
 	launch_part_b(false);
-	read_header();
-	for (int guard = 0; hdr_.status & (ST_OVF_A | ST_OVF_B); guard++) {
-		if (guard > 8) fail("bensolve_b200: capacity negotiation did not converge");
+	launch_part_c(header_only);
+	fetch_delta();
+	for (int guard = 0; hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE); guard++) {
+		if (guard > 12) fail("bensolve_b200: capacity negotiation did not converge");
 		if (hdr_.status & ST_OVF_A) {
 			if (hdr_.status & ST_OVF_ROWS) ensure_rows(hdr_.nrows + hdr_.n_new + B200_TILE);
 			if (hdr_.status & ST_OVF_INC) ensure_inc(hdr_.inc_used + hdr_.inc_new);
 			if (hdr_.status & ST_OVF_PADJ) ensure_padj(hdr_.padj_new);
 			launch_part_a(P);
 			launch_part_b(false);
-		} else {
-			if (hdr_.status & ST_OVF_PAIRS) ensure_pairs(hdr_.n_pairs);
+		} else if (hdr_.status & ST_OVF_B) {
+			if (hdr_.status & ST_OVF_PAIRS) ensure_pairs(std::max(hdr_.n_pairs, hdr_.n_surv));
+			if (hdr_.status & ST_OVF_BITS) ensure_bits((u64)hdr_.wl * hdr_.mpad);
 			if (hdr_.status & ST_OVF_ADJ) ensure_adj(hdr_.adj_used + hdr_.adj_new);
 			launch_part_b(true);
-		}
-		read_header();
+		} else
+			ensure_stage(hdr_.stage_bytes);
+		launch_part_c(header_only);
+		fetch_delta();
 	}
 #ifndef B200_EMULATE
 	if (flags_ & 1) {
@@ -438,48 +528,27 @@ void CutEngine::cut(const CutParams &P, CutDelta &out)
 		stats_.classify_ms += ms;
 		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[2], (cudaEvent_t)ev_[3]));
 		stats_.cut_ms += ms;
+		static const char *trace = getenv("B200_TRACE");
+		if (trace && ms > atof(trace))
+			fprintf(stderr, "[b200] slow cut %.3f ms: facet=%u nrows=%u live=%u n_vis=%u n_new=%u n_local=%u wl=%u n_surv=%u n_pairs=%u status=%u stage=%u\n",
+			        ms, P.facet, hdr_.nrows, hdr_.n_live, hdr_.n_vis, hdr_.n_new, hdr_.n_local, hdr_.wl, hdr_.n_surv, hdr_.n_pairs, hdr_.status, hdr_.stage_bytes);
 	}
 #endif
 	if (hdr_.status & ST_ERR_DEGENERATE)
 		fail("bensolve_b200: a vertex on the cutting hyperplane lies on more than " + std::to_string(B200_MAXINC) + " facets");
+}
+
+// statistics of the cut just fetched (SURVEY 8(d) algorithmic bytes)
+void CutEngine::account(const CutParams &P, u32 n_live_before, u32 nrows_before)
+{
 	stats_.vertex_evals += hdr_.n_live_scanned;
 	stats_.rows_scanned += nrows_before;
 	if (hdr_.status & ST_REDUNDANT) {
-		out.redundant = 1;
 		stats_.redundant++;
 		stats_.algorithmic_bytes += (u64)n_live_before * (8 * d_ + 1);
 		return;
 	}
-	// ---- delta download (new rows are [first_row, first_row + n_new))
-	const u32 n_new = hdr_.n_new, first_row = hdr_.nrows - n_new;
-	out.trigger_slot = hdr_.min_strict_slot;
-	out.n_new = n_new;
-	out.first_new_slot = hdr_.slot_cnt - n_new;
-	out.coords.resize((size_t)n_new * d_);
-	out.ideal.assign(n_new, 0);
-	out.parent_slot.resize(n_new);
-	if (n_new) {
-		std::vector<double> col(n_new);
-		for (int j = 0; j < d_; j++) {
-			d2h(col.data(), S_.coord + (size_t)j * S_.cap_rows + first_row, (size_t)n_new * sizeof(double));
-			for (u32 r = 0; r < n_new; r++) out.coords[(size_t)r * d_ + j] = col[r];
-		}
-		const u32 w0 = first_row >> 5, w1 = (first_row + n_new - 1) >> 5;
-		std::vector<u32> words(w1 - w0 + 1);
-		d2h(words.data(), S_.ideal + w0, words.size() * 4);
-		for (u32 r = 0; r < n_new; r++) {
-			u32 g = first_row + r;
-			out.ideal[r] = (words[(g >> 5) - w0] >> (g & 31)) & 1u;
-		}
-		d2h(out.parent_slot.data(), S_.new_parent, (size_t)n_new * 4);
-	}
-	std::vector<u32> ds(hdr_.n_vis);
-	d2h(ds.data(), S_.dead_slots, (size_t)hdr_.n_vis * 4);
-	for (u32 s : ds) if (s != B200_NONE) out.dead_slots.push_back(s);
-	out.dead_facets.resize(hdr_.n_dead_facets);
-	d2h(out.dead_facets.data(), S_.dead_facets, (size_t)hdr_.n_dead_facets * 4);
-	// ---- statistics (SURVEY 8(d) algorithmic bytes)
-	const u64 N = n_live_before, nm = hdr_.n_minus, nz = hdr_.n_zero, E = n_new - nz, M = n_new;
+	const u64 N = n_live_before, nm = hdr_.n_minus, nz = hdr_.n_zero, M = hdr_.n_new, E = M - nz;
 	const u64 W = (P.facet + 64) / 64, A = hdr_.n_pairs;
 	stats_.cuts++;
 	stats_.minus += nm;
@@ -490,11 +559,228 @@ void CutEngine::cut(const CutParams &P, CutDelta &out)
 	stats_.pair_tests += M * (M - (M ? 1 : 0)) / 2;
 	stats_.new_adjacent_pairs += A;
 	stats_.algorithmic_bytes += N * (8 * d_ + 1) + N + 4 * (nm + nz) + E * (24 * d_ + 24 * W) + nz * (16 * d_ + 16 * W) + 8 * M * W + 8 * A;
+}
+
+void CutEngine::cut(const CutParams &P, CutDelta &out)
+{
+	out = CutDelta();
+	const u32 n_live_before = hdr_.n_live, nrows_before = hdr_.nrows;
+	run_cut(P, false);
+	account(P, n_live_before, nrows_before);
+	if (hdr_.status & ST_REDUNDANT) { out.redundant = 1; return; }
+	// ---- unpack the delta record
+	const u32 n_new = hdr_.n_new;
+	const StageLayout L = stage_layout(hdr_, d_);
+	out.trigger_slot = hdr_.min_strict_slot;
+	out.n_new = n_new;
+	out.first_new_slot = hdr_.slot_cnt - n_new;
+	out.coords.resize((size_t)n_new * d_);
+	out.ideal.resize(n_new);
+	out.parent_slot.resize(n_new);
+	if (n_new) {
+		memcpy(out.coords.data(), pinned_stage_ + L.coords, (size_t)n_new * d_ * sizeof(double));
+		memcpy(out.parent_slot.data(), pinned_stage_ + L.parent, (size_t)n_new * 4);
+		memcpy(out.ideal.data(), pinned_stage_ + L.ideal, n_new);
+	}
+	const u32 *ds = (const u32 *)(pinned_stage_ + L.dead_slots);
+	for (u32 i = 0; i < hdr_.n_vis; i++) if (ds[i] != B200_NONE) out.dead_slots.push_back(ds[i]);
+	const u32 *df = (const u32 *)(pinned_stage_ + L.dead_facets);
+	out.dead_facets.assign(df, df + hdr_.n_dead_facets);
 	maybe_compact();
 }
 
-void CutEngine::maybe_compact() {}
-void CutEngine::compact() {}
+int CutEngine::cut_from_device(const double *d_vals, const unsigned char *d_ideal, u64 i, u32 facet, u32 batch_first)
+{
+	CutParams P;
+	memset(&P, 0, sizeof P);
+	P.facet = facet;
+	P.batch_first = batch_first;
+	dev_vals_ = d_vals;
+	dev_ideal_ = d_ideal;
+	dev_index_ = i;
+	const u32 n_live_before = hdr_.n_live, nrows_before = hdr_.nrows;
+	try {
+		run_cut(P, true);
+	} catch (...) {
+		dev_vals_ = nullptr;
+		throw;
+	}
+	dev_vals_ = nullptr;
+	account(P, n_live_before, nrows_before);
+	const int redundant = (hdr_.status & ST_REDUNDANT) ? 1 : 0;
+	if (!redundant) maybe_compact();
+	return redundant;
+}
+
+void CutEngine::reserve(u64 rows, u64 inc_entries, u64 adj_entries)
+{
+	if (rows > 0xFFFF0000ull || inc_entries > 0xFFFF0000ull || adj_entries > 0xFFFF0000ull) fail("bensolve_b200: reserve beyond 32-bit row/pool indices");
+	ensure_rows((u32)rows);
+	ensure_inc((u32)inc_entries);
+	ensure_adj((u32)adj_entries);
+}
+
+void CutEngine::download_mirror(MirrorDump &o, u32 n_facets)
+{
+#ifndef B200_EMULATE
+	CK(cudaSetDevice(g_device));
+	CK(cudaStreamSynchronize(STREAM));
+#endif
+	const u32 n = hdr_.nrows;
+	o.nrows = n;
+	o.slot_cnt = hdr_.slot_cnt;
+	o.row_slot.resize(n); o.root.resize(n);
+	o.live_words.resize((n + 31) / 32); o.ideal_words.resize((n + 31) / 32);
+	o.coords_soa.resize((size_t)n * d_);
+	o.facet_alive.resize(n_facets);
+	d2h(o.row_slot.data(), S_.row_slot, (size_t)n * 4);
+	d2h(o.root.data(), S_.root, (size_t)n * 4);
+	d2h(o.live_words.data(), S_.live, o.live_words.size() * 4);
+	d2h(o.ideal_words.data(), S_.ideal, o.ideal_words.size() * 4);
+	for (int j = 0; j < d_; j++) d2h(o.coords_soa.data() + (size_t)j * n, S_.coord + (size_t)j * S_.cap_rows, (size_t)n * sizeof(double));
+	ensure_facets(n_facets);
+	d2h(o.facet_alive.data(), S_.facet_alive, (size_t)n_facets * 4);
+}
+
+void *CutEngine::device_alloc(size_t bytes) { return dalloc(bytes); }
+void CutEngine::device_free(void *p) { dfree(p); }
+void CutEngine::device_upload(void *dst, const void *src, size_t bytes) { h2d(dst, src, bytes); }
+void CutEngine::device_download(void *dst, const void *src, size_t bytes)
+{
+#ifndef B200_EMULATE
+	CK(cudaStreamSynchronize(STREAM));
+#endif
+	d2h(dst, src, bytes);
+}
+
+double CutEngine::classify_bench(const CutParams &P, int iters, int flush_l2)
+{
+#ifndef B200_EMULATE
+	CK(cudaSetDevice(g_device));
+	const size_t flush_bytes = (size_t)256 << 20;     // > 126 MB L2
+	if (flush_l2 && !flush_buf_) flush_buf_ = dalloc(flush_bytes);
+	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
+	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
+	double total = 0;
+	for (int it = 0; it < iters; it++) {
+		k_begin<<<1, 32, 0, STREAM>>>(S_, P);
+		if (flush_l2) CK(cudaMemsetAsync(flush_buf_, it & 0xff, flush_bytes, STREAM));
+		CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
+		launch_classify_dim(gcls);
+		CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
+		CK(cudaEventSynchronize((cudaEvent_t)ev_[1]));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[0], (cudaEvent_t)ev_[1]));
+		total += ms;
+	}
+	// the probe halfspace is not a facet: undo what k_begin registered
+	CK(cudaMemsetAsync(S_.facet_alive + P.facet, 0, 4, STREAM));
+	CK(cudaStreamSynchronize(STREAM));
+	return iters > 0 ? total / iters : 0.0;
+#else
+	(void)P; (void)iters; (void)flush_l2;
+	return 0.0;
+#endif
+}
+
+void CutEngine::maybe_compact()
+{
+	const bool eager = flags_ & 2;          // test hook: compact as soon as one row is dead
+	if (hdr_.nrows == hdr_.n_live) return;
+	if (!eager && (hdr_.nrows < 4 * B200_TILE || hdr_.nrows < 2 * hdr_.n_live)) return;
+	compact();
+}
+
+#ifndef B200_EMULATE
+void CutEngine::compact()
+{
+	CK(cudaSetDevice(g_device));
+	const u32 nrows = hdr_.nrows, n_live = hdr_.n_live;
+	if (nrows == n_live) return;
+	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE, ltiles = std::max<u32>(1, (n_live + B200_TILE - 1) / B200_TILE);
+	u32 *remap = S_.vis, *old_of = S_.dead_slots, *new_inc_off = S_.adj_base, *new_adj_off = S_.adj_fill;
+	u32 *totals = (u32 *)dalloc(4 * sizeof(u32));
+	// 1. remap = exclusive scan of the live bits
+	LiveBitOf lb{S_.live};
+	k_gscan_reduce<<<ntiles, K_THREADS, 0, STREAM>>>(lb, nrows, S_.tile_cnt);
+	k_gscan_tiles<<<1, SCAN_THREADS, 0, STREAM>>>(S_.tile_cnt, ntiles, S_.tile_base, totals + 0);
+	k_gscan_apply<<<ntiles, K_THREADS, 0, STREAM>>>(lb, nrows, S_.tile_base, remap);
+	k_gc_invert<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_.live, remap, nrows, old_of);
+	// 2. new pool offsets
+	LenOfOld li{S_.inc_len, old_of}, la{S_.adj_len, old_of};
+	k_gscan_reduce<<<ltiles, K_THREADS, 0, STREAM>>>(li, n_live, S_.tile_cnt);
+	k_gscan_tiles<<<1, SCAN_THREADS, 0, STREAM>>>(S_.tile_cnt, ltiles, S_.tile_base, totals + 1);
+	k_gscan_apply<<<ltiles, K_THREADS, 0, STREAM>>>(li, n_live, S_.tile_base, new_inc_off);
+	k_gscan_reduce<<<ltiles, K_THREADS, 0, STREAM>>>(la, n_live, S_.tile_cnt);
+	k_gscan_tiles<<<1, SCAN_THREADS, 0, STREAM>>>(S_.tile_cnt, ltiles, S_.tile_base, totals + 2);
+	k_gscan_apply<<<ltiles, K_THREADS, 0, STREAM>>>(la, n_live, S_.tile_base, new_adj_off);
+	// 3. gather into fresh arrays of the same capacity, then swap
+	GcTarget T;
+	const u32 cap = S_.cap_rows;
+	T.coord = (double *)dalloc((size_t)cap * d_ * sizeof(double));
+	T.row_slot = (u32 *)dalloc((size_t)cap * 4);
+	T.root = (u32 *)dalloc((size_t)cap * 4);
+	T.live = (u32 *)dalloc((size_t)cap / 8);
+	T.ideal = (u32 *)dalloc((size_t)cap / 8);
+	T.inc_off = (u32 *)dalloc((size_t)cap * 4);
+	T.inc_len = (u32 *)dalloc((size_t)cap * 4);
+	T.adj_off = (u32 *)dalloc((size_t)cap * 4);
+	T.adj_len = (u32 *)dalloc((size_t)cap * 4);
+	T.inc_pool = (u32 *)dalloc((size_t)S_.cap_inc * 4);
+	T.adj_pool = (u32 *)dalloc((size_t)S_.cap_adj * 4);
+	k_gc_gather<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, T, n_live, remap, old_of, new_inc_off, new_adj_off);
+	k_gc_finish<<<1, 32, 0, STREAM>>>(S_, n_live, totals + 1, totals + 2);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(pinned_hdr_, S_.ctl, sizeof(CutCtl), cudaMemcpyDeviceToHost, STREAM));
+	CK(cudaStreamSynchronize(STREAM));
+	hdr_ = *pinned_hdr_;
+	if (hdr_.nrows != n_live) fail("bensolve_b200: compaction lost rows");
+	void *old[] = {S_.coord, S_.row_slot, S_.root, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len, S_.inc_pool, S_.adj_pool};
+	for (void *p : old) dfree(p);
+	dfree(totals);
+	S_.coord = T.coord; S_.row_slot = T.row_slot; S_.root = T.root; S_.live = T.live; S_.ideal = T.ideal;
+	S_.inc_off = T.inc_off; S_.inc_len = T.inc_len; S_.adj_off = T.adj_off; S_.adj_len = T.adj_len;
+	S_.inc_pool = T.inc_pool; S_.adj_pool = T.adj_pool;
+	stats_.compactions++;
+	stats_.kernel_launches += 12;
+}
+#else
+void CutEngine::compact()
+{
+	DevState &S = S_;
+	const u32 nrows = hdr_.nrows, n_live = hdr_.n_live, cap = S.cap_rows;
+	if (nrows == n_live) return;
+	std::vector<u32> remap(nrows, 0), old_of;
+	for (u32 r = 0; r < nrows; r++) if (bit_test(S.live, r)) { remap[r] = (u32)old_of.size(); old_of.push_back(r); }
+	double *coord = (double *)dalloc((size_t)cap * d_ * sizeof(double));
+	u32 *row_slot = (u32 *)dalloc((size_t)cap * 4), *root = (u32 *)dalloc((size_t)cap * 4), *live = (u32 *)dalloc(cap / 8), *ideal = (u32 *)dalloc(cap / 8);
+	u32 *inc_off = (u32 *)dalloc((size_t)cap * 4), *inc_len = (u32 *)dalloc((size_t)cap * 4);
+	u32 *adj_off = (u32 *)dalloc((size_t)cap * 4), *adj_len = (u32 *)dalloc((size_t)cap * 4);
+	u32 *inc_pool = (u32 *)dalloc((size_t)S.cap_inc * 4), *adj_pool = (u32 *)dalloc((size_t)S.cap_adj * 4);
+	u32 iu = 0, au = 0;
+	for (u32 n = 0; n < old_of.size(); n++) {
+		const u32 o = old_of[n];
+		for (int j = 0; j < d_; j++) coord[(size_t)j * cap + n] = S.coord[(size_t)j * cap + o];
+		row_slot[n] = S.row_slot[o];
+		root[n] = S.root[o];
+		live[n >> 5] |= 1u << (n & 31);
+		if (bit_test(S.ideal, o)) ideal[n >> 5] |= 1u << (n & 31);
+		inc_off[n] = iu; inc_len[n] = S.inc_len[o];
+		for (u32 q = 0; q < S.inc_len[o]; q++) inc_pool[iu++] = S.inc_pool[S.inc_off[o] + q];
+		adj_off[n] = au; adj_len[n] = S.adj_len[o];
+		for (u32 q = 0; q < S.adj_len[o]; q++) adj_pool[au++] = remap[S.adj_pool[S.adj_off[o] + q]];
+	}
+	void *old[] = {S.coord, S.row_slot, S.root, S.live, S.ideal, S.inc_off, S.inc_len, S.adj_off, S.adj_len, S.inc_pool, S.adj_pool};
+	for (void *p : old) dfree(p);
+	S.coord = coord; S.row_slot = row_slot; S.root = root; S.live = live; S.ideal = ideal; S.inc_off = inc_off; S.inc_len = inc_len;
+	S.adj_off = adj_off; S.adj_len = adj_len; S.inc_pool = inc_pool; S.adj_pool = adj_pool;
+	S.ctl->nrows = S.ctl->n_live = n_live;
+	S.ctl->inc_used = iu;
+	S.ctl->adj_used = au;
+	hdr_ = *S.ctl;
+	stats_.compactions++;
+}
+#endif
 
 void CutEngine::reupload_coords(const double *data_aos, size_t n_slots)
 {

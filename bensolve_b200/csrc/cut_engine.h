@@ -19,6 +19,12 @@ struct CutDelta {             // what one cut changed, in host slot numbers (SUR
 	std::vector<u32> dead_facets;
 };
 
+struct MirrorDump {           // bulk state for rebuilding the host mirror after a device-resident batch
+	u32 nrows = 0, slot_cnt = 0;
+	std::vector<u32> row_slot, live_words, ideal_words, root, facet_alive;
+	std::vector<double> coords_soa;   // [d][nrows]
+};
+
 struct HostStructure {        // snapshot for lazy materialisation of the host poly_lists
 	u32 nrows = 0;
 	std::vector<u32> row_slot, live_words, inc_off, inc_len, adj_off, adj_len, inc_pool, adj_pool;
@@ -45,6 +51,18 @@ public:
 	                    u32 n_facets, const std::vector<u32> &facet_counts);
 	// One halfspace; fills `out`.  Throws std::runtime_error on CUDA errors.
 	void cut(const CutParams &P, CutDelta &out);
+	// Device-resident batch path: halfspace i of `d_vals` (device memory, [n][d], default callback
+	// meaning), no delta transfer; only the 128-byte header comes back.  Returns 1 if redundant.
+	int cut_from_device(const double *d_vals, const unsigned char *d_ideal, u64 i, u32 facet, u32 batch_first);
+	void download_mirror(MirrorDump &out, u32 n_facets);
+	void reserve(u64 rows, u64 inc_entries, u64 adj_entries);
+	// Launch K1 alone `iters` times against halfspace P (no mutation), optionally flushing L2
+	// before each launch; returns the mean CUDA-event time of one launch in ms.
+	double classify_bench(const CutParams &P, int iters, int flush_l2);
+	void *device_alloc(size_t bytes);
+	void device_free(void *p);
+	void device_upload(void *dst, const void *src, size_t bytes);
+	void device_download(void *dst, const void *src, size_t bytes);
 	// Overwrite device coordinates of the given live slots from the host mirror (after the caller
 	// edited primal.data in place, bslv_algs.c:193-273).
 	void reupload_coords(const double *data_aos, size_t n_slots);
@@ -62,20 +80,32 @@ private:
 	void ensure_adj(u32 need);
 	void ensure_padj(u32 need);
 	void ensure_pairs(u32 need);
+	void ensure_bits(u64 need);
 	void ensure_facets(u32 need);
 	void launch_part_a(const CutParams &P);
+	void launch_classify_dim(int gcls);
+	void run_cut(const CutParams &P, bool header_only);
+	void account(const CutParams &P, u32 n_live_before, u32 nrows_before);
 	void launch_part_b(bool rerun);
-	void read_header();
+	void launch_part_c(bool header_only);
+	void fetch_delta();
+	void ensure_stage(u64 need);
 	void maybe_compact();
 
 	int d_;
 	unsigned flags_ = 0;
+	bool header_only_ = false;
 	DevState S_{};
 	CutCtl hdr_{};            // host copy of the control block as of the last sync
 	CutCtl *pinned_hdr_ = nullptr;
+	unsigned char *pinned_stage_ = nullptr;
 	void *stream_ = nullptr;
 	void *ev_[4] = {nullptr, nullptr, nullptr, nullptr};
 	int num_sms_ = 148;
+	const double *dev_vals_ = nullptr;      // set while a device-resident batch is running
+	const unsigned char *dev_ideal_ = nullptr;
+	u64 dev_index_ = 0;
+	void *flush_buf_ = nullptr;
 	EngineStats stats_;
 };
 

@@ -8,6 +8,7 @@
 #include "cut_bodies.h"
 
 #define K_THREADS 256
+#define POLY_EPS_D 1e-9   // POLY_EPS, bslv_poly.h:47
 #define SCAN_THREADS 1024
 #define ST_SKIP_A (ST_REDUNDANT | ST_OVF_A | ST_ERR_DEGENERATE)
 #define ST_SKIP_B (ST_SKIP_A | ST_OVF_B)
@@ -58,8 +59,47 @@ __global__ void k_begin(DevState S, CutParams P)
 	c->n_minus = c->n_zero = 0;
 	c->n_pairs = c->adj_new = c->n_dead_facets = 0;
 	c->n_live_scanned = 0;
+	c->n_local = c->wl = c->mpad = c->n_surv = 0;
 	S.facet_cnt[P.facet] = 0;
 	S.facet_alive[P.facet] = 1;
+}
+
+// begin for the device-resident batch path: the halfspace is built on the device from the dual
+// point vals[i] with the default callback's meaning (cone_polar, bslv_poly.c:30-39)
+__global__ void k_begin_dev(DevState S, const double *vals, const unsigned char *ideal, u64 i, u32 facet, u32 batch_first)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	CutParams P;
+	double hh = 0;
+	for (int j = 0; j < B200_MAXD; j++) {
+		const double v = j < S.d ? vals[i * S.d + j] : 0.0;
+		P.h[j] = v;
+		hh = __dadd_rn(hh, __dmul_rn(v, v));
+	}
+	P.alpha = (ideal && ideal[i]) ? 0.0 : -1.0;
+	for (int id = 0; id < 2; id++) {
+		const double thr = id ? 0.0 : P.alpha;
+		P.hi[id] = __dadd_rn(thr, POLY_EPS_D);
+		P.mid[id] = __dadd_rn(thr, 1.0e-2 * POLY_EPS_D);
+		P.lo[id] = __dsub_rn(thr, POLY_EPS_D);
+	}
+	P.hh = hh;
+	P.facet = facet;
+	P.batch_first = batch_first;
+	*S.cur = P;
+	CutCtl *c = S.ctl;
+	c->status = 0;
+	c->n_strict = 0;
+	c->min_strict_row = B200_NONE;
+	c->min_strict_slot = B200_NONE;
+	c->n_zp = c->n_zp_projected = 0;
+	c->n_vis = c->n_new = c->inc_new = c->padj_new = 0;
+	c->n_minus = c->n_zero = 0;
+	c->n_pairs = c->adj_new = c->n_dead_facets = 0;
+	c->n_live_scanned = 0;
+	c->n_local = c->wl = c->mpad = c->n_surv = 0;
+	S.facet_cnt[facet] = 0;
+	S.facet_alive[facet] = 1;
 }
 
 // ------------------------------------------------------------------ K1: classify
@@ -287,22 +327,132 @@ __global__ void __launch_bounds__(K_THREADS) k_dead_facets(DevState S)
 	B200_GRID_STRIDE(i, S.ctl->n_vis) collect_dead_facets(S, (u32)i);
 }
 
-// ------------------------------------------------------------------ K4 (list form) and adjacency build
+// ------------------------------------------------------------------ K4: pair adjacency on packed bitsets
 __global__ void __launch_bounds__(K_THREADS) k_pairs_reset(DevState S)
 {
 	if (S.ctl->status & ST_SKIP_A) return;
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		S.ctl->n_pairs = 0;
+		S.ctl->n_surv = 0;
 		S.ctl->status &= ~(u32)ST_OVF_B;
 	}
 	B200_GRID_STRIDE(j, S.ctl->n_new) S.deg[j] = 0;
 }
 
-__global__ void __launch_bounds__(K_THREADS) k_pairs(DevState S)
+__global__ void __launch_bounds__(K_THREADS) k4_assign(DevState S)
 {
 	if (S.ctl->status & ST_SKIP_A) return;
-	const u32 M = S.ctl->n_new;
-	B200_GRID_STRIDE(p, (u64)M * M) pair_test(S, p, M);
+	B200_GRID_STRIDE(j, S.ctl->n_new) k4_assign_columns(S, (u32)j);
+}
+__global__ void k4_plan_kernel(DevState S)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	if (S.ctl->status & ST_SKIP_A) return;
+	k4_plan(S);
+}
+__global__ void __launch_bounds__(K_THREADS) k4_build(DevState S)
+{
+	if (S.ctl->status & ST_SKIP_B) return;
+	B200_GRID_STRIDE(j, S.ctl->n_new) k4_build_row(S, (u32)j);
+}
+
+// AND + POPC prefilter over 64x64 tiles of the pair space.  Both row tiles of the word-major bit
+// matrix are staged in shared memory K4_WCH words at a time; thread (i0, j) owns the 16 pairs
+// (i0 + 4k, j), so a warp reads 32 consecutive B words (conflict-free) and one broadcast A word.
+#define K4_T 64
+#define K4_WCH 16
+__global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S)
+{
+	__shared__ u64 sa[K4_WCH][K4_T], sb[K4_WCH][K4_T];
+	const CutCtl *c = S.ctl;
+	if (c->status & ST_SKIP_B) return;
+	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad;
+	const u32 nt = (M + K4_T - 1) / K4_T;
+	const u32 thr = S.d >= 2 ? (u32)(S.d - 2) : 0;
+	const u32 j = threadIdx.x & (K4_T - 1), i0 = threadIdx.x >> 6;
+	for (u32 tp = blockIdx.x; tp < nt * nt; tp += gridDim.x) {
+		const u32 ta = tp / nt, tb = tp % nt;
+		if (tb < ta) continue;                       // block-uniform
+		u32 cnt[K4_T / 4];
+#pragma unroll
+		for (int k = 0; k < K4_T / 4; k++) cnt[k] = 0;
+		for (u32 w0 = 0; w0 < wl; w0 += K4_WCH) {
+			const u32 wn = min((u32)K4_WCH, wl - w0);
+			for (u32 e = threadIdx.x; e < wn * K4_T; e += K_THREADS) {
+				const u32 w = e / K4_T, x = e % K4_T;
+				const u32 xa = ta * K4_T + x, xb = tb * K4_T + x;
+				sa[w][x] = xa < mpad ? S.bits[(size_t)(w0 + w) * mpad + xa] : 0;
+				sb[w][x] = xb < mpad ? S.bits[(size_t)(w0 + w) * mpad + xb] : 0;
+			}
+			__syncthreads();
+			for (u32 w = 0; w < wn; w++) {
+				const u64 bj = sb[w][j];
+#pragma unroll
+				for (int k = 0; k < K4_T / 4; k++) cnt[k] += __popcll(sa[w][i0 + 4 * k] & bj);
+			}
+			__syncthreads();
+		}
+		const u32 b = tb * K4_T + j;
+#pragma unroll
+		for (int k = 0; k < K4_T / 4; k++) {
+			const u32 a = ta * K4_T + i0 + 4 * k;
+			if (a < b && b < M && cnt[k] >= thr) k4_push_survivor(S, a, b);
+		}
+	}
+}
+
+// Containment test, one warp per surviving pair: the pair is adjacent iff no third new row contains
+// inc(a) & inc(b) (edge_test, bslv_poly.c:487-505).  Lanes scan 32 candidate rows per step; only the
+// non-zero words of the mask are compared (a mask holds >= d-2 bits, rarely more than a few words).
+#define K4_NZ 8
+__global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
+{
+	const CutCtl *c = S.ctl;
+	if (c->status & ST_SKIP_B) return;
+	if (c->n_surv > S.cap_pairs) return;             // overflow is flagged by k_adj_scan
+	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad, ns = c->n_surv;
+	const u32 lane = threadIdx.x & 31;
+	const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (u32 s = warp; s < ns; s += nwarps) {
+		const u32 a = S.surv_a[s], b = S.surv_b[s];
+		bool adjacent = true;
+		if (S.d != 1) {
+			u64 mw[K4_NZ];
+			u32 mi[K4_NZ], nz = 0;
+			bool generic = false;
+			for (u32 w0 = 0; w0 < wl && !generic; w0 += 32) {
+				const u32 w = w0 + lane;
+				const u64 m = w < wl ? (S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b]) : 0;
+				u32 bal = __ballot_sync(0xffffffffu, m != 0);
+				while (bal) {
+					const int src = __ffs(bal) - 1;
+					bal &= bal - 1;
+					const u64 mv = __shfl_sync(0xffffffffu, m, src);
+					if (nz < K4_NZ) { mw[nz] = mv; mi[nz] = w0 + src; }
+					nz++;
+				}
+				if (nz > K4_NZ) generic = true;
+			}
+			for (u32 x0 = 0; x0 < M; x0 += 32) {
+				const u32 x = x0 + lane;
+				bool cont = x < M && x != a && x != b;
+				if (cont) {
+					if (!generic) {
+#pragma unroll
+						for (int q = 0; q < K4_NZ; q++)
+							if (q < (int)nz && (S.bits[(size_t)mi[q] * mpad + x] & mw[q]) != mw[q]) cont = false;
+					} else {
+						for (u32 w = 0; w < wl && cont; w++) {
+							const u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];
+							cont = (S.bits[(size_t)w * mpad + x] & m) == m;
+						}
+					}
+				}
+				if (__any_sync(0xffffffffu, cont)) { adjacent = false; break; }
+			}
+		}
+		if (adjacent && lane == 0) k4_push_pair(S, a, b);
+	}
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_adj_scan(DevState S)
@@ -310,7 +460,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_adj_scan(DevState S)
 	__shared__ u32 ws[33];
 	CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_A) return;
-	if (c->n_pairs > S.cap_pairs) {
+	if (c->status & ST_OVF_BITS) return;
+	if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) {
 		if (threadIdx.x == 0) c->status |= ST_OVF_PAIRS;
 		return;
 	}
@@ -355,4 +506,125 @@ __global__ void k_finish(DevState S)
 	c->slot_cnt += c->n_new;
 	c->inc_used += c->inc_new;
 	c->adj_used += c->adj_new;
+}
+
+// ------------------------------------------------------------------ pack the delta for the host
+__global__ void __launch_bounds__(K_THREADS) k_pack_delta(DevState S, int header_only)
+{
+	CutCtl *c = S.ctl;
+	const StageLayout L = stage_layout(*c, S.d);
+	const bool fits = header_only || L.total <= S.cap_stage;
+	if (blockIdx.x == 0 && threadIdx.x < sizeof(CutCtl) / 4) {
+		u32 v = ((const u32 *)c)[threadIdx.x];
+		if (threadIdx.x == offsetof(CutCtl, status) / 4 && !fits) v |= ST_OVF_STAGE;
+		if (threadIdx.x == offsetof(CutCtl, stage_bytes) / 4) v = (u32)L.total;
+		((u32 *)S.stage)[threadIdx.x] = v;
+	}
+	if (header_only || !fits || (c->status & (ST_SKIP_B))) return;
+	const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
+	B200_GRID_STRIDE(e, n) pack_delta_item(S, L, e);
+}
+
+// ------------------------------------------------------------------ compaction of dead rows (GC)
+// Host slots are never reused (bslv_poly.c never compacts either, poly_defrag :296-312 is dead
+// code), but device rows are: once dead rows outnumber live ones the live rows are packed to the
+// front (stable, so rows stay sorted by slot), the two pools are repacked and adjacency entries
+// are renamed.  K1 then streams live coordinates only.
+struct LiveBitOf {
+	const u32 *live;
+	__device__ u32 operator()(u32 i) const { return (live[i >> 5] >> (i & 31)) & 1u; }
+};
+struct LenOfOld {
+	const u32 *len, *old_of;
+	__device__ u32 operator()(u32 i) const { return len[old_of[i]]; }
+};
+
+// exclusive scan of f(0..n) in three launches: tile sums, scan of tile sums, tile-local scan
+template <class F> __global__ void __launch_bounds__(K_THREADS) k_gscan_reduce(F f, u32 n, u32 *tile_sum)
+{
+	__shared__ u32 red[K_THREADS / 32];
+	const u32 base = blockIdx.x * B200_TILE + threadIdx.x * 8;
+	u32 s = 0;
+#pragma unroll
+	for (int b = 0; b < 8; b++) s += (base + b < n) ? f(base + b) : 0;
+	s = __reduce_add_sync(0xffffffffu, s);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		u32 t = 0;
+		for (int w = 0; w < K_THREADS / 32; w++) t += red[w];
+		tile_sum[blockIdx.x] = t;
+	}
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_gscan_tiles(const u32 *tile_sum, u32 ntiles, u32 *tile_base, u32 *total)
+{
+	__shared__ u32 ws[33];
+	u32 carry = 0;
+	for (u32 base = 0; base < ntiles; base += SCAN_THREADS) {
+		u32 i = base + threadIdx.x, v = i < ntiles ? tile_sum[i] : 0, tot;
+		u32 e = block_excl_scan(v, ws, tot);
+		if (i < ntiles) tile_base[i] = carry + e;
+		carry += tot;
+	}
+	if (threadIdx.x == 0) *total = carry;
+}
+template <class F> __global__ void __launch_bounds__(K_THREADS) k_gscan_apply(F f, u32 n, const u32 *tile_base, u32 *out)
+{
+	__shared__ u32 ws[33];
+	const u32 base = blockIdx.x * B200_TILE + threadIdx.x * 8;
+	u32 v[8], s = 0;
+#pragma unroll
+	for (int b = 0; b < 8; b++) { v[b] = (base + b < n) ? f(base + b) : 0; s += v[b]; }
+	u32 tot, e = block_excl_scan(s, ws, tot);
+	u32 run = tile_base[blockIdx.x] + e;
+#pragma unroll
+	for (int b = 0; b < 8; b++) {
+		if (base + b < n) out[base + b] = run;
+		run += v[b];
+	}
+}
+
+__global__ void __launch_bounds__(K_THREADS) k_gc_invert(const u32 *live, const u32 *remap, u32 nrows, u32 *old_of)
+{
+	B200_GRID_STRIDE(r, nrows)
+		if ((live[r >> 5] >> (r & 31)) & 1u) old_of[remap[r]] = (u32)r;
+}
+
+struct GcTarget {      // the fresh persistent arrays the live rows are gathered into
+	double *coord;
+	u32 *row_slot, *root, *live, *ideal, *inc_off, *inc_len, *adj_off, *adj_len, *inc_pool, *adj_pool;
+};
+// one thread per NEW row (blockDim multiple of 32 so a warp owns one word of the bitsets)
+__global__ void __launch_bounds__(K_THREADS) k_gc_gather(DevState S, GcTarget T, u32 n_live, const u32 *remap,
+                                                         const u32 *old_of, const u32 *new_inc_off, const u32 *new_adj_off)
+{
+	const size_t cap = S.cap_rows;
+	const u32 npad = (n_live + 31) & ~31u;
+	B200_GRID_STRIDE(n, npad) {
+		const bool in = n < n_live;
+		const u32 o = in ? old_of[n] : 0;
+		const u32 idl = __ballot_sync(0xffffffffu, in && ((S.ideal[o >> 5] >> (o & 31)) & 1u));
+		const u32 liv = __ballot_sync(0xffffffffu, in);
+		if ((threadIdx.x & 31) == 0) { T.ideal[n >> 5] = idl; T.live[n >> 5] = liv; }
+		if (!in) continue;
+		for (int j = 0; j < S.d; j++) T.coord[j * cap + n] = S.coord[j * cap + o];
+		T.row_slot[n] = S.row_slot[o];
+		T.root[n] = S.root[o];
+		const u32 il = S.inc_len[o], io = S.inc_off[o], ni = new_inc_off[n];
+		T.inc_off[n] = ni;
+		T.inc_len[n] = il;
+		for (u32 q = 0; q < il; q++) T.inc_pool[ni + q] = S.inc_pool[io + q];
+		const u32 al = S.adj_len[o], ao = S.adj_off[o], na = new_adj_off[n];
+		T.adj_off[n] = na;
+		T.adj_len[n] = al;
+		for (u32 q = 0; q < al; q++) T.adj_pool[na + q] = remap[S.adj_pool[ao + q]];
+	}
+}
+__global__ void k_gc_finish(DevState S, u32 n_live, const u32 *inc_total, const u32 *adj_total)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	S.ctl->nrows = n_live;
+	S.ctl->n_live = n_live;
+	S.ctl->inc_used = *inc_total;
+	S.ctl->adj_used = *adj_total;
 }

@@ -37,10 +37,12 @@ enum : u32 {
 	ST_OVF_PADJ = 8u,       // PLUS-neighbour scratch too small (idem)
 	ST_OVF_PAIRS = 16u,     // K4 pair buffer too small        (K4 is re-runnable)
 	ST_OVF_ADJ = 32u,       // adjacency pool too small        (adjacency build is re-runnable)
-	ST_ERR_DEGENERATE = 64u // an incidence list exceeds B200_MAXINC
+	ST_ERR_DEGENERATE = 64u,// an incidence list exceeds B200_MAXINC
+	ST_OVF_BITS = 128u,     // K4 bit matrix too small         (K4 is re-runnable)
+	ST_OVF_STAGE = 256u     // delta staging buffer too small  (packing is re-runnable)
 };
 #define ST_OVF_A (ST_OVF_ROWS | ST_OVF_INC | ST_OVF_PADJ)
-#define ST_OVF_B (ST_OVF_PAIRS | ST_OVF_ADJ)
+#define ST_OVF_B (ST_OVF_PAIRS | ST_OVF_ADJ | ST_OVF_BITS)
 
 // The halfspace of the current cut, h.x >= alpha (alpha replaced by 0 for ideal vertices), with
 // the reference's three thresholds pre-added in FP64 exactly as bslv_poly.c:126,573,596,666 does.
@@ -52,7 +54,7 @@ struct CutParams {
 	double lo[2];   // thr - 1e-9
 	double hh;      // sum h_j^2, left to right (bslv_poly.c:668-670)
 	u32 facet;      // id of the new facet = dual slot of this halfspace
-	u32 pad;
+	u32 batch_first; // primal.cnt when the host mirror was last coherent (sltn inheritance roots, bslv_poly.c:583-587)
 };
 
 // Counters shared by the kernels of one cut; the host reads it back once per cut.
@@ -76,14 +78,23 @@ struct CutCtl {
 	u32 n_dead_facets;
 	u32 n_live_scanned; // live rows classified by K1
 	u32 min_strict_slot;
-	u32 reserved[3];
+	// K4 (bitset form)
+	u32 n_local;        // distinct facets (other than the new one) met on the new facet's vertices
+	u32 wl;             // 64-bit words per bit-matrix row = ceil(n_local/64)
+	u32 mpad;           // n_new rounded up to 32: column stride of the word-major bit matrix
+	u32 n_surv;         // pairs that pass the AND+POPC filter
+	u32 stage_bytes;    // size of the packed delta record (header included)
+	u32 reserved[2];
 };
+#define B200_STAGE_HDR 128u   // the packed delta starts with a copy of CutCtl, padded to this size
 
 struct DevState {
 	int d;
 	u32 cap_rows, cap_inc, cap_adj, cap_facets, cap_padj, cap_pairs, cap_tiles;
+	u64 cap_bits;
 	double *coord;
 	u32 *row_slot, *live, *ideal;
+	u32 *root;           // per row: slot (< batch_first) whose sltn flag / pre-image this row inherits, or NONE
 	u32 *inc_off, *inc_len, *adj_off, *adj_len;
 	u32 *inc_pool, *adj_pool;
 	u32 *facet_cnt, *facet_alive;
@@ -94,9 +105,14 @@ struct DevState {
 	u32 *cnt3, *base3;   // [3*cap_rows] (new rows, incidence entries, PLUS neighbours) per visited row
 	u32 *padj;           // [cap_padj] PLUS neighbours of the new rows
 	u32 *new_padj_off, *new_padj_len, *new_parent, *deg, *adj_fill, *adj_base; // [cap_rows], by new-row index
-	u32 *pair_a, *pair_b; // [cap_pairs]
+	u32 *pair_a, *pair_b; // [cap_pairs] adjacent pairs (new-row indices)
+	u32 *surv_a, *surv_b; // [cap_pairs] pairs that passed the popcount filter
+	u32 *facet_epoch, *facet_local; // [cap_facets] K4 column relabelling, valid where epoch == facet+1
+	u64 *bits;            // [cap_bits] K4 incidence bit matrix, word-major: bits[w*mpad + new_row]
 	u32 *dead_slots;     // [cap_rows] by visited index
 	u32 *dead_facets;    // [cap_facets]
+	unsigned char *stage; // [cap_stage] packed per-cut delta: header | coords AoS | parent | ideal | dead slots | dead facets
+	u64 cap_stage;
 	CutCtl *ctl;
 	CutParams *cur;
 };

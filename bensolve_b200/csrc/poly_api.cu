@@ -239,6 +239,7 @@ extern "C" int poly__add_vrtx(poly_args *args)
 	}
 	CutParams P;
 	make_params(hp, d, (u32)f, P);
+	P.batch_first = (u32)args->primal.cnt;
 	CutDelta dl;
 	h->engine->cut(P, dl);
 	if (dl.redundant) {                                                  // (:132-136)
@@ -716,23 +717,126 @@ extern "C" int b200_poly_set_flags(poly_args *a, unsigned flags)
 	return 0;
 }
 
-extern "C" long b200_poly_add_batch(poly_args *a, const double *vals, const unsigned char *ideal, size_t n, int *rc_out)
+// Rebuild the host mirror in bulk after a device-resident batch (the per-cut deltas were never
+// transferred): used/ideal bits and coordinates of every slot created since `first_slot`, dead
+// bits of older slots, sltn inheritance through the device-side root journal, dual.used.
+static void rebuild_mirror(poly_args *a, Handle *h, size_t first_slot)
 {
-	long cuts = 0;
-	for (size_t i = 0; i < n; i++) {
-		for (size_t j = 0; j < a->dim; j++) a->val[j] = vals[i * a->dim + j];
-		a->ideal = ideal ? ideal[i] : 0;
-		const int rc = poly__add_vrtx(a);
-		if (rc_out) rc_out[i] = rc;
-		cuts += (rc == EXIT_SUCCESS);
+	polytope *P = &a->primal, *D = &a->dual;
+	const size_t d = a->dim;
+	MirrorDump m;
+	h->engine->download_mirror(m, (u32)D->cnt);
+	mirror_reserve(P, m.slot_cnt);
+	for (size_t s = P->cnt; s < m.slot_cnt; s++) { UNST_BT(P->used, s); UNST_BT(P->ideal, s); UNST_BT(P->sltn, s); }
+	P->cnt = m.slot_cnt;
+	for (size_t w = 0; w < (P->cnt + BTCNT - 1) / BTCNT; w++) P->used[w] = 0;
+	for (u32 r = 0; r < m.nrows; r++) {
+		if (!((m.live_words[r >> 5] >> (r & 31)) & 1u)) continue;
+		const size_t s = m.row_slot[r];
+		ST_BT(P->used, s);
+		if (s < first_slot) continue;
+		for (size_t j = 0; j < d; j++) P->data[s * d + j] = m.coords_soa[j * m.nrows + r];
+		if ((m.ideal_words[r >> 5] >> (r & 31)) & 1u) ST_BT(P->ideal, s);
+		const u32 root = m.root[r];
+		if (root != B200_NONE && IS_ELEM(P->sltn, root)) {
+			ST_BT(P->sltn, s);
+			memcpy(P->data_primg + s * P->dim_primg, P->data_primg + (size_t)root * P->dim_primg, P->dim_primg * sizeof(double));
+		}
 	}
-	return cuts;
+	for (size_t f = 0; f < D->cnt; f++) {
+		if (m.facet_alive[f]) ST_BT(D->used, f);
+		else UNST_BT(D->used, f);
+	}
+	h->lists_current = false;
 }
 
-extern "C" long b200_poly_add_batch_device(poly_args *, const double *, const unsigned char *, size_t, int *)
+extern "C" long b200_poly_add_batch_device(poly_args *a, const double *d_vals, const unsigned char *d_ideal, size_t n, int *rc_out)
 {
-	b200_set_error("b200_poly_add_batch_device: not implemented yet");
-	return -1;
+	GUARD_BEGIN
+	Handle *h = handle_of(&a->primal);
+	if (!a->init_data.intlsd || !h->engine) { b200_set_error("b200_poly_add_batch_device: call poly__intl_apprx first"); return -1; }
+	if ((void (*)(double *, int, double *))a->dualV2primalH != default_dual_to_halfspace) {
+		b200_set_error("b200_poly_add_batch_device: only the default dual->halfspace callback (cone_polar) is evaluated on the device");
+		return -1;
+	}
+	if (a->dim_primg_dl) { b200_set_error("b200_poly_add_batch_device: dual pre-images are not supported in batch mode"); return -1; }
+	polytope *D = &a->dual;
+	const size_t d = a->dim, first_slot = a->primal.cnt, f0 = D->cnt;
+	if (h->host_may_have_edited) {
+		h->engine->reupload_coords(a->primal.data, a->primal.cnt);
+		h->host_may_have_edited = false;
+	}
+	long cuts = 0;
+	for (size_t i = 0; i < n; i++) {
+		const size_t f = mirror_append(D);
+		const int rc = h->engine->cut_from_device(d_vals, d_ideal, i, (u32)f, (u32)first_slot);
+		if (rc_out) rc_out[i] = rc;
+		cuts += (rc == 0);
+	}
+	// dual rows: the points themselves (host copy of the device inputs) and their ideal flags
+	std::vector<double> hv(n * d);
+	std::vector<unsigned char> hi(n, 0);
+	h->engine->device_download(hv.data(), d_vals, n * d * sizeof(double));
+	if (d_ideal) h->engine->device_download(hi.data(), d_ideal, n);
+	for (size_t i = 0; i < n; i++) {
+		memcpy(D->data + (f0 + i) * d, hv.data() + i * d, d * sizeof(double));
+		if (hi[i]) ST_BT(D->ideal, f0 + i);
+	}
+	rebuild_mirror(a, h, first_slot);
+	a->idx = a->primal.cnt;
+	return cuts;
+	GUARD_END("b200_poly_add_batch_device")
+}
+
+extern "C" long b200_poly_add_batch(poly_args *a, const double *vals, const unsigned char *ideal, size_t n, int *rc_out)
+{
+	GUARD_BEGIN
+	Handle *h = handle_of(&a->primal);
+	const bool device_path = a->init_data.intlsd && h->engine && !a->dim_primg_dl &&
+	                         (void (*)(double *, int, double *))a->dualV2primalH == default_dual_to_halfspace;
+	if (!device_path) {                      // generic callback / not yet initialised: one call per halfspace
+		long cuts = 0;
+		for (size_t i = 0; i < n; i++) {
+			for (size_t j = 0; j < a->dim; j++) a->val[j] = vals[i * a->dim + j];
+			a->ideal = ideal ? ideal[i] : 0;
+			const int rc = poly__add_vrtx(a);
+			if (rc_out) rc_out[i] = rc;
+			cuts += (rc == EXIT_SUCCESS);
+		}
+		return cuts;
+	}
+	double *dv = (double *)h->engine->device_alloc(n * a->dim * sizeof(double));
+	unsigned char *di = ideal ? (unsigned char *)h->engine->device_alloc(n) : nullptr;
+	h->engine->device_upload(dv, vals, n * a->dim * sizeof(double));
+	if (ideal) h->engine->device_upload(di, ideal, n);
+	const long cuts = b200_poly_add_batch_device(a, dv, di, n, rc_out);
+	h->engine->device_free(dv);
+	h->engine->device_free(di);
+	return cuts;
+	GUARD_END("b200_poly_add_batch")
+}
+
+extern "C" int b200_poly_reserve(poly_args *a, size_t vertices, size_t incidence_entries, size_t adjacency_entries)
+{
+	GUARD_BEGIN
+	Handle *h = handle_of(&a->primal);
+	if (!h->engine) h->engine = new CutEngine((int)a->dim);
+	h->engine->reserve(vertices, incidence_entries, adjacency_entries);
+	mirror_reserve(&a->primal, vertices);
+	return 0;
+	GUARD_END("b200_poly_reserve")
+}
+
+extern "C" double b200_poly_classify_bench(poly_args *a, const double *hp, int iters, int flush_l2)
+{
+	GUARD_BEGIN
+	Handle *h = handle_of(&a->primal);
+	if (!h->engine) return -1.0;
+	CutParams P;
+	make_params(hp, a->dim, (u32)a->dual.cnt, P);     // an id one past the last facet: scratch only
+	P.batch_first = (u32)a->primal.cnt;
+	return h->engine->classify_bench(P, iters, flush_l2);
+	GUARD_END("b200_poly_classify_bench")
 }
 
 extern "C" int b200_set_device(int device) { return b200_select_device(device); }

@@ -121,3 +121,19 @@ def replay(engine, trace: Trace, upto: int | None = None, on_cut=None):
         if on_cut is not None:
             on_cut(i, rc)
     return rcs
+
+
+def replay_batched(engine, trace: Trace, chunk: int = 0):
+    """Same trace through the batch entry point b200_poly_add_batch (device-resident runs of
+    `chunk` halfspaces; 0 = everything after initialisation in one call)."""
+    for i in range(trace.n_init):
+        engine.add(trace.vals[i], int(trace.ideal[i]))
+    if engine.init_approx():
+        raise RuntimeError(f"poly__intl_apprx failed on trace {trace.name}")
+    rest = np.arange(trace.n_init, len(trace))
+    rcs = []
+    step = chunk if chunk > 0 else max(1, len(rest))
+    for s in range(0, len(rest), step):
+        idx = rest[s:s + step]
+        rcs += engine.add_batch(trace.vals[idx], trace.ideal[idx])
+    return rcs

@@ -116,6 +116,15 @@ long b200_poly_add_batch(poly_args *, const double *vals, const unsigned char *i
 /* Same with the dual points already resident in HBM (device pointer, row-major [n][dim]). */
 long b200_poly_add_batch_device(poly_args *, const double *d_vals, const unsigned char *d_ideal, size_t n, int *rc_out);
 
+/* Pre-size device and host storage (vertices ever created, incidence and adjacency entries) so
+ * that no re-allocation happens inside a timed region.  May be called right after poly__initialise. */
+int b200_poly_reserve(poly_args *, size_t vertices, size_t incidence_entries, size_t adjacency_entries);
+
+/* Measurement hook: launch K1 (classify) alone `iters` times against halfspace hp[dim+1] without
+ * mutating the polytope, flushing L2 before each launch when flush_l2 != 0.  Returns the mean
+ * CUDA-event time of one launch in milliseconds (< 0 on error). */
+double b200_poly_classify_bench(poly_args *, const double *hp, int iters, int flush_l2);
+
 /* Cumulative statistics of one engine since poly__initialise. */
 typedef struct {
 	uint64_t cuts;             /* non-redundant poly__add_vrtx calls */

@@ -41,10 +41,10 @@ def check_against_golden(lib, path):
     assert same.all(), "coordinates are not bit-identical to the reference's"
 
 
-def run_pair(lib_a, lib_b, tr, stepwise=False, exact=True):
+def run_pair(lib_a, lib_b, tr, stepwise=False, exact=True, flags_b=0):
     """Replay one trace into two engines; compare rc sequences and canonical state (after every
     cut when stepwise)."""
-    a, b = capi.PolyEngine(lib_a, tr.dim), capi.PolyEngine(lib_b, tr.dim)
+    a, b = capi.PolyEngine(lib_a, tr.dim), capi.PolyEngine(lib_b, tr.dim, flags=flags_b)
     try:
         if not stepwise:
             ra, rb = P.replay(a, tr), P.replay(b, tr)

@@ -44,26 +44,23 @@ def test_gpu_matches_checker_medium(product_lib, checker, tr):
 
 
 def _check_invariants(s, tr, rcs, simple=True):
-    """Size-independent properties: every live vertex satisfies every halfspace,
-    is tight on exactly its incident facets, adjacency is symmetric; simple polytopes have exactly
-    d facets and d neighbours per vertex."""
+    """Size-independent properties: every live vertex satisfies every halfspace and
+    is tight on its incident facets, adjacency is symmetric; simple polytopes have exactly d facets
+    and d neighbours per vertex.  Assumes n_init == dim and a generic trace, so that halfspace i
+    is dual slot i+1 (slot 0 is the facet at infinity)."""
     d = tr.dim
     n_v = len(s.incidence)
-    h = tr.vals                                  # halfspace h.y >= -1 (default callback)
-    vals = s.coords @ h.T                        # [n_v, n_h]
+    vals = s.coords @ tr.vals.T                  # halfspace i: vals[:, i] >= -1 (default callback)
     assert (vals >= -1 - 1e-7).all(), "a vertex violates a halfspace"
-    for i in range(0, n_v, max(1, n_v // 500)):
-        for f in s.incidence[i]:
-            hs = f - 1 if f - 1 < len(tr) else None      # dual slot f (>=1) <-> halfspace index (generic traces)
-            if hs is not None and f >= 1:
-                pass
+    for i in range(n_v):
         if simple:
             assert len(s.incidence[i]) == d and len(s.adjacency[i]) == d
+        for f in s.incidence[i]:
+            assert f >= 1 and abs(vals[i, f - 1] + 1.0) < 1e-7, "vertex not on an incident facet"
+    for i in range(0, n_v, max(1, n_v // 2000)):
         for j in s.adjacency[i]:
             assert i in s.adjacency[j]
-    tight = np.isclose(vals, -1.0, atol=1e-7).sum(axis=1)
-    if simple:
-        assert (tight == d).all()
+            assert len(set(s.incidence[i]) & set(s.incidence[j])) >= d - 1
 
 
 def test_gpu_large_tangent_properties_and_reference(product_lib, checker):
@@ -155,3 +152,41 @@ def test_gpu_dual_adjacency_and_polyck(product_lib, checker, capfd):
     assert adj[0] == adj[1]
     err = capfd.readouterr().err
     assert "appears in vertex'" not in err and "are adjacent" not in err
+
+
+FLAG_EAGER_GC = 2   # compact device rows after every cut that killed a vertex
+
+
+@pytest.mark.parametrize("tr", stepwise_traces(), ids=lambda t: t.name)
+def test_gpu_row_compaction_after_every_cut(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, stepwise=True, exact=True, flags_b=FLAG_EAGER_GC)
+
+
+@pytest.mark.parametrize("tr", medium_traces(), ids=lambda t: t.name)
+def test_gpu_row_compaction_medium(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, exact=True, flags_b=FLAG_EAGER_GC)
+
+
+@pytest.mark.parametrize("tr", small_traces()[::2] + medium_traces()[:3], ids=lambda t: t.name)
+@pytest.mark.parametrize("chunk", [0, 7])
+def test_gpu_batch_entry_point(product_lib, checker, tr, chunk):
+    """Device-resident batch path (halfspaces built on the device, header-only readback, bulk mirror
+    rebuild) against the checker fed one halfspace per call."""
+    a, b = capi.PolyEngine(checker, tr.dim), capi.PolyEngine(product_lib, tr.dim, flags=FLAG_EAGER_GC if chunk else 0)
+    ra, rb = P.replay(a, tr), P.replay_batched(b, tr, chunk)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+
+
+def test_gpu_reserve_then_run(product_lib, oracle_lib):
+    tr = P.tangent_polytope(5, 120, 5)
+    a, b = capi.PolyEngine(oracle_lib, 5), capi.PolyEngine(product_lib, 5)
+    assert b.reserve(200000, 1 << 20, 1 << 20) == 0
+    ra, rb = P.replay(a, tr), P.replay(b, tr)
+    assert ra == rb
+    capi.compare_states(a.state(), b.state(), exact_coords=True)
+    st = b.stats()
+    assert st["cuts"] == len(tr) - 5 - sum(rb) and st["vertex_evals"] > 0 and st["kernel_launches"] > 0
+    a.kill(); b.kill()

@@ -175,3 +175,48 @@ def test_polyck_silent(emul_lib, capfd):
     e.kill()
     err = capfd.readouterr().err
     assert "appears in vertex'" not in err and "are adjacent" not in err and "Hyperplane" not in err.replace("Hyperplane 0 ", "")
+
+
+FLAG_EAGER_GC = 2   # compact device rows after every cut that killed a vertex
+
+
+@pytest.mark.parametrize("tr", stepwise_traces(), ids=lambda t: t.name)
+def test_host_logic_row_compaction_after_every_cut(ref_lib, emul_lib, tr):
+    run_pair(ref_lib, emul_lib, tr, stepwise=True, exact=True, flags_b=FLAG_EAGER_GC)
+
+
+@pytest.mark.parametrize("tr", medium_traces()[:4], ids=lambda t: t.name)
+def test_host_logic_row_compaction_medium(oracle_lib, emul_lib, tr):
+    run_pair(oracle_lib, emul_lib, tr, exact=True, flags_b=FLAG_EAGER_GC)
+
+
+@pytest.mark.parametrize("tr", small_traces()[::2], ids=lambda t: t.name)
+@pytest.mark.parametrize("chunk", [0, 7])
+def test_host_logic_batch_entry_point(ref_lib, emul_lib, tr, chunk):
+    """b200_poly_add_batch (no per-cut delta; mirror rebuilt in bulk) against one call per halfspace."""
+    a, b = capi.PolyEngine(ref_lib, tr.dim), capi.PolyEngine(emul_lib, tr.dim, flags=FLAG_EAGER_GC if chunk else 0)
+    ra, rb = P.replay(a, tr), P.replay_batched(b, tr, chunk)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+
+
+def test_host_logic_batch_inherits_sltn(ref_lib, emul_lib):
+    tr = P.cube_with_cuts(4)
+    states = []
+    for lib, batched in ((ref_lib, False), (emul_lib, True)):
+        e = capi.PolyEngine(lib, 4)
+        P.replay(e, tr, upto=8)
+        for _ in range(12):
+            rc, idx, _, _ = e.get_vrtx()
+            e.mark_solution(idx)
+        if batched:
+            e.add_batch(tr.vals[8:], tr.ideal[8:])
+        else:
+            for i in range(8, len(tr)):
+                e.add(tr.vals[i], 0)
+        states.append(e.state())
+        e.kill()
+    capi.compare_states(states[0], states[1], exact_coords=True)
+    assert 0 < states[1].sltn.sum() < len(states[1].sltn)
