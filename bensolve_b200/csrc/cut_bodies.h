@@ -19,6 +19,7 @@
 #define B200_ATOMIC_AND(p, v) atomicAnd((p), (v))
 #define B200_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define B200_ATOMIC_EXCH(p, v) atomicExch((p), (v))
+#define B200_ATOMIC_OR64(p, v) atomicOr((unsigned long long *)(p), (unsigned long long)(v))
 #else // host compilation pass (must be built with -ffp-contract=off)
 #define B200_MUL(a, b) ((a) * (b))
 #define B200_ADD(a, b) ((a) + (b))
@@ -36,9 +37,18 @@ static inline u32 b200_exch(u32 *p, u32 v) { u32 o = *p; *p = v; return o; }
 #define B200_ATOMIC_AND(p, v) b200_fetch_and((p), (v))
 #define B200_ATOMIC_MIN(p, v) b200_fetch_min((p), (v))
 #define B200_ATOMIC_EXCH(p, v) b200_exch((p), (v))
+#define B200_ATOMIC_OR64(p, v) (*(p) |= (v))
 #endif
 
 B200_HD bool bit_test(const u32 *w, u32 i) { return (w[i >> 5] >> (i & 31)) & 1u; }
+B200_HD u32 popc64(u64 x)
+{
+#if defined(__CUDA_ARCH__)
+	return (u32)__popcll(x);
+#else
+	return (u32)__builtin_popcountll(x);
+#endif
+}
 
 // h . x for device row r, strict left-to-right from 0 (bslv_poly.c:123-125, 569-571, 593-595)
 B200_HD double row_dot(const DevState &S, const double *h, u32 r)
@@ -165,127 +175,222 @@ B200_HD void rewire(const DevState &S, u32 k, u32 v, u32 nw)
 		if (S.adj_pool[off + q] == v) { S.adj_pool[off + q] = nw; return; }
 }
 
-// K3b + K5 for visited entry i: append its new rows (edge vertices, bslv_poly.c:597-627, or the
-// copy of an on-plane vertex, :573-588), their incidence lists (:634-665), rewire the PLUS
-// neighbours (:628-633) and retire the row itself (:568, :697-705).
-B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
+// ---- K3b pieces, shared by the vertex-serial form (emit_outputs) and the half-edge-parallel form
+
+// new vertex on the edge (v MINUS, k PLUS), SURVEY A.3 / bslv_poly.c:597-627 + incidence :634-665.
+// j = index among this cut's new rows, ipos = where its incidence list goes, pslot = its padj slot.
+B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 k, u32 j, u32 ipos, u32 pslot)
 {
-	u32 v = S.vis[i];
-	u8 c = S.cls[v];
-	if (!is_visited_class(c)) { S.dead_slots[i] = B200_NONE; return; }
-	CutCtl *ctl = S.ctl;
-	const u32 nrows = ctl->nrows, f = P.facet;
+	const CutCtl *ctl = S.ctl;
 	const size_t cap = S.cap_rows;
 	const int d = S.d;
-	u32 jrow = S.base3[3 * (size_t)i + 0];
-	u32 ipos = ctl->inc_used + S.base3[3 * (size_t)i + 1];
-	u32 ppos = S.base3[3 * (size_t)i + 2];
+	const u32 nw = ctl->nrows + j, f = P.facet;
+	const bool v_ideal = bit_test(S.ideal, v), k_ideal = bit_test(S.ideal, k);
+	const u32 rb = k_ideal ? v : k;           // base
+	const u32 rd = k_ideal ? k : v;           // direction source
+	const bool both = k_ideal && v_ideal, none = !k_ideal && !v_ideal;
+	double base[B200_MAXD], dir[B200_MAXD];
+	for (int t = 0; t < d; t++) {
+		base[t] = S.coord[t * cap + rb];
+		double dv = S.coord[t * cap + rd];
+		if (both) dv = B200_SUB(dv, S.coord[t * cap + v]);
+		else if (none) dv = B200_SUB(dv, S.coord[t * cap + k]);
+		dir[t] = dv;
+	}
+	double hb = B200_MUL(P.h[0], base[0]), hd = B200_MUL(P.h[0], dir[0]);
+	for (int t = 1; t < d; t++) {
+		hb = B200_ADD(hb, B200_MUL(P.h[t], base[t]));
+		hd = B200_ADD(hd, B200_MUL(P.h[t], dir[t]));
+	}
+	const double mu = B200_DIV(B200_SUB(both ? 0.0 : P.alpha, hb), hd);
+	for (int t = 0; t < d; t++) S.coord[t * cap + nw] = B200_ADD(base[t], B200_MUL(mu, dir[t]));
+	if (both) set_bit_atomic(S.ideal, nw);
+	set_bit_atomic(S.live, nw);
+	S.row_slot[nw] = ctl->slot_cnt + j;
+	S.new_parent[j] = B200_NONE;
+	S.root[nw] = B200_NONE;
+	S.deg[j] = 0;
+	S.new_padj_off[j] = pslot;
+	S.new_padj_len[j] = 1;
+	S.padj[pslot] = k;
+	rewire(S, k, v, nw);
+	// incidence {f} u (inc(k) n inc(v)), sorted; f is the largest facet id so far
+	const u32 *iv = S.inc_pool + S.inc_off[v], *ik = S.inc_pool + S.inc_off[k];
+	const u32 niv = S.inc_len[v], nik = S.inc_len[k];
+	u32 a = 0, b = 0, w = ipos;
+	while (a < niv && b < nik) {
+		const u32 x = iv[a], y = ik[b];
+		if (x == y) {
+			S.inc_pool[w++] = x;
+			B200_ATOMIC_ADD(&S.facet_cnt[x], 1u);
+		}
+		a += (x <= y);
+		b += (y <= x);
+	}
+	S.inc_pool[w++] = f;
+	B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
+	S.inc_off[nw] = ipos;
+	S.inc_len[nw] = w - ipos;
+}
+
+// which elements of inc(v) also lie in inc(k): bit a of mask <=> iv[a] in inc(k)   (bslv_poly.c:634-652)
+B200_HD void shared_facet_mask(const DevState &S, u32 v, u32 k, u64 mask[B200_MAXINC / 64])
+{
+	const u32 *iv = S.inc_pool + S.inc_off[v], *ik = S.inc_pool + S.inc_off[k];
+	const u32 niv = S.inc_len[v], nik = S.inc_len[k];
+	u32 a = 0, b = 0;
+	while (a < niv && a < B200_MAXINC && b < nik) {
+		const u32 x = iv[a], y = ik[b];
+		if (x == y) mask[a >> 6] |= (u64)1 << (a & 63);
+		a += (x <= y);
+		b += (y <= x);
+	}
+}
+
+// the copy of an on-plane vertex v (bslv_poly.c:573-588): same coordinates, incidence = the masked
+// part of inc(v) plus the new facet; its PLUS neighbours were attached separately.
+B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, u32 ipos, u32 pslot, u32 nplus,
+                           const u64 mask[B200_MAXINC / 64])
+{
+	const CutCtl *ctl = S.ctl;
+	const size_t cap = S.cap_rows;
+	const u32 nw = ctl->nrows + j, f = P.facet;
+	for (int t = 0; t < S.d; t++) S.coord[t * cap + nw] = S.coord[t * cap + v];
+	if (bit_test(S.ideal, v)) set_bit_atomic(S.ideal, nw);
+	set_bit_atomic(S.live, nw);
+	S.row_slot[nw] = ctl->slot_cnt + j;
+	S.new_parent[j] = S.row_slot[v];
+	S.root[nw] = S.row_slot[v] < P.batch_first ? S.row_slot[v] : S.root[v];
+	S.deg[j] = 0;
+	S.new_padj_off[j] = pslot;
+	S.new_padj_len[j] = nplus;
 	const u32 *iv = S.inc_pool + S.inc_off[v];
 	const u32 niv = S.inc_len[v];
-	const bool v_ideal = bit_test(S.ideal, v);
-	const u32 aoff = S.adj_off[v], an = S.adj_len[v];
+	u32 w = ipos;
+	for (u32 a = 0; a < niv && a < B200_MAXINC; a++)
+		if ((mask[a >> 6] >> (a & 63)) & 1) {
+			S.inc_pool[w++] = iv[a];
+			B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
+		}
+	S.inc_pool[w++] = f;
+	B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
+	S.inc_off[nw] = ipos;
+	S.inc_len[nw] = w - ipos;
+}
 
+// retire visited row v (bslv_poly.c:568, 679-688, 697-705): its facets lose one vertex
+B200_HD void retire_row(const DevState &S, u32 v, u32 i)
+{
+	const u32 *iv = S.inc_pool + S.inc_off[v];
+	clr_bit_atomic(S.live, v);
+	for (u32 a = 0, n = S.inc_len[v]; a < n; a++) B200_ATOMIC_SUB(&S.facet_cnt[iv[a]], 1u);
+	S.dead_slots[i] = S.row_slot[v];
+}
+
+// K3b + K5 for visited entry i, vertex-serial form (multi-kernel path and host test double)
+B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
+{
+	const u32 v = S.vis[i];
+	const u8 c = S.cls[v];
+	if (!is_visited_class(c)) { S.dead_slots[i] = B200_NONE; return; }
+	CutCtl *ctl = S.ctl;
+	const u32 jrow = S.base3[3 * (size_t)i + 0];
+	u32 ipos = ctl->inc_used + S.base3[3 * (size_t)i + 1];
+	const u32 ppos = S.base3[3 * (size_t)i + 2];
+	const u32 aoff = S.adj_off[v], an = S.adj_len[v];
+	u32 np = 0;
 	if (c == CLS_ZERO) {
-		const u32 j = jrow, nw = nrows + j;
-		for (int t = 0; t < d; t++) S.coord[t * cap + nw] = S.coord[t * cap + v];
-		if (v_ideal) set_bit_atomic(S.ideal, nw);
-		set_bit_atomic(S.live, nw);
-		S.row_slot[nw] = ctl->slot_cnt + j;
-		S.new_parent[j] = S.row_slot[v];
-		S.root[nw] = S.row_slot[v] < P.batch_first ? S.row_slot[v] : S.root[v];
-		S.deg[j] = 0;
-		S.new_padj_off[j] = ppos;
+		const u32 nw = ctl->nrows + jrow;
 		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
-		u32 np = 0;
 		for (u32 q = 0; q < an; q++) {
-			u32 k = S.adj_pool[aoff + q];
+			const u32 k = S.adj_pool[aoff + q];
 			if (S.cls[k] != CLS_PLUS) continue;
 			S.padj[ppos + np++] = k;
 			rewire(S, k, v, nw);
-			const u32 *ik = S.inc_pool + S.inc_off[k];
-			const u32 nik = S.inc_len[k];
-			u32 a = 0, b = 0;
-			while (a < niv && a < B200_MAXINC && b < nik) {
-				u32 x = iv[a], y = ik[b];
-				if (x == y) mask[a >> 6] |= (u64)1 << (a & 63);
-				a += (x <= y);
-				b += (y <= x);
-			}
+			shared_facet_mask(S, v, k, mask);
 		}
-		S.new_padj_len[j] = np;
-		u32 w = ipos;
-		for (u32 a = 0; a < niv && a < B200_MAXINC; a++)
-			if ((mask[a >> 6] >> (a & 63)) & 1) {
-				S.inc_pool[w++] = iv[a];
-				B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
-			}
-		S.inc_pool[w++] = f;                          // f is the largest facet id: list stays sorted
-		B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
-		S.inc_off[nw] = ipos;
-		S.inc_len[nw] = w - ipos;
+		emit_copy_row(S, P, v, jrow, ipos, ppos, np, mask);
 		B200_ATOMIC_ADD(&ctl->n_zero, 1u);
 	} else {
-		u32 np = 0;
 		for (u32 q = 0; q < an; q++) {
-			u32 k = S.adj_pool[aoff + q];
+			const u32 k = S.adj_pool[aoff + q];
 			if (S.cls[k] != CLS_PLUS) continue;
-			const u32 j = jrow + np, nw = nrows + j;
-			const bool k_ideal = bit_test(S.ideal, k);
-			// A.3: base + mu*dir with (base,dir) chosen by the ideal flags (bslv_poly.c:600-623)
-			const u32 rb = k_ideal ? v : k;           // base
-			const u32 rd = k_ideal ? k : v;           // direction source
-			const bool both = k_ideal && v_ideal, none = !k_ideal && !v_ideal;
-			double base[B200_MAXD], dir[B200_MAXD];
-			for (int t = 0; t < d; t++) {
-				base[t] = S.coord[t * cap + rb];
-				double dv = S.coord[t * cap + rd];
-				if (both) dv = B200_SUB(dv, S.coord[t * cap + v]);
-				else if (none) dv = B200_SUB(dv, S.coord[t * cap + k]);
-				dir[t] = dv;
-			}
-			double hb = B200_MUL(P.h[0], base[0]), hd = B200_MUL(P.h[0], dir[0]);
-			for (int t = 1; t < d; t++) {
-				hb = B200_ADD(hb, B200_MUL(P.h[t], base[t]));
-				hd = B200_ADD(hd, B200_MUL(P.h[t], dir[t]));
-			}
-			double mu = B200_DIV(B200_SUB(both ? 0.0 : P.alpha, hb), hd);
-			for (int t = 0; t < d; t++) S.coord[t * cap + nw] = B200_ADD(base[t], B200_MUL(mu, dir[t]));
-			if (both) set_bit_atomic(S.ideal, nw);
-			set_bit_atomic(S.live, nw);
-			S.row_slot[nw] = ctl->slot_cnt + j;
-			S.new_parent[j] = B200_NONE;
-			S.root[nw] = B200_NONE;
-			S.deg[j] = 0;
-			S.new_padj_off[j] = ppos + np;
-			S.new_padj_len[j] = 1;
-			S.padj[ppos + np] = k;
-			rewire(S, k, v, nw);
-			// incidence {f} u (inc(k) n inc(v)), sorted (bslv_poly.c:625-626, 634-665)
-			const u32 *ik = S.inc_pool + S.inc_off[k];
-			const u32 nik = S.inc_len[k];
-			u32 a = 0, b = 0, w = ipos;
-			while (a < niv && b < nik) {
-				u32 x = iv[a], y = ik[b];
-				if (x == y) {
-					S.inc_pool[w++] = x;
-					B200_ATOMIC_ADD(&S.facet_cnt[x], 1u);
-				}
-				a += (x <= y);
-				b += (y <= x);
-			}
-			S.inc_pool[w++] = f;
-			B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
-			S.inc_off[nw] = ipos;
-			S.inc_len[nw] = w - ipos;
-			ipos = w;
+			emit_edge_vertex(S, P, v, k, jrow + np, ipos, ppos + np);
+			ipos += S.inc_len[ctl->nrows + jrow + np];
 			np++;
 		}
 		B200_ATOMIC_ADD(&ctl->n_minus, 1u);
 	}
-	// retire v: its facets lose one vertex (bslv_poly.c:679-688, 697-705)
-	clr_bit_atomic(S.live, v);
-	for (u32 a = 0; a < niv; a++) B200_ATOMIC_SUB(&S.facet_cnt[iv[a]], 1u);
-	S.dead_slots[i] = S.row_slot[v];
+	retire_row(S, v, i);
+}
+
+// ---- half-edge-parallel form (tail kernels): one work item per (visited vertex, adjacency slot)
+B200_HD void he_owner_fill(const DevState &S, u32 i)
+{
+	for (u32 e = S.he_off[i]; e < S.he_off[i + 1]; e++) S.he_own[e] = i;
+}
+B200_HD void he_eval(const DevState &S, u32 e)
+{
+	const u32 i = S.he_own[e], v = S.vis[i], k = S.adj_pool[S.adj_off[v] + (e - S.he_off[i])];
+	const bool plus = S.cls[k] == CLS_PLUS;
+	S.he_flag[e] = plus ? 1 : 0;
+	S.he_inc[e] = 0;
+	if (!plus) return;
+	if (S.cls[v] == CLS_MINUS) {
+		S.he_inc[e] = 1 + isect_count(S.inc_pool + S.inc_off[v], S.inc_len[v], S.inc_pool + S.inc_off[k], S.inc_len[k]);
+	} else {
+		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
+		shared_facet_mask(S, v, k, mask);
+		for (int w = 0; w < B200_MAXINC / 64; w++)
+			if (mask[w]) B200_ATOMIC_OR64(&S.zmask[(size_t)i * (B200_MAXINC / 64) + w], mask[w]);
+	}
+}
+B200_HD void he_count(const DevState &S, u32 i)
+{
+	const u32 v = S.vis[i];
+	const u8 c = S.cls[v];
+	u32 n_out = 0, inc_sz = 0, nplus = 0;
+	if (is_visited_class(c)) {
+		for (u32 e = S.he_off[i]; e < S.he_off[i + 1]; e++) { nplus += S.he_flag[e]; inc_sz += S.he_inc[e]; }
+		if (c == CLS_ZERO) {
+			if (S.inc_len[v] > B200_MAXINC) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
+			n_out = 1;
+			inc_sz = 1;
+			for (int w = 0; w < B200_MAXINC / 64; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
+		} else
+			n_out = nplus;
+	}
+	S.cnt3[3 * (size_t)i + 0] = n_out;
+	S.cnt3[3 * (size_t)i + 1] = inc_sz;
+	S.cnt3[3 * (size_t)i + 2] = nplus;
+}
+B200_HD void he_emit(const DevState &S, const CutParams &P, u32 e)
+{
+	if (!S.he_flag[e]) return;
+	const u32 i = S.he_own[e], v = S.vis[i], e0 = S.he_off[i];
+	const u32 k = S.adj_pool[S.adj_off[v] + (e - e0)];
+	u32 rank = 0, incpre = 0;
+	for (u32 x = e0; x < e; x++) { rank += S.he_flag[x]; incpre += S.he_inc[x]; }
+	const u32 jrow = S.base3[3 * (size_t)i + 0], ibase = S.ctl->inc_used + S.base3[3 * (size_t)i + 1], ppos = S.base3[3 * (size_t)i + 2];
+	if (S.cls[v] == CLS_MINUS)
+		emit_edge_vertex(S, P, v, k, jrow + rank, ibase + incpre, ppos + rank);
+	else {
+		S.padj[ppos + rank] = k;
+		rewire(S, k, v, S.ctl->nrows + jrow);
+	}
+}
+B200_HD void he_finish_vertex(const DevState &S, const CutParams &P, u32 i)
+{
+	const u32 v = S.vis[i];
+	const u8 c = S.cls[v];
+	if (!is_visited_class(c)) { S.dead_slots[i] = B200_NONE; return; }
+	if (c == CLS_ZERO) {
+		emit_copy_row(S, P, v, S.base3[3 * (size_t)i + 0], S.ctl->inc_used + S.base3[3 * (size_t)i + 1], S.base3[3 * (size_t)i + 2],
+		              S.cnt3[3 * (size_t)i + 2], &S.zmask[(size_t)i * (B200_MAXINC / 64)]);
+		B200_ATOMIC_ADD(&S.ctl->n_zero, 1u);
+	} else
+		B200_ATOMIC_ADD(&S.ctl->n_minus, 1u);
+	retire_row(S, v, i);
 }
 
 // after all counts are final: a facet without live vertices dies (clean rule; the reference's
@@ -368,14 +473,6 @@ B200_HD void k4_build_row(const DevState &S, u32 j)
 		const u32 col = S.facet_local[fc];
 		S.bits[(size_t)(col >> 6) * mpad + j] |= (u64)1 << (col & 63);
 	}
-}
-B200_HD u32 popc64(u64 x)
-{
-#if defined(__CUDA_ARCH__)
-	return (u32)__popcll(x);
-#else
-	return (u32)__builtin_popcountll(x);
-#endif
 }
 B200_HD void k4_push_survivor(const DevState &S, u32 a, u32 b)
 {

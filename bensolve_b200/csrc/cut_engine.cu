@@ -124,6 +124,11 @@ CutEngine::CutEngine(int dim) : d_(dim)
 #endif
 	S_.ctl = (CutCtl *)dalloc(sizeof(CutCtl));
 	S_.cur = (CutParams *)dalloc(sizeof(CutParams));
+	S_.he_off = (u32 *)dalloc((B200_VIS_MAX + 1) * sizeof(u32));
+	S_.he_own = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
+	S_.he_inc = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
+	S_.he_flag = (u8 *)dalloc(B200_HE_CAP);
+	S_.zmask = (u64 *)dalloc((size_t)B200_VIS_MAX * (B200_MAXINC / 64) * sizeof(u64));
 	ensure_rows(4 * B200_TILE);
 	ensure_inc(1u << 16);
 	ensure_adj(1u << 16);
@@ -143,7 +148,7 @@ CutEngine::~CutEngine()
 	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
 	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.tile_list, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 #ifndef B200_EMULATE
 	for (int i = 0; i < 4; i++) if (ev_[i]) cudaEventDestroy((cudaEvent_t)ev_[i]);
@@ -191,6 +196,8 @@ void CutEngine::ensure_rows(u32 need)
 	S_.cap_tiles = cap / B200_TILE;
 	regrow(S_.tile_cnt, S_.cap_tiles, 0);
 	regrow(S_.tile_base, S_.cap_tiles, 0);
+	regrow(S_.tile_list, (size_t)S_.cap_tiles * B200_TLIST, 0);
+	small_dirty_ = true;
 	S_.cap_rows = cap;
 }
 void CutEngine::ensure_inc(u32 need)
@@ -303,7 +310,9 @@ void CutEngine::upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
 	hdr_.nrows = hdr_.slot_cnt = hdr_.n_live = n;
 	hdr_.inc_used = (u32)ipool.size();
 	hdr_.adj_used = (u32)apool.size();
+	hdr_.min_strict_row = B200_NONE;
 	h2d(S_.ctl, &hdr_, sizeof hdr_);
+	small_dirty_ = true;
 }
 
 // ------------------------------------------------------------------ the pipeline
@@ -326,6 +335,7 @@ void CutEngine::launch_classify_dim(int gcls)
 
 void CutEngine::launch_part_a(const CutParams &P)
 {
+	small_dirty_ = true;
 	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
 	const int gmap = num_sms_ * 4;
 	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
@@ -364,6 +374,50 @@ void CutEngine::launch_part_b(bool rerun)
 	CK(cudaGetLastError());
 }
 
+template <int D> static void launch_classify_lists(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, int grid, cudaStream_t st)
+{
+	if (dv) k_classify_lists<D, true><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi);
+	else k_classify_lists<D, false><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0);
+}
+
+// small-cut path: streaming K1 + single-CTA tail (+ multi-block K4 pair test for medium cuts)
+void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
+{
+	if (small_dirty_) {
+		CK(cudaMemsetAsync(S_.tile_cnt, 0, (size_t)S_.cap_tiles * 4, STREAM));
+		k_reset_small<<<1, 32, 0, STREAM>>>(S_);
+		small_dirty_ = false;
+		stats_.kernel_launches++;
+	}
+	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
+	const u32 groups = ntiles * ((d_ >= 2 && d_ <= 8) ? 1 : B200_TILE / (2 * K_THREADS));
+	const int g = (int)std::max<u32>(1, std::min<u32>(groups, (u32)num_sms_ * 8));
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
+	switch (d_) {
+	case 2: launch_classify_lists<2>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	case 3: launch_classify_lists<3>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	case 4: launch_classify_lists<4>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	case 5: launch_classify_lists<5>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	case 6: launch_classify_lists<6>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	case 7: launch_classify_lists<7>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	case 8: launch_classify_lists<8>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	default: launch_classify_lists<0>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
+	}
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
+	k_tail<<<1, TAIL_THREADS, 0, STREAM>>>(S_, mode, header_only ? 1 : 0);
+	stats_.kernel_launches += 2;
+	if (mode == 1) launch_k4_and_tail2(header_only);
+	CK(cudaGetLastError());
+}
+
+void CutEngine::launch_k4_and_tail2(bool header_only)
+{
+	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
+	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
+	k_tail2<<<1, TAIL_THREADS, 0, STREAM>>>(S_, header_only ? 1 : 0);
+	stats_.kernel_launches += 3;
+}
+
 void CutEngine::launch_part_c(bool header_only)
 {
 	k_pack_delta<<<header_only ? 1 : num_sms_ * 2, K_THREADS, 0, STREAM>>>(S_, header_only ? 1 : 0);
@@ -378,24 +432,28 @@ void CutEngine::fetch_delta()
 	CK(cudaMemcpyAsync(pinned_stage_, S_.stage, first, cudaMemcpyDeviceToHost, STREAM));
 	CK(cudaStreamSynchronize(STREAM));
 	memcpy(&hdr_, pinned_stage_, sizeof(CutCtl));
-	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE)) && hdr_.stage_bytes > first) {
+	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE | ST_NEED_BIG | ST_K4_PENDING)) && hdr_.stage_bytes > first) {
 		CK(cudaMemcpyAsync(pinned_stage_ + first, S_.stage + first, hdr_.stage_bytes - first, cudaMemcpyDeviceToHost, STREAM));
 		CK(cudaStreamSynchronize(STREAM));
 	}
 }
 #else // ---- host-side test double: same stage bodies, run serially
-void CutEngine::launch_part_a(const CutParams &Pin)
+static CutParams emu_params(const DevState &S, const CutParams &Pin, const double *dv, const unsigned char *di, u64 vi)
 {
-	DevState &S = S_;
-	CutCtl *c = S.ctl;
 	CutParams P = Pin;
-	if (dev_vals_) {
+	if (dv) {
 		double hh = 0;
-		for (int j = 0; j < B200_MAXD; j++) { const double v = j < S.d ? dev_vals_[dev_index_ * S.d + j] : 0.0; P.h[j] = v; hh += v * v; }
-		P.alpha = (dev_ideal_ && dev_ideal_[dev_index_]) ? 0.0 : -1.0;
+		for (int j = 0; j < B200_MAXD; j++) { const double v = j < S.d ? dv[vi * S.d + j] : 0.0; P.h[j] = v; hh += v * v; }
+		P.alpha = (di && di[vi]) ? 0.0 : -1.0;
 		for (int id = 0; id < 2; id++) { const double thr = id ? 0.0 : P.alpha; P.hi[id] = thr + 1e-9; P.mid[id] = thr + 1.0e-2 * 1e-9; P.lo[id] = thr - 1e-9; }
 		P.hh = hh;
 	}
+	return P;
+}
+// K1 + ordered compaction + decision; returns false when the cut ends here (redundant)
+static bool emu_classify(DevState &S, const CutParams &P)
+{
+	CutCtl *c = S.ctl;
 	*S.cur = P;
 	c->status = 0;
 	c->n_strict = 0;
@@ -415,17 +473,23 @@ void CutEngine::launch_part_a(const CutParams &Pin)
 		if (zp) c->n_zp++;
 		if (cl != CLS_PLUS) S.vis[c->n_vis++] = r;
 	}
-	if (c->n_strict == 0) { c->status |= ST_REDUNDANT; S.facet_alive[P.facet] = 0; return; }
+	if (c->n_strict == 0) { c->status |= ST_REDUNDANT; S.facet_alive[P.facet] = 0; return false; }
 	c->min_strict_slot = S.row_slot[c->min_strict_row];
-	if (c->n_zp) {
-		bool changed;
-		do {
-			changed = false;
-			for (u32 i = 0; i < c->n_vis; i++) changed |= zp_activate(S, P, i);
-		} while (changed);
-	}
-	for (u32 i = 0; i < c->n_vis; i++) count_outputs(S, i);
-	if (c->status & ST_ERR_DEGENERATE) return;
+	return true;
+}
+static void emu_zp(DevState &S, const CutParams &P)
+{
+	CutCtl *c = S.ctl;
+	if (!c->n_zp) return;
+	bool changed;
+	do {
+		changed = false;
+		for (u32 i = 0; i < c->n_vis; i++) changed |= zp_activate(S, P, i);
+	} while (changed);
+}
+static void emu_scan3_plan(DevState &S)
+{
+	CutCtl *c = S.ctl;
 	u32 carry[3] = {0, 0, 0};
 	for (u32 i = 0; i < c->n_vis; i++)
 		for (int k = 0; k < 3; k++) { S.base3[3 * (size_t)i + k] = carry[k]; carry[k] += S.cnt3[3 * (size_t)i + k]; }
@@ -433,26 +497,30 @@ void CutEngine::launch_part_a(const CutParams &Pin)
 	if ((u64)c->nrows + carry[0] > S.cap_rows) c->status |= ST_OVF_ROWS;
 	if ((u64)c->inc_used + carry[1] > S.cap_inc) c->status |= ST_OVF_INC;
 	if (carry[2] > S.cap_padj) c->status |= ST_OVF_PADJ;
-	if (c->status & ST_OVF_A) return;
-	for (u32 i = 0; i < c->n_vis; i++) emit_outputs(S, P, i);
-	for (u32 i = 0; i < c->n_vis; i++) collect_dead_facets(S, i);
 }
-void CutEngine::launch_part_b(bool rerun)
+static void emu_k4_matrix(DevState &S)
 {
-	DevState &S = S_;
 	CutCtl *c = S.ctl;
-	if (c->status & (ST_REDUNDANT | ST_OVF_A | ST_ERR_DEGENERATE)) return;
-	if (rerun) { c->n_pairs = c->n_surv = 0; c->status &= ~(u32)ST_OVF_B; for (u32 j = 0; j < c->n_new; j++) S.deg[j] = 0; }
-	const u32 M = c->n_new;
-	for (u32 j = 0; j < M; j++) k4_assign_columns(S, j);
+	for (u32 j = 0; j < c->n_new; j++) k4_assign_columns(S, j);
 	k4_plan(S);
 	if (c->status & ST_OVF_BITS) return;
-	for (u32 j = 0; j < M; j++) k4_build_row(S, j);
+	for (u32 j = 0; j < c->n_new; j++) k4_build_row(S, j);
+}
+static void emu_k4_pairs(DevState &S)
+{
+	CutCtl *c = S.ctl;
+	const u32 M = c->n_new;
 	for (u32 a = 0; a < M; a++)
 		for (u32 b = a + 1; b < M; b++) k4_filter_pair(S, a, b);
-	if (c->n_surv > S.cap_pairs) { c->status |= ST_OVF_PAIRS; return; }
+	if (c->n_surv > S.cap_pairs) return;
 	for (u32 s = 0; s < c->n_surv; s++) k4_contain_pair(S, s);
-	if (c->n_pairs > S.cap_pairs) { c->status |= ST_OVF_PAIRS; return; }
+}
+static void emu_adjacency_commit(DevState &S)
+{
+	CutCtl *c = S.ctl;
+	if (c->status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE)) return;
+	if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) { c->status |= ST_OVF_PAIRS; return; }
+	const u32 M = c->n_new;
 	u32 carry = 0;
 	for (u32 j = 0; j < M; j++) { S.adj_base[j] = carry; carry += S.new_padj_len[j] + S.deg[j]; }
 	c->adj_new = carry;
@@ -466,24 +534,102 @@ void CutEngine::launch_part_b(bool rerun)
 	c->inc_used += c->inc_new;
 	c->adj_used += c->adj_new;
 }
+
+void CutEngine::launch_part_a(const CutParams &Pin)
+{
+	DevState &S = S_;
+	CutCtl *c = S.ctl;
+	const CutParams P = emu_params(S, Pin, dev_vals_, dev_ideal_, dev_index_);
+	if (!emu_classify(S, P)) return;
+	emu_zp(S, P);
+	for (u32 i = 0; i < c->n_vis; i++) count_outputs(S, i);
+	if (c->status & ST_ERR_DEGENERATE) return;
+	emu_scan3_plan(S);
+	if (c->status & ST_OVF_A) return;
+	for (u32 i = 0; i < c->n_vis; i++) emit_outputs(S, P, i);
+	for (u32 i = 0; i < c->n_vis; i++) collect_dead_facets(S, i);
+}
+void CutEngine::launch_part_b(bool rerun)
+{
+	DevState &S = S_;
+	CutCtl *c = S.ctl;
+	if (c->status & (ST_REDUNDANT | ST_OVF_A | ST_ERR_DEGENERATE)) return;
+	if (rerun) { c->n_pairs = c->n_surv = 0; c->status &= ~(u32)ST_OVF_B; for (u32 j = 0; j < c->n_new; j++) S.deg[j] = 0; }
+	emu_k4_matrix(S);
+	if (c->status & ST_OVF_BITS) return;
+	emu_k4_pairs(S);
+	emu_adjacency_commit(S);
+}
 void CutEngine::launch_part_c(bool header_only)
 {
 	CutCtl *c = S_.ctl;
 	const StageLayout L = stage_layout(*c, S_.d);
 	CutCtl h = *c;
 	h.stage_bytes = (u32)L.total;
+	h.status |= emu_extra_status_;
+	emu_extra_status_ = 0;
 	if (!header_only && L.total > S_.cap_stage) h.status |= ST_OVF_STAGE;
 	memcpy(S_.stage, &h, sizeof h);
 	if (header_only || (h.status & ST_OVF_STAGE) || (c->status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE))) return;
 	const u64 n = (u64)c->n_new * S_.d + c->n_new + c->n_vis + c->n_dead_facets;
 	for (u64 e = 0; e < n; e++) pack_delta_item(S_, L, e);
 }
+// the single-CTA tail of the small-cut path, phase by phase (half-edge-parallel stage bodies)
+void CutEngine::launch_small(const CutParams &Pin, int mode, bool header_only)
+{
+	DevState &S = S_;
+	CutCtl *c = S.ctl;
+	const CutParams P = emu_params(S, Pin, dev_vals_, dev_ideal_, dev_index_);
+	if (!emu_classify(S, P)) { launch_part_c(header_only); return; }
+	if (c->n_vis > B200_VIS_MAX) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
+	emu_zp(S, P);
+	u32 H = 0;
+	for (u32 i = 0; i < c->n_vis; i++) {
+		const u32 r = S.vis[i];
+		S.he_off[i] = H;
+		H += is_visited_class(S.cls[r]) ? S.adj_len[r] : 0;
+		for (int w = 0; w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
+	}
+	S.he_off[c->n_vis] = H;
+	if (H > B200_HE_CAP) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
+	for (u32 i = 0; i < c->n_vis; i++) he_owner_fill(S, i);
+	for (u32 e = 0; e < H; e++) he_eval(S, e);
+	for (u32 i = 0; i < c->n_vis; i++) he_count(S, i);
+	emu_scan3_plan(S);
+	if (c->status & (ST_OVF_A | ST_ERR_DEGENERATE)) { launch_part_c(header_only); return; }
+	for (u32 e = H; e-- > 0;) he_emit(S, P, e);            // any order is valid: run it backwards here
+	for (u32 i = 0; i < c->n_vis; i++) he_finish_vertex(S, P, i);
+	for (u32 i = 0; i < c->n_vis; i++) collect_dead_facets(S, i);
+	emu_k4_matrix(S);
+	if (!(c->status & ST_OVF_BITS)) {
+		if (mode == 1) { launch_k4_and_tail2(header_only); return; }
+		if (c->n_new > B200_K4_SMALL) { emu_extra_status_ = ST_K4_PENDING; launch_part_c(true); return; }
+		emu_k4_pairs(S);
+	}
+	emu_adjacency_commit(S);
+	launch_part_c(header_only);
+}
+void CutEngine::launch_k4_and_tail2(bool header_only)
+{
+	if (!(S_.ctl->status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE))) emu_k4_pairs(S_);
+	emu_adjacency_commit(S_);
+	launch_part_c(header_only);
+}
 void CutEngine::fetch_delta()
 {
 	memcpy(&hdr_, S_.stage, sizeof(CutCtl));
-	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE))) memcpy(pinned_stage_, S_.stage, hdr_.stage_bytes);
+	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE | ST_NEED_BIG | ST_K4_PENDING))) memcpy(pinned_stage_, S_.stage, hdr_.stage_bytes);
 }
 #endif
+
+bool CutEngine::use_small_path() const
+{
+#ifndef B200_EMULATE
+	return true;
+#else
+	return (flags_ & 8) != 0;       // the test double runs the tail phases only when asked to
+#endif
+}
 
 void CutEngine::run_cut(const CutParams &P, bool header_only)
 {
@@ -497,28 +643,47 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 #ifndef B200_EMULATE
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[2], STREAM));
 #endif
-	launch_part_a(P);
-	launch_part_b(false);
-	launch_part_c(header_only);
+	const bool force_big = (flags_ & 4) != 0;
+	bool small = use_small_path() && !force_big && !prefer_big_;
+	auto launch_all = [&]() {
+		if (small) {
+			launch_small(P, expect_m_ > (B200_K4_SMALL * 3) / 4 ? 1 : 0, header_only);
+		} else {
+			launch_part_a(P);
+			launch_part_b(false);
+			launch_part_c(header_only);
+		}
+	};
+	launch_all();
 	fetch_delta();
-	for (int guard = 0; hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE); guard++) {
-		if (guard > 12) fail("bensolve_b200: capacity negotiation did not converge");
-		if (hdr_.status & ST_OVF_A) {
+	const u32 redo = ST_OVF_A | ST_OVF_B | ST_OVF_STAGE | ST_NEED_BIG | ST_K4_PENDING;
+	for (int guard = 0; hdr_.status & redo; guard++) {
+		if (guard > 16) fail("bensolve_b200: capacity negotiation did not converge");
+		if (hdr_.status & ST_NEED_BIG) {            // nothing was mutated: rerun through the multi-kernel path
+			small = false;
+			prefer_big_ = true;
+			launch_all();
+		} else if (hdr_.status & ST_K4_PENDING) {   // tail stopped before the pair test
+			launch_k4_and_tail2(header_only);
+		} else if (hdr_.status & ST_OVF_A) {
 			if (hdr_.status & ST_OVF_ROWS) ensure_rows(hdr_.nrows + hdr_.n_new + B200_TILE);
 			if (hdr_.status & ST_OVF_INC) ensure_inc(hdr_.inc_used + hdr_.inc_new);
 			if (hdr_.status & ST_OVF_PADJ) ensure_padj(hdr_.padj_new);
-			launch_part_a(P);
-			launch_part_b(false);
+			launch_all();
 		} else if (hdr_.status & ST_OVF_B) {
 			if (hdr_.status & ST_OVF_PAIRS) ensure_pairs(std::max(hdr_.n_pairs, hdr_.n_surv));
 			if (hdr_.status & ST_OVF_BITS) ensure_bits((u64)hdr_.wl * hdr_.mpad);
 			if (hdr_.status & ST_OVF_ADJ) ensure_adj(hdr_.adj_used + hdr_.adj_new);
 			launch_part_b(true);
-		} else
+			launch_part_c(header_only);
+		} else {
 			ensure_stage(hdr_.stage_bytes);
-		launch_part_c(header_only);
+			launch_part_c(header_only);
+		}
 		fetch_delta();
 	}
+	expect_m_ = hdr_.n_new;
+	if (prefer_big_ && hdr_.n_vis < B200_VIS_MAX / 4) prefer_big_ = false;
 #ifndef B200_EMULATE
 	if (flags_ & 1) {
 		CK(cudaEventRecord((cudaEvent_t)ev_[3], STREAM));

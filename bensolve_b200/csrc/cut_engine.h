@@ -84,6 +84,9 @@ private:
 	void ensure_facets(u32 need);
 	void launch_part_a(const CutParams &P);
 	void launch_classify_dim(int gcls);
+	void launch_small(const CutParams &P, int mode, bool header_only);
+	void launch_k4_and_tail2(bool header_only);
+	bool use_small_path() const;
 	void run_cut(const CutParams &P, bool header_only);
 	void account(const CutParams &P, u32 n_live_before, u32 nrows_before);
 	void launch_part_b(bool rerun);
@@ -95,6 +98,10 @@ private:
 	int d_;
 	unsigned flags_ = 0;
 	bool header_only_ = false;
+	bool small_dirty_ = true;      // tile counters / K1 accumulators must be cleared before the small-cut path runs
+	bool prefer_big_ = false;      // the last cut did not fit the single-CTA tail
+	u32 emu_extra_status_ = 0;
+	u32 expect_m_ = 0;             // new vertices of the previous cut (predicts whether the tail can run K4 itself)
 	DevState S_{};
 	CutCtl hdr_{};            // host copy of the control block as of the last sync
 	CutCtl *pinned_hdr_ = nullptr;

@@ -405,6 +405,47 @@ __global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S)
 // inc(a) & inc(b) (edge_test, bslv_poly.c:487-505).  Lanes scan 32 candidate rows per step; only the
 // non-zero words of the mask are compared (a mask holds >= d-2 bits, rarely more than a few words).
 #define K4_NZ 8
+__device__ __forceinline__ void k4_contain_warp(const DevState &S, u32 s, u32 lane, u32 M, u32 wl, u32 mpad)
+{
+	const u32 a = S.surv_a[s], b = S.surv_b[s];
+	bool adjacent = true;
+	if (S.d != 1) {
+		u64 mw[K4_NZ];
+		u32 mi[K4_NZ], nz = 0;
+		bool generic = false;
+		for (u32 w0 = 0; w0 < wl && !generic; w0 += 32) {
+			const u32 w = w0 + lane;
+			const u64 m = w < wl ? (S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b]) : 0;
+			u32 bal = __ballot_sync(0xffffffffu, m != 0);
+			while (bal) {
+				const int src = __ffs(bal) - 1;
+				bal &= bal - 1;
+				const u64 mv = __shfl_sync(0xffffffffu, m, src);
+				if (nz < K4_NZ) { mw[nz] = mv; mi[nz] = w0 + src; }
+				nz++;
+			}
+			if (nz > K4_NZ) generic = true;
+		}
+		for (u32 x0 = 0; x0 < M; x0 += 32) {
+			const u32 x = x0 + lane;
+			bool cont = x < M && x != a && x != b;
+			if (cont) {
+				if (!generic) {
+#pragma unroll
+					for (int q = 0; q < K4_NZ; q++)
+						if (q < (int)nz && (S.bits[(size_t)mi[q] * mpad + x] & mw[q]) != mw[q]) cont = false;
+				} else {
+					for (u32 w = 0; w < wl && cont; w++) {
+						const u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];
+						cont = (S.bits[(size_t)w * mpad + x] & m) == m;
+					}
+				}
+			}
+			if (__any_sync(0xffffffffu, cont)) { adjacent = false; break; }
+		}
+	}
+	if (adjacent && lane == 0) k4_push_pair(S, a, b);
+}
 __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 {
 	const CutCtl *c = S.ctl;
@@ -413,46 +454,7 @@ __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad, ns = c->n_surv;
 	const u32 lane = threadIdx.x & 31;
 	const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (u32 s = warp; s < ns; s += nwarps) {
-		const u32 a = S.surv_a[s], b = S.surv_b[s];
-		bool adjacent = true;
-		if (S.d != 1) {
-			u64 mw[K4_NZ];
-			u32 mi[K4_NZ], nz = 0;
-			bool generic = false;
-			for (u32 w0 = 0; w0 < wl && !generic; w0 += 32) {
-				const u32 w = w0 + lane;
-				const u64 m = w < wl ? (S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b]) : 0;
-				u32 bal = __ballot_sync(0xffffffffu, m != 0);
-				while (bal) {
-					const int src = __ffs(bal) - 1;
-					bal &= bal - 1;
-					const u64 mv = __shfl_sync(0xffffffffu, m, src);
-					if (nz < K4_NZ) { mw[nz] = mv; mi[nz] = w0 + src; }
-					nz++;
-				}
-				if (nz > K4_NZ) generic = true;
-			}
-			for (u32 x0 = 0; x0 < M; x0 += 32) {
-				const u32 x = x0 + lane;
-				bool cont = x < M && x != a && x != b;
-				if (cont) {
-					if (!generic) {
-#pragma unroll
-						for (int q = 0; q < K4_NZ; q++)
-							if (q < (int)nz && (S.bits[(size_t)mi[q] * mpad + x] & mw[q]) != mw[q]) cont = false;
-					} else {
-						for (u32 w = 0; w < wl && cont; w++) {
-							const u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];
-							cont = (S.bits[(size_t)w * mpad + x] & m) == m;
-						}
-					}
-				}
-				if (__any_sync(0xffffffffu, cont)) { adjacent = false; break; }
-			}
-		}
-		if (adjacent && lane == 0) k4_push_pair(S, a, b);
-	}
+	for (u32 s = warp; s < ns; s += nwarps) k4_contain_warp(S, s, lane, M, wl, mpad);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_adj_scan(DevState S)
@@ -627,4 +629,352 @@ __global__ void k_gc_finish(DevState S, u32 n_live, const u32 *inc_total, const 
 	S.ctl->n_live = n_live;
 	S.ctl->inc_used = *inc_total;
 	S.ctl->adj_used = *adj_total;
+}
+
+// ====================================================================================================
+// Small-cut path: a streaming K1 with no block-level synchronisation followed by single-CTA "tail"
+// kernels that run every remaining stage of the cut as __syncthreads()-separated phases.  A cut of a
+// 10^6-vertex polytope touches a few hundred vertices; as separate launches those stages cost ~20
+// launch latencies, as phases of one CTA they cost ~20 block barriers.
+// ====================================================================================================
+
+// K1, streaming form: all loads of a tile are independent (no liveness test before the coordinate
+// loads), classes are written as before, and the rare non-PLUS rows go to a per-tile list through
+// one atomic each -- no shared memory, no barrier.
+template <int D, bool FROMDEV>
+__global__ void __launch_bounds__(K_THREADS) k_classify_lists(DevState S, CutParams Parg, const double *vals,
+                                                              const unsigned char *ideal, u64 vi)
+{
+	const int d = D > 0 ? D : S.d;
+	double h[D > 0 ? D : B200_MAXD];
+	double alpha;
+	if (FROMDEV) {
+		for (int j = 0; j < d; j++) h[j] = vals[vi * d + j];
+		alpha = (ideal && ideal[vi]) ? 0.0 : -1.0;
+	} else {
+		for (int j = 0; j < d; j++) h[j] = Parg.h[j];
+		alpha = Parg.alpha;
+	}
+	const double hi0 = __dadd_rn(alpha, POLY_EPS_D), mid0 = __dadd_rn(alpha, 1.0e-2 * POLY_EPS_D), lo0 = __dsub_rn(alpha, POLY_EPS_D);
+	const double hi1 = POLY_EPS_D, mid1 = 1.0e-2 * POLY_EPS_D, lo1 = -POLY_EPS_D;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {          // publish the halfspace for the later stages
+		CutParams P = Parg;
+		if (FROMDEV) {
+			double hh = 0;
+			for (int j = 0; j < B200_MAXD; j++) { P.h[j] = j < d ? h[j] : 0.0; hh = __dadd_rn(hh, __dmul_rn(P.h[j], P.h[j])); }
+			P.alpha = alpha;
+			P.hh = hh;
+		}
+		P.hi[0] = hi0; P.mid[0] = mid0; P.lo[0] = lo0;
+		P.hi[1] = hi1; P.mid[1] = mid1; P.lo[1] = lo1;
+		*S.cur = P;
+		S.facet_cnt[P.facet] = 0;
+		S.facet_alive[P.facet] = 1;
+	}
+	const u32 nrows = S.ctl->nrows;
+	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE;
+	const size_t cap = S.cap_rows;
+	constexpr int NIT = B200_TILE / (2 * K_THREADS);
+	constexpr int IT = (D > 0 && D <= 8) ? NIT : 1;       // loads kept in flight per thread: IT * D double2
+	for (u32 tg = blockIdx.x; tg < ntiles * (NIT / IT); tg += gridDim.x) {
+		const u32 tile = tg / (NIT / IT), it0 = (tg % (NIT / IT)) * IT;
+		u32 lw[IT], iw[IT];
+		double2 x[IT][D > 0 ? D : B200_MAXD];
+#pragma unroll
+		for (int it = 0; it < IT; it++) {
+			const u32 r = tile * B200_TILE + (it0 + it) * 2 * K_THREADS + 2 * threadIdx.x;
+			lw[it] = S.live[r >> 5] >> (r & 31);
+			iw[it] = S.ideal[r >> 5] >> (r & 31);
+#pragma unroll
+			for (int j = 0; j < d; j++) x[it][j] = *reinterpret_cast<const double2 *>(S.coord + j * cap + r);
+		}
+#pragma unroll
+		for (int it = 0; it < IT; it++) {
+			const u32 r = tile * B200_TILE + (it0 + it) * 2 * K_THREADS + 2 * threadIdx.x;
+			double t0 = __dmul_rn(h[0], x[it][0].x), t1 = __dmul_rn(h[0], x[it][0].y);
+#pragma unroll
+			for (int j = 1; j < d; j++) {
+				t0 = __dadd_rn(t0, __dmul_rn(h[j], x[it][j].x));
+				t1 = __dadd_rn(t1, __dmul_rn(h[j], x[it][j].y));
+			}
+			u8 c[2] = {CLS_DEAD, CLS_DEAD};
+			const double t[2] = {t0, t1};
+#pragma unroll
+			for (int s = 0; s < 2; s++) {
+				if (!((lw[it] >> s) & 1u)) continue;
+				const bool id = (iw[it] >> s) & 1u;
+				const double hi = id ? hi1 : hi0, mid = id ? mid1 : mid0, lo = id ? lo1 : lo0;
+				c[s] = t[s] > hi ? CLS_PLUS : t[s] > mid ? CLS_ZP : t[s] > lo ? CLS_ZERO : CLS_MINUS;
+				if (c[s] != CLS_PLUS) {                  // rare
+					const u32 pos = atomicAdd(&S.tile_cnt[tile], 1u);
+					if (pos < B200_TLIST) S.tile_list[(size_t)tile * B200_TLIST + pos] = r + s;
+					if (c[s] == CLS_ZP) atomicAdd(&S.ctl->n_zp, 1u);
+					if (t[s] < lo) { atomicAdd(&S.ctl->n_strict, 1u); atomicMin(&S.ctl->min_strict_row, r + s); }
+				}
+			}
+			*reinterpret_cast<uchar2 *>(S.cls + r) = make_uchar2(c[0], c[1]);
+		}
+	}
+}
+
+#define TAIL_THREADS 1024
+#define TAIL_LOOP(i, n) for (u32 i = threadIdx.x; i < (u32)(n); i += TAIL_THREADS)
+
+__device__ __forceinline__ void tail_stage_header(const DevState &S, u32 extra_status, bool header_only)
+{
+	// all threads; stages the control block as the head of the delta record
+	CutCtl *c = S.ctl;
+	const StageLayout L = stage_layout(*c, S.d);
+	const bool fits = header_only || L.total <= S.cap_stage;
+	if (threadIdx.x < sizeof(CutCtl) / 4) {
+		u32 v = ((const u32 *)c)[threadIdx.x];
+		if (threadIdx.x == offsetof(CutCtl, status) / 4) v |= extra_status | (fits ? 0u : (u32)ST_OVF_STAGE);
+		if (threadIdx.x == offsetof(CutCtl, stage_bytes) / 4) v = (u32)L.total;
+		((u32 *)S.stage)[threadIdx.x] = v;
+	}
+}
+__device__ __forceinline__ void tail_reset_for_next_cut(const DevState &S)
+{
+	__syncthreads();
+	if (threadIdx.x == 0) {            // the counters the streaming K1 accumulates into
+		S.ctl->n_strict = 0;
+		S.ctl->min_strict_row = B200_NONE;
+		S.ctl->n_zp = 0;
+	}
+}
+
+// phases after K4: adjacency build, commit, delta record (also the body of k_tail2)
+__device__ void tail_adjacency_and_pack(const DevState &S, u32 *ws, bool header_only)
+{
+	CutCtl *c = S.ctl;
+	if (!(c->status & ST_SKIP_B)) {
+		if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) {
+			if (threadIdx.x == 0) c->status |= ST_OVF_PAIRS;
+		} else {
+			const u32 n = c->n_new;
+			u32 carry = 0;
+			for (u32 base = 0; base < n; base += TAIL_THREADS) {
+				u32 j = base + threadIdx.x, v = j < n ? S.new_padj_len[j] + S.deg[j] : 0, tot;
+				u32 e = block_excl_scan(v, ws, tot);
+				if (j < n) S.adj_base[j] = carry + e;
+				carry += tot;
+			}
+			if (threadIdx.x == 0) {
+				c->adj_new = carry;
+				if ((u64)c->adj_used + carry > S.cap_adj) c->status |= ST_OVF_ADJ;
+			}
+		}
+		__syncthreads();
+		if (!(c->status & ST_SKIP_B)) {
+			TAIL_LOOP(j, c->n_new) adj_place(S, j);
+			__syncthreads();
+			TAIL_LOOP(p, c->n_pairs) adj_pair_fill(S, p);
+			__syncthreads();
+			TAIL_LOOP(j, c->n_new) adj_sort(S, j);
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
+				c->nrows += c->n_new;
+				c->slot_cnt += c->n_new;
+				c->inc_used += c->inc_new;
+				c->adj_used += c->adj_new;
+			}
+		}
+	}
+	__syncthreads();
+	tail_stage_header(S, 0, header_only);
+	const StageLayout L = stage_layout(*c, S.d);
+	if (!header_only && L.total <= S.cap_stage && !(c->status & ST_SKIP_B)) {
+		const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
+		for (u64 e = threadIdx.x; e < n; e += TAIL_THREADS) pack_delta_item(S, L, e);
+	}
+	tail_reset_for_next_cut(S);
+}
+
+// mode 0: the whole rest of the cut; mode 1: stop after building K4's bit matrix (the multi-block
+// k4_filter / k4_contain and k_tail2 follow)
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, int header_only)
+{
+	__shared__ u32 ws[33];
+	__shared__ int changed;
+	CutCtl *c = S.ctl;
+	// ---- P0: reset per-cut outputs, decide, gather the per-tile lists into the ordered visited list
+	if (threadIdx.x == 0) {
+		c->status = 0;
+		c->min_strict_slot = B200_NONE;
+		c->n_zp_projected = 0;
+		c->n_vis = c->n_new = c->inc_new = c->padj_new = 0;
+		c->n_minus = c->n_zero = 0;
+		c->n_pairs = c->adj_new = c->n_dead_facets = 0;
+		c->n_live_scanned = c->n_live;
+		c->n_local = c->wl = c->mpad = c->n_surv = 0;
+	}
+	__syncthreads();
+	const u32 ntiles = (c->nrows + B200_TILE - 1) / B200_TILE;
+	{
+		u32 carry = 0, over = 0;
+		for (u32 base = 0; base < ntiles; base += TAIL_THREADS) {
+			u32 t = base + threadIdx.x, v = t < ntiles ? S.tile_cnt[t] : 0, tot;
+			over |= (v > B200_TLIST);
+			u32 e = block_excl_scan(v, ws, tot);
+			if (t < ntiles) S.tile_base[t] = carry + e;
+			carry += tot;
+		}
+		over = __syncthreads_or(over);
+		if (threadIdx.x == 0) {
+			c->n_vis = carry;
+			if (c->n_strict == 0) {                      // nothing to cut: redundant (bslv_poly.c:132-136)
+				c->status |= ST_REDUNDANT;
+				S.facet_alive[S.cur->facet] = 0;
+			} else {
+				c->min_strict_slot = S.row_slot[c->min_strict_row];
+				if (over || carry > B200_VIS_MAX) c->status |= ST_NEED_BIG;
+			}
+		}
+		__syncthreads();
+		const bool gather = !(c->status & (ST_REDUNDANT | ST_NEED_BIG));
+		for (u32 t = threadIdx.x; t < ntiles; t += TAIL_THREADS) {
+			const u32 cnt = S.tile_cnt[t];
+			if (!cnt) continue;
+			S.tile_cnt[t] = 0;
+			if (!gather) continue;
+			u32 *dst = S.vis + S.tile_base[t];
+			const u32 *src = S.tile_list + (size_t)t * B200_TLIST;
+			for (u32 q = 0; q < cnt; q++) {               // insertion sort: rows ascending within the tile
+				u32 key = src[q], y = q;
+				while (y > 0 && dst[y - 1] > key) { dst[y] = dst[y - 1]; y--; }
+				dst[y] = key;
+			}
+		}
+		__syncthreads();
+	}
+	if (c->status & (ST_REDUNDANT | ST_NEED_BIG)) {
+		tail_stage_header(S, 0, header_only);
+		tail_reset_for_next_cut(S);
+		return;
+	}
+	const CutParams &P = *S.cur;
+	const u32 n_vis = c->n_vis;
+	// ---- P1: ZERO+ closure (rare)
+	if (c->n_zp) {
+		do {
+			__syncthreads();
+			if (threadIdx.x == 0) changed = 0;
+			__syncthreads();
+			TAIL_LOOP(i, n_vis) if (zp_activate(S, P, i)) changed = 1;
+			__syncthreads();
+		} while (changed);
+	}
+	// ---- P2: half-edge offsets
+	{
+		u32 carry = 0;
+		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
+			u32 i = base + threadIdx.x, v = 0, tot;
+			if (i < n_vis) {
+				const u32 r = S.vis[i];
+				v = is_visited_class(S.cls[r]) ? S.adj_len[r] : 0;
+				for (int w = 0; w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
+			}
+			u32 e = block_excl_scan(v, ws, tot);
+			if (i < n_vis) S.he_off[i] = carry + e;
+			carry += tot;
+		}
+		if (threadIdx.x == 0) {
+			S.he_off[n_vis] = carry;
+			if (carry > B200_HE_CAP) c->status |= ST_NEED_BIG;
+		}
+		__syncthreads();
+		if (c->status & ST_NEED_BIG) {
+			tail_stage_header(S, 0, header_only);
+			tail_reset_for_next_cut(S);
+			return;
+		}
+	}
+	const u32 H = S.he_off[n_vis];
+	// ---- P3: evaluate every (visited vertex, neighbour) pair
+	TAIL_LOOP(i, n_vis) he_owner_fill(S, i);
+	__syncthreads();
+	TAIL_LOOP(e, H) he_eval(S, e);
+	__syncthreads();
+	// ---- P4: sizes, offsets, capacity plan (nothing mutated so far except ZERO+ projections)
+	TAIL_LOOP(i, n_vis) he_count(S, i);
+	__syncthreads();
+	{
+		u32 carry[3] = {0, 0, 0};
+		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
+			u32 i = base + threadIdx.x;
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				u32 v = i < n_vis ? S.cnt3[3 * (size_t)i + k] : 0, tot;
+				u32 e = block_excl_scan(v, ws, tot);
+				if (i < n_vis) S.base3[3 * (size_t)i + k] = carry[k] + e;
+				carry[k] += tot;
+			}
+		}
+		if (threadIdx.x == 0) {
+			c->n_new = carry[0];
+			c->inc_new = carry[1];
+			c->padj_new = carry[2];
+			u32 st = 0;
+			if ((u64)c->nrows + carry[0] > S.cap_rows) st |= ST_OVF_ROWS;
+			if ((u64)c->inc_used + carry[1] > S.cap_inc) st |= ST_OVF_INC;
+			if (carry[2] > S.cap_padj) st |= ST_OVF_PADJ;
+			c->status |= st;
+		}
+		__syncthreads();
+	}
+	if (c->status & ST_SKIP_A) {
+		tail_stage_header(S, 0, header_only);
+		tail_reset_for_next_cut(S);
+		return;
+	}
+	// ---- P5: new rows, rewiring, retirement, dead facets
+	TAIL_LOOP(e, H) he_emit(S, P, e);
+	__syncthreads();
+	TAIL_LOOP(i, n_vis) he_finish_vertex(S, P, i);
+	__syncthreads();
+	TAIL_LOOP(i, n_vis) collect_dead_facets(S, i);
+	// ---- P6: K4 bit matrix
+	const u32 M = c->n_new;
+	TAIL_LOOP(j, M) k4_assign_columns(S, j);
+	__syncthreads();
+	if (threadIdx.x == 0) k4_plan(S);
+	__syncthreads();
+	if (!(c->status & ST_OVF_BITS)) {
+		TAIL_LOOP(j, M) k4_build_row(S, j);
+		__syncthreads();
+		if (mode == 1) return;                            // k4_filter, k4_contain, k_tail2 follow
+		if (M > B200_K4_SMALL) {
+			tail_stage_header(S, ST_K4_PENDING, header_only);
+			return;
+		}
+		// ---- P7: pair test inside the CTA (bit matrix is a few KB: L1-resident)
+		for (u32 p = threadIdx.x; p < M * M; p += TAIL_THREADS) {
+			const u32 a = p / M, b = p % M;
+			if (a < b) k4_filter_pair(S, a, b);
+		}
+		__syncthreads();
+		if (c->n_surv <= S.cap_pairs) {
+			const u32 ns = c->n_surv, wl = c->wl, mpad = c->mpad;
+			for (u32 s = threadIdx.x >> 5; s < ns; s += TAIL_THREADS / 32) k4_contain_warp(S, s, threadIdx.x & 31, M, wl, mpad);
+		}
+		__syncthreads();
+	} else if (mode == 1)
+		return;
+	// ---- P8: adjacency, commit, delta record
+	tail_adjacency_and_pack(S, ws, header_only);
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail2(DevState S, int header_only)
+{
+	__shared__ u32 ws[33];
+	tail_adjacency_and_pack(S, ws, header_only);
+}
+
+__global__ void k_reset_small(DevState S)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	S.ctl->n_strict = 0;
+	S.ctl->min_strict_row = B200_NONE;
+	S.ctl->n_zp = 0;
 }

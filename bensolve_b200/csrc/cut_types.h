@@ -39,7 +39,9 @@ enum : u32 {
 	ST_OVF_ADJ = 32u,       // adjacency pool too small        (adjacency build is re-runnable)
 	ST_ERR_DEGENERATE = 64u,// an incidence list exceeds B200_MAXINC
 	ST_OVF_BITS = 128u,     // K4 bit matrix too small         (K4 is re-runnable)
-	ST_OVF_STAGE = 256u     // delta staging buffer too small  (packing is re-runnable)
+	ST_OVF_STAGE = 256u,    // delta staging buffer too small  (packing is re-runnable)
+	ST_NEED_BIG = 512u,     // cut too large for the single-CTA tail: rerun through the multi-kernel path (nothing mutated)
+	ST_K4_PENDING = 1024u   // tail stopped before K4's pair test (too many new vertices for one CTA): run k4_filter/k4_contain/k_tail2
 };
 #define ST_OVF_A (ST_OVF_ROWS | ST_OVF_INC | ST_OVF_PADJ)
 #define ST_OVF_B (ST_OVF_PAIRS | ST_OVF_ADJ | ST_OVF_BITS)
@@ -110,6 +112,13 @@ struct DevState {
 	u32 *facet_epoch, *facet_local; // [cap_facets] K4 column relabelling, valid where epoch == facet+1
 	u64 *bits;            // [cap_bits] K4 incidence bit matrix, word-major: bits[w*mpad + new_row]
 	u32 *dead_slots;     // [cap_rows] by visited index
+	// tail-kernel scratch (small cuts): per-tile lists of non-PLUS rows written by the streaming K1,
+	// and the half-edge work items (visited vertex, adjacency slot)
+	u32 *tile_list;      // [cap_tiles * B200_TLIST]
+	u32 *he_off;         // [B200_VIS_MAX + 1]
+	u32 *he_own, *he_inc; // [B200_HE_CAP]
+	u8 *he_flag;         // [B200_HE_CAP]
+	u64 *zmask;          // [B200_VIS_MAX * B200_MAXINC/64] shared-facet masks of ZERO vertices
 	u32 *dead_facets;    // [cap_facets]
 	unsigned char *stage; // [cap_stage] packed per-cut delta: header | coords AoS | parent | ideal | dead slots | dead facets
 	u64 cap_stage;
@@ -118,3 +127,7 @@ struct DevState {
 };
 
 #define B200_TILE 2048u  // rows per K1/K2 tile
+#define B200_TLIST 256u  // capacity of one tile's list of non-PLUS rows (small-cut path)
+#define B200_VIS_MAX 4096u // most visited vertices the single-CTA tail handles
+#define B200_HE_CAP 65536u // most half-edges the single-CTA tail handles
+#define B200_K4_SMALL 384u // most new vertices whose pair test the single-CTA tail does itself

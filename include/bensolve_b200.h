@@ -142,7 +142,9 @@ typedef struct {
 	double cut_ms;             /* sum of CUDA-event times of whole cuts when timing is enabled */
 } b200_stats;
 int b200_poly_get_stats(poly_args *, b200_stats *out);
-/* flags: bit0 = time every K1 launch and every cut with CUDA events (adds two syncs per cut) */
+/* flags: bit0 = time every K1 launch and every cut with CUDA events (adds two syncs per cut);
+ *        bit1 = compact device rows as soon as one is dead (test hook);
+ *        bit2 = always use the multi-kernel path, never the single-CTA tail (test hook) */
 int b200_poly_set_flags(poly_args *, unsigned flags);
 
 /* Library-wide: device selection (before the first poly__initialise), version, last error text. */

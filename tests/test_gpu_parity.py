@@ -190,3 +190,16 @@ def test_gpu_reserve_then_run(product_lib, oracle_lib):
     st = b.stats()
     assert st["cuts"] == len(tr) - 5 - sum(rb) and st["vertex_evals"] > 0 and st["kernel_launches"] > 0
     a.kill(); b.kill()
+
+
+FLAG_MULTI_KERNEL = 4   # never use the single-CTA tail: every cut goes through the multi-kernel path
+
+
+@pytest.mark.parametrize("tr", small_traces()[::3] + medium_traces(), ids=lambda t: t.name)
+def test_gpu_multi_kernel_path(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, exact=True, flags_b=FLAG_MULTI_KERNEL)
+
+
+@pytest.mark.parametrize("tr", stepwise_traces()[:4], ids=lambda t: t.name)
+def test_gpu_multi_kernel_path_after_every_cut(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, stepwise=True, exact=True, flags_b=FLAG_MULTI_KERNEL | FLAG_EAGER_GC)

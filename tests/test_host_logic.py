@@ -220,3 +220,21 @@ def test_host_logic_batch_inherits_sltn(ref_lib, emul_lib):
         e.kill()
     capi.compare_states(states[0], states[1], exact_coords=True)
     assert 0 < states[1].sltn.sum() < len(states[1].sltn)
+
+
+FLAG_TAIL_PHASES = 8   # test double: run the small-cut path (half-edge-parallel stage bodies) phase by phase
+
+
+@pytest.mark.parametrize("tr", small_traces(), ids=lambda t: t.name)
+def test_host_logic_tail_phases(oracle_lib, emul_lib, tr):
+    run_pair(oracle_lib, emul_lib, tr, exact=True, flags_b=FLAG_TAIL_PHASES)
+
+
+@pytest.mark.parametrize("tr", stepwise_traces(), ids=lambda t: t.name)
+def test_host_logic_tail_phases_after_every_cut(ref_lib, emul_lib, tr):
+    run_pair(ref_lib, emul_lib, tr, stepwise=True, exact=True, flags_b=FLAG_TAIL_PHASES | FLAG_EAGER_GC)
+
+
+@pytest.mark.parametrize("tr", medium_traces()[:4], ids=lambda t: t.name)
+def test_host_logic_tail_phases_medium(oracle_lib, emul_lib, tr):
+    run_pair(oracle_lib, emul_lib, tr, exact=True, flags_b=FLAG_TAIL_PHASES)
