@@ -124,6 +124,7 @@ CutEngine::CutEngine(int dim) : d_(dim)
 #endif
 	S_.ctl = (CutCtl *)dalloc(sizeof(CutCtl));
 	S_.cur = (CutParams *)dalloc(sizeof(CutParams));
+	S_.dbg = (u64 *)dalloc(32 * sizeof(u64));
 	S_.he_off = (u32 *)dalloc((B200_VIS_MAX + 1) * sizeof(u32));
 	S_.he_own = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
 	S_.he_inc = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
@@ -141,6 +142,11 @@ CutEngine::CutEngine(int dim) : d_(dim)
 
 CutEngine::~CutEngine()
 {
+	if (getenv("B200_PHASES")) {
+		fprintf(stderr, "[b200] tail phase ns:");
+		for (int k = 0; k < 10; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
+		fprintf(stderr, " (per cut, %llu cuts)\n", (unsigned long long)stats_.cuts);
+	}
 #ifndef B200_EMULATE
 	cudaSetDevice(g_device);
 	if (stream_) cudaStreamSynchronize(STREAM);
@@ -148,7 +154,7 @@ CutEngine::~CutEngine()
 	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
 	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.tile_list, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.tile_list, S_.dbg, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 #ifndef B200_EMULATE
 	for (int i = 0; i < 4; i++) if (ev_[i]) cudaEventDestroy((cudaEvent_t)ev_[i]);
@@ -404,7 +410,21 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 	default: launch_classify_lists<0>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
 	}
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
-	k_tail<<<1, TAIL_THREADS, 0, STREAM>>>(S_, mode, header_only ? 1 : 0);
+	// tiny cuts run the tail in one CTA (block barriers); larger ones in an 8-CTA cluster
+	const bool tiny = expect_vis_ <= 96 && expect_m_ <= B200_K4_SMALL / 2;
+	if (tiny) {
+		k_tail<1><<<1, TAIL_THREADS, 0, STREAM>>>(S_, mode, header_only ? 1 : 0);
+	} else {
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(TAIL_CTAS);
+		cfg.blockDim = dim3(TAIL_THREADS);
+		cfg.stream = STREAM;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeClusterDimension;
+		at[0].val.clusterDim.x = TAIL_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+		CK(cudaLaunchKernelEx(&cfg, k_tail<TAIL_CTAS>, S_, mode, header_only ? 1 : 0));
+	}
 	stats_.kernel_launches += 2;
 	if (mode == 1) launch_k4_and_tail2(header_only);
 	CK(cudaGetLastError());
@@ -414,7 +434,7 @@ void CutEngine::launch_k4_and_tail2(bool header_only)
 {
 	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
 	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
-	k_tail2<<<1, TAIL_THREADS, 0, STREAM>>>(S_, header_only ? 1 : 0);
+	k_tail2<1><<<1, TAIL_THREADS, 0, STREAM>>>(S_, header_only ? 1 : 0);
 	stats_.kernel_launches += 3;
 }
 
@@ -647,7 +667,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 	bool small = use_small_path() && !force_big && !prefer_big_;
 	auto launch_all = [&]() {
 		if (small) {
-			launch_small(P, expect_m_ > (B200_K4_SMALL * 3) / 4 ? 1 : 0, header_only);
+			launch_small(P, expect_m_ > (B200_K4_SMALL * 7) / 8 ? 1 : 0, header_only);
 		} else {
 			launch_part_a(P);
 			launch_part_b(false);
@@ -683,6 +703,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 		fetch_delta();
 	}
 	expect_m_ = hdr_.n_new;
+	expect_vis_ = hdr_.n_vis;
 	if (prefer_big_ && hdr_.n_vis < B200_VIS_MAX / 4) prefer_big_ = false;
 #ifndef B200_EMULATE
 	if (flags_ & 1) {
@@ -693,6 +714,11 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 		stats_.classify_ms += ms;
 		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[2], (cudaEvent_t)ev_[3]));
 		stats_.cut_ms += ms;
+		{
+			u64 tp[16];
+			d2h(tp, S_.dbg, sizeof tp);
+			for (int k = 0; k < 10; k++) if (tp[k + 1] > tp[k] && tp[10] > tp[0]) stats_.phase_ns[k] += tp[k + 1] - tp[k];
+		}
 		static const char *trace = getenv("B200_TRACE");
 		if (trace && ms > atof(trace))
 			fprintf(stderr, "[b200] slow cut %.3f ms: facet=%u nrows=%u live=%u n_vis=%u n_new=%u n_local=%u wl=%u n_surv=%u n_pairs=%u status=%u stage=%u\n",
@@ -908,6 +934,7 @@ void CutEngine::compact()
 	S_.inc_pool = T.inc_pool; S_.adj_pool = T.adj_pool;
 	stats_.compactions++;
 	stats_.kernel_launches += 12;
+	small_dirty_ = true;      // the scans above used the tile counters as scratch
 }
 #else
 void CutEngine::compact()

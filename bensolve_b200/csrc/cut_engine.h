@@ -35,6 +35,7 @@ struct EngineStats {
 	u64 minus = 0, zero = 0, zero_plus_projected = 0, edge_vertices = 0, copies = 0;
 	u64 pair_tests = 0, new_adjacent_pairs = 0, algorithmic_bytes = 0, kernel_launches = 0, compactions = 0;
 	double classify_ms = 0, cut_ms = 0;
+	u64 phase_ns[16] = {0};
 };
 
 class CutEngine {
@@ -101,6 +102,7 @@ private:
 	bool small_dirty_ = true;      // tile counters / K1 accumulators must be cleared before the small-cut path runs
 	bool prefer_big_ = false;      // the last cut did not fit the single-CTA tail
 	u32 emu_extra_status_ = 0;
+	u32 expect_vis_ = 0;
 	u32 expect_m_ = 0;             // new vertices of the previous cut (predicts whether the tail can run K4 itself)
 	DevState S_{};
 	CutCtl hdr_{};            // host copy of the control block as of the last sync

@@ -3,6 +3,7 @@
 // from the device-side CutCtl, so the host never has to read a count back between stages.
 // Tensor cores are deliberately not used: the path is matrix-vector and list/bitset work.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "cut_bodies.h"
@@ -718,11 +719,28 @@ __global__ void __launch_bounds__(K_THREADS) k_classify_lists(DevState S, CutPar
 }
 
 #define TAIL_THREADS 1024
-#define TAIL_LOOP(i, n) for (u32 i = threadIdx.x; i < (u32)(n); i += TAIL_THREADS)
+#define TAIL_CTAS 8            // medium cuts: one thread-block cluster (portable size), phases separated by cluster barriers;
+                               // tiny cuts: a single CTA, phases separated by __syncthreads()
+template <int NC> __device__ __forceinline__ u32 tail_rank()
+{
+	if (NC == 1) return 0;
+	u32 r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+template <int NC> __device__ __forceinline__ void tail_sync()
+{
+	if (NC == 1) __syncthreads();
+	else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#define TAIL_LOOP(i, n) for (u32 i = ctid; i < (u32)(n); i += NC * TAIL_THREADS)
+#define TAIL_SYNC() tail_sync<NC>()
+__device__ __forceinline__ u64 b200_globaltimer() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TP(k) do { if (ctid == 0) S.dbg[k] = b200_globaltimer(); } while (0)
 
 __device__ __forceinline__ void tail_stage_header(const DevState &S, u32 extra_status, bool header_only)
 {
-	// all threads; stages the control block as the head of the delta record
+	// stages the control block as the head of the delta record (first threads of CTA 0)
 	CutCtl *c = S.ctl;
 	const StageLayout L = stage_layout(*c, S.d);
 	const bool fits = header_only || L.total <= S.cap_stage;
@@ -735,44 +753,47 @@ __device__ __forceinline__ void tail_stage_header(const DevState &S, u32 extra_s
 }
 __device__ __forceinline__ void tail_reset_for_next_cut(const DevState &S)
 {
-	__syncthreads();
-	if (threadIdx.x == 0) {            // the counters the streaming K1 accumulates into
-		S.ctl->n_strict = 0;
-		S.ctl->min_strict_row = B200_NONE;
-		S.ctl->n_zp = 0;
-	}
+	// the counters the streaming K1 accumulates into (one thread, after the header was staged)
+	S.ctl->n_strict = 0;
+	S.ctl->min_strict_row = B200_NONE;
+	S.ctl->n_zp = 0;
 }
 
 // phases after K4: adjacency build, commit, delta record (also the body of k_tail2)
-__device__ void tail_adjacency_and_pack(const DevState &S, u32 *ws, bool header_only)
+template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32 *ws, bool header_only)
 {
 	CutCtl *c = S.ctl;
-	if (!(c->status & ST_SKIP_B)) {
-		if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) {
-			if (threadIdx.x == 0) c->status |= ST_OVF_PAIRS;
-		} else {
-			const u32 n = c->n_new;
-			u32 carry = 0;
-			for (u32 base = 0; base < n; base += TAIL_THREADS) {
-				u32 j = base + threadIdx.x, v = j < n ? S.new_padj_len[j] + S.deg[j] : 0, tot;
-				u32 e = block_excl_scan(v, ws, tot);
-				if (j < n) S.adj_base[j] = carry + e;
-				carry += tot;
-			}
-			if (threadIdx.x == 0) {
-				c->adj_new = carry;
-				if ((u64)c->adj_used + carry > S.cap_adj) c->status |= ST_OVF_ADJ;
+	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
+	const u32 st_in = c->status;      // every CTA reads the status before CTA 0 may change it below
+	TAIL_SYNC();
+	if (!(st_in & ST_SKIP_B)) {
+		if (rank == 0) {
+			if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) {
+				if (threadIdx.x == 0) c->status |= ST_OVF_PAIRS;
+			} else {
+				const u32 n = c->n_new;
+				u32 carry = 0;
+				for (u32 base = 0; base < n; base += TAIL_THREADS) {
+					u32 j = base + threadIdx.x, v = j < n ? S.new_padj_len[j] + S.deg[j] : 0, tot;
+					u32 e = block_excl_scan(v, ws, tot);
+					if (j < n) S.adj_base[j] = carry + e;
+					carry += tot;
+				}
+				if (threadIdx.x == 0) {
+					c->adj_new = carry;
+					if ((u64)c->adj_used + carry > S.cap_adj) c->status |= ST_OVF_ADJ;
+				}
 			}
 		}
-		__syncthreads();
+		TAIL_SYNC();
 		if (!(c->status & ST_SKIP_B)) {
 			TAIL_LOOP(j, c->n_new) adj_place(S, j);
-			__syncthreads();
+			TAIL_SYNC();
 			TAIL_LOOP(p, c->n_pairs) adj_pair_fill(S, p);
-			__syncthreads();
+			TAIL_SYNC();
 			TAIL_LOOP(j, c->n_new) adj_sort(S, j);
-			__syncthreads();
-			if (threadIdx.x == 0) {
+			TAIL_SYNC();
+			if (ctid == 0) {
 				c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
 				c->nrows += c->n_new;
 				c->slot_cnt += c->n_new;
@@ -781,37 +802,39 @@ __device__ void tail_adjacency_and_pack(const DevState &S, u32 *ws, bool header_
 			}
 		}
 	}
-	__syncthreads();
-	tail_stage_header(S, 0, header_only);
+	TAIL_SYNC();
+	if (rank == 0) tail_stage_header(S, 0, header_only);
 	const StageLayout L = stage_layout(*c, S.d);
 	if (!header_only && L.total <= S.cap_stage && !(c->status & ST_SKIP_B)) {
 		const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
-		for (u64 e = threadIdx.x; e < n; e += TAIL_THREADS) pack_delta_item(S, L, e);
+		for (u64 e = ctid; e < n; e += NC * TAIL_THREADS) pack_delta_item(S, L, e);
 	}
-	tail_reset_for_next_cut(S);
+	TAIL_SYNC();
+	if (ctid == 0) tail_reset_for_next_cut(S);
 }
 
 // mode 0: the whole rest of the cut; mode 1: stop after building K4's bit matrix (the multi-block
 // k4_filter / k4_contain and k_tail2 follow)
-__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, int header_only)
+template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, int header_only)
 {
 	__shared__ u32 ws[33];
-	__shared__ int changed;
+	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
 	CutCtl *c = S.ctl;
+	TP(0);
 	// ---- P0: reset per-cut outputs, decide, gather the per-tile lists into the ordered visited list
-	if (threadIdx.x == 0) {
-		c->status = 0;
-		c->min_strict_slot = B200_NONE;
-		c->n_zp_projected = 0;
-		c->n_vis = c->n_new = c->inc_new = c->padj_new = 0;
-		c->n_minus = c->n_zero = 0;
-		c->n_pairs = c->adj_new = c->n_dead_facets = 0;
-		c->n_live_scanned = c->n_live;
-		c->n_local = c->wl = c->mpad = c->n_surv = 0;
-	}
-	__syncthreads();
 	const u32 ntiles = (c->nrows + B200_TILE - 1) / B200_TILE;
-	{
+	if (rank == 0) {
+		if (threadIdx.x == 0) {
+			c->status = 0;
+			c->min_strict_slot = B200_NONE;
+			c->n_zp_projected = 0;
+			c->n_vis = c->n_new = c->inc_new = c->padj_new = 0;
+			c->n_minus = c->n_zero = 0;
+			c->n_pairs = c->adj_new = c->n_dead_facets = 0;
+			c->n_live_scanned = c->n_live;
+			c->n_local = c->wl = c->mpad = c->n_surv = 0;
+			c->scratch_flag = 0;
+		}
 		u32 carry = 0, over = 0;
 		for (u32 base = 0; base < ntiles; base += TAIL_THREADS) {
 			u32 t = base + threadIdx.x, v = t < ntiles ? S.tile_cnt[t] : 0, tot;
@@ -831,42 +854,56 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, 
 				if (over || carry > B200_VIS_MAX) c->status |= ST_NEED_BIG;
 			}
 		}
-		__syncthreads();
+	}
+	TAIL_SYNC();
+	{
+		// one warp per tile: each lane places its entries at their rank within the tile's list
+		// (rows are distinct), so the visited list comes out ascending without a sort
 		const bool gather = !(c->status & (ST_REDUNDANT | ST_NEED_BIG));
-		for (u32 t = threadIdx.x; t < ntiles; t += TAIL_THREADS) {
+		const u32 lane = threadIdx.x & 31;
+		for (u32 t = ctid >> 5; t < ntiles; t += NC * TAIL_THREADS / 32) {
 			const u32 cnt = S.tile_cnt[t];
 			if (!cnt) continue;
-			S.tile_cnt[t] = 0;
+			__syncwarp();
+			if (lane == 0) S.tile_cnt[t] = 0;
 			if (!gather) continue;
 			u32 *dst = S.vis + S.tile_base[t];
 			const u32 *src = S.tile_list + (size_t)t * B200_TLIST;
-			for (u32 q = 0; q < cnt; q++) {               // insertion sort: rows ascending within the tile
-				u32 key = src[q], y = q;
-				while (y > 0 && dst[y - 1] > key) { dst[y] = dst[y - 1]; y--; }
-				dst[y] = key;
+			for (u32 q = lane; q < cnt; q += 32) {
+				const u32 key = src[q];
+				u32 rk = 0;
+				for (u32 x = 0; x < cnt; x++) rk += (src[x] < key);
+				dst[rk] = key;
 			}
 		}
-		__syncthreads();
 	}
+	TAIL_SYNC();
 	if (c->status & (ST_REDUNDANT | ST_NEED_BIG)) {
-		tail_stage_header(S, 0, header_only);
-		tail_reset_for_next_cut(S);
+		if (rank == 0) tail_stage_header(S, 0, header_only);
+		TAIL_SYNC();
+		if (ctid == 0) tail_reset_for_next_cut(S);
 		return;
 	}
 	const CutParams &P = *S.cur;
 	const u32 n_vis = c->n_vis;
+	TP(1);
 	// ---- P1: ZERO+ closure (rare)
 	if (c->n_zp) {
-		do {
-			__syncthreads();
-			if (threadIdx.x == 0) changed = 0;
-			__syncthreads();
-			TAIL_LOOP(i, n_vis) if (zp_activate(S, P, i)) changed = 1;
-			__syncthreads();
-		} while (changed);
+		for (;;) {
+			bool any = false;
+			TAIL_LOOP(i, n_vis) any |= zp_activate(S, P, i);
+			if (any) atomicOr(&c->scratch_flag, 1u);
+			TAIL_SYNC();
+			const u32 f = c->scratch_flag;
+			TAIL_SYNC();
+			if (!f) break;
+			if (ctid == 0) c->scratch_flag = 0;
+			TAIL_SYNC();
+		}
 	}
 	// ---- P2: half-edge offsets
-	{
+	TAIL_SYNC();                      // all CTAs are past the status check above before CTA 0 may set NEED_BIG
+	if (rank == 0) {
 		u32 carry = 0;
 		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
 			u32 i = base + threadIdx.x, v = 0, tot;
@@ -883,23 +920,26 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, 
 			S.he_off[n_vis] = carry;
 			if (carry > B200_HE_CAP) c->status |= ST_NEED_BIG;
 		}
-		__syncthreads();
-		if (c->status & ST_NEED_BIG) {
-			tail_stage_header(S, 0, header_only);
-			tail_reset_for_next_cut(S);
-			return;
-		}
+	}
+	TAIL_SYNC();
+	if (c->status & ST_NEED_BIG) {
+		if (rank == 0) tail_stage_header(S, 0, header_only);
+		TAIL_SYNC();
+		if (ctid == 0) tail_reset_for_next_cut(S);
+		return;
 	}
 	const u32 H = S.he_off[n_vis];
+	TP(2);
 	// ---- P3: evaluate every (visited vertex, neighbour) pair
 	TAIL_LOOP(i, n_vis) he_owner_fill(S, i);
-	__syncthreads();
+	TAIL_SYNC();
 	TAIL_LOOP(e, H) he_eval(S, e);
-	__syncthreads();
+	TAIL_SYNC();
+	TP(3);
 	// ---- P4: sizes, offsets, capacity plan (nothing mutated so far except ZERO+ projections)
 	TAIL_LOOP(i, n_vis) he_count(S, i);
-	__syncthreads();
-	{
+	TAIL_SYNC();
+	if (rank == 0) {
 		u32 carry[3] = {0, 0, 0};
 		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
 			u32 i = base + threadIdx.x;
@@ -921,54 +961,62 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, 
 			if (carry[2] > S.cap_padj) st |= ST_OVF_PADJ;
 			c->status |= st;
 		}
-		__syncthreads();
 	}
+	TAIL_SYNC();
 	if (c->status & ST_SKIP_A) {
-		tail_stage_header(S, 0, header_only);
-		tail_reset_for_next_cut(S);
+		if (rank == 0) tail_stage_header(S, 0, header_only);
+		TAIL_SYNC();
+		if (ctid == 0) tail_reset_for_next_cut(S);
 		return;
 	}
+	TP(4);
 	// ---- P5: new rows, rewiring, retirement, dead facets
 	TAIL_LOOP(e, H) he_emit(S, P, e);
-	__syncthreads();
+	TAIL_SYNC();
+	TP(5);
 	TAIL_LOOP(i, n_vis) he_finish_vertex(S, P, i);
-	__syncthreads();
+	TAIL_SYNC();
 	TAIL_LOOP(i, n_vis) collect_dead_facets(S, i);
+	TP(6);
 	// ---- P6: K4 bit matrix
 	const u32 M = c->n_new;
 	TAIL_LOOP(j, M) k4_assign_columns(S, j);
-	__syncthreads();
-	if (threadIdx.x == 0) k4_plan(S);
-	__syncthreads();
+	TAIL_SYNC();
+	if (ctid == 0) k4_plan(S);
+	TAIL_SYNC();
 	if (!(c->status & ST_OVF_BITS)) {
 		TAIL_LOOP(j, M) k4_build_row(S, j);
-		__syncthreads();
+		TAIL_SYNC();
+		TP(7);
 		if (mode == 1) return;                            // k4_filter, k4_contain, k_tail2 follow
-		if (M > B200_K4_SMALL) {
-			tail_stage_header(S, ST_K4_PENDING, header_only);
+		if (M > (NC == 1 ? B200_K4_SMALL / 2 : B200_K4_SMALL)) {
+			if (rank == 0) tail_stage_header(S, ST_K4_PENDING, header_only);
 			return;
 		}
-		// ---- P7: pair test inside the CTA (bit matrix is a few KB: L1-resident)
-		for (u32 p = threadIdx.x; p < M * M; p += TAIL_THREADS) {
+		// ---- P7: pair test inside the cluster (the bit matrix is a few KB: cache-resident)
+		for (u32 p = ctid; p < M * M; p += NC * TAIL_THREADS) {
 			const u32 a = p / M, b = p % M;
 			if (a < b) k4_filter_pair(S, a, b);
 		}
-		__syncthreads();
+		TAIL_SYNC();
+		TP(8);
 		if (c->n_surv <= S.cap_pairs) {
 			const u32 ns = c->n_surv, wl = c->wl, mpad = c->mpad;
-			for (u32 s = threadIdx.x >> 5; s < ns; s += TAIL_THREADS / 32) k4_contain_warp(S, s, threadIdx.x & 31, M, wl, mpad);
+			for (u32 s = ctid >> 5; s < ns; s += NC * TAIL_THREADS / 32) k4_contain_warp(S, s, threadIdx.x & 31, M, wl, mpad);
 		}
-		__syncthreads();
+		TAIL_SYNC();
 	} else if (mode == 1)
 		return;
+	TP(9);
 	// ---- P8: adjacency, commit, delta record
-	tail_adjacency_and_pack(S, ws, header_only);
+	tail_adjacency_and_pack<NC>(S, ws, header_only);
+	TP(10);
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail2(DevState S, int header_only)
+template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail2(DevState S, int header_only)
 {
 	__shared__ u32 ws[33];
-	tail_adjacency_and_pack(S, ws, header_only);
+	tail_adjacency_and_pack<NC>(S, ws, header_only);
 }
 
 __global__ void k_reset_small(DevState S)

@@ -86,7 +86,8 @@ struct CutCtl {
 	u32 mpad;           // n_new rounded up to 32: column stride of the word-major bit matrix
 	u32 n_surv;         // pairs that pass the AND+POPC filter
 	u32 stage_bytes;    // size of the packed delta record (header included)
-	u32 reserved[2];
+	u32 scratch_flag;   // cluster-wide 'something changed' flag of the ZERO+ closure
+	u32 reserved[1];
 };
 #define B200_STAGE_HDR 128u   // the packed delta starts with a copy of CutCtl, padded to this size
 
@@ -124,10 +125,11 @@ struct DevState {
 	u64 cap_stage;
 	CutCtl *ctl;
 	CutParams *cur;
+	u64 *dbg;            // [32] phase time stamps of the tail kernel (diagnostics, flags bit0)
 };
 
 #define B200_TILE 2048u  // rows per K1/K2 tile
 #define B200_TLIST 256u  // capacity of one tile's list of non-PLUS rows (small-cut path)
 #define B200_VIS_MAX 4096u // most visited vertices the single-CTA tail handles
 #define B200_HE_CAP 65536u // most half-edges the single-CTA tail handles
-#define B200_K4_SMALL 384u // most new vertices whose pair test the single-CTA tail does itself
+#define B200_K4_SMALL 256u // most new vertices whose pair test the single-CTA tail does itself
