@@ -186,27 +186,38 @@ def run_b200(a, trace):
         assert e.init_approx() == 0
         return e
 
-    def step_value(keep=False):
-        e = fresh_engine()
-        rcs = e.add_batch_device(d_vals.data_ptr(), 0, n - d)
-        st = e.stats()
-        if keep:
-            return e, st, rcs
-        e.kill()
-        return None, st, rcs
-
-    def step_e2e():
-        e = fresh_engine()
-        rcs = [e.add(trace.vals[i], 0) for i in range(d, n)]
-        st = e.stats()
-        e.kill()
-        return st, rcs
-
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # A step is timed from before poly__initialise to the return of the last cut (host mirror
+    # coherent), bracketed by barrier + synchronize; poly__kill (teardown) lies between steps.
+    def step_value(keep=False):
+        barrier()
+        t0 = time.perf_counter()
+        e = fresh_engine()
+        rcs = e.add_batch_device(d_vals.data_ptr(), 0, n - d)
+        barrier()
+        dt = time.perf_counter() - t0
+        st = e.stats()
+        if keep:
+            return e, st, dt
+        e.kill()
+        return None, st, dt
+
+    def step_e2e():
+        barrier()
+        t0 = time.perf_counter()
+        e = fresh_engine()
+        for i in range(d, n):
+            e.add(trace.vals[i], 0)
+        barrier()
+        dt = time.perf_counter() - t0
+        st = e.stats()
+        e.kill()
+        return st, dt
 
     # warm-up (also reveals the capacities to reserve, so the timed steps do not re-allocate)
     for w in range(max(a.warmup, 1)):
@@ -218,23 +229,19 @@ def run_b200(a, trace):
         step_e2e()
 
     with ClockSampler(local) as clk:
-        barrier()
-        t0 = time.perf_counter()
+        t_value = t_e2e = 0.0
         cuts_v = launches_v = evals_v = 0
         for k in range(a.steps):
-            eng, st, rcs = step_value(keep=(k == a.steps - 1))
+            eng, st, dt = step_value(keep=(k == a.steps - 1))
+            t_value += dt
             cuts_v += st["cuts"]; launches_v += st["kernel_launches"]; evals_v += st["vertex_evals"]
-        barrier()
-        t_value = time.perf_counter() - t0
-        barrier()
-        t0 = time.perf_counter()
+        eng_keep = eng
         cuts_e = launches_e = 0
-        d2h = 0
         for k in range(a.steps):
-            st_e, _ = step_e2e()
+            st_e, dt = step_e2e()
+            t_e2e += dt
             cuts_e += st_e["cuts"]; launches_e += st_e["kernel_launches"]
-        barrier()
-        t_e2e = time.perf_counter() - t0
+        eng = eng_keep
         # roofline of the dominant kernel on the final polytope of the last value step
         st_final = eng.stats()
         hp = np.append(trace.vals[n // 2] * 1.0000001, -1.0)
@@ -267,12 +274,13 @@ def run_b200(a, trace):
             "live_vertices": int(n_live), "slots": int(per_step["slots"]), "facets": int(per_step["facets"]),
             "l2": "step: coordinates (%.0f MB) stay L2-resident across cuts, inherent to the workload; roofline: L2 flushed (256 MB memset) before every timed K1 launch" % (n_live * 8 * d / 1e6),
             "multi_gpu": "replicas" if world > 1 else "single",
+            "timed_region": "poly__initialise .. last cut returned with a coherent host mirror; poly__kill between steps is untimed; device and host storage pre-sized with b200_poly_reserve from the warm-up's counts",
         },
         "vertex_evals_per_s": evals_v / t_value,
         "e2e": {"value": cuts_e / t_e2e, "unit": "cuts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step,
                 "ms_per_step": 1e3 * t_e2e / a.steps},
         "gpu_launches": int(launches_v + launches_e),
-        "roofline": {"bound": "hbm", "kernel": f"k_classify<{d}>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": f"k_classify_lists<{d},false>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                      "ms_per_launch": ms_flush, "ms_per_launch_l2_resident": ms_l2,
                      "achieved_l2_resident": alg_bytes / (ms_l2 * 1e-3) / 1e9 if ms_l2 > 0 else None,

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <stdexcept>
 
 #ifndef B200_EMULATE
@@ -26,6 +27,8 @@
 static thread_local std::string g_last_error;
 void b200_set_error(const std::string &msg) { g_last_error = msg; }
 const char *b200_get_error() { return g_last_error.c_str(); }
+
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 [[noreturn]] static void fail(const std::string &msg)
 {
@@ -146,6 +149,7 @@ CutEngine::~CutEngine()
 		fprintf(stderr, "[b200] tail phase ns:");
 		for (int k = 0; k < 10; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, " (per cut, %llu cuts)\n", (unsigned long long)stats_.cuts);
+		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions);
 	}
 #ifndef B200_EMULATE
 	cudaSetDevice(g_device);
@@ -156,6 +160,7 @@ CutEngine::~CutEngine()
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
 	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.tile_list, S_.dbg, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
+	drop_shadow();
 #ifndef B200_EMULATE
 	for (int i = 0; i < 4; i++) if (ev_[i]) cudaEventDestroy((cudaEvent_t)ev_[i]);
 	if (pinned_hdr_) cudaFreeHost(pinned_hdr_);
@@ -168,9 +173,17 @@ CutEngine::~CutEngine()
 }
 
 // ------------------------------------------------------------------ capacity
+void CutEngine::drop_shadow()
+{
+	if (!shadow_valid_) return;
+	for (int k = 0; k < 11; k++) { dfree(shadow_[k]); shadow_[k] = nullptr; }
+	shadow_valid_ = false;
+}
+
 void CutEngine::ensure_rows(u32 need)
 {
 	if (need <= S_.cap_rows) return;
+	drop_shadow();
 	const u32 old = S_.cap_rows, keep = hdr_.nrows;
 	const u32 cap = round_up(std::max<u64>(need, (u64)old * 2), B200_TILE);
 #ifndef B200_EMULATE
@@ -209,6 +222,7 @@ void CutEngine::ensure_rows(u32 need)
 void CutEngine::ensure_inc(u32 need)
 {
 	if (need <= S_.cap_inc) return;
+	drop_shadow();
 	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_inc * 2);
 	regrow(S_.inc_pool, cap, hdr_.inc_used);
 	S_.cap_inc = cap;
@@ -216,6 +230,7 @@ void CutEngine::ensure_inc(u32 need)
 void CutEngine::ensure_adj(u32 need)
 {
 	if (need <= S_.cap_adj) return;
+	drop_shadow();
 	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_adj * 2);
 	regrow(S_.adj_pool, cap, hdr_.adj_used);
 	S_.cap_adj = cap;
@@ -323,6 +338,12 @@ void CutEngine::upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
 
 // ------------------------------------------------------------------ the pipeline
 #ifndef B200_EMULATE
+template <int D> static void launch_classify_lists(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, int grid, cudaStream_t st)
+{
+	if (dv) k_classify_lists<D, true><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi);
+	else k_classify_lists<D, false><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0);
+}
+
 template <int D> static void launch_classify(const DevState &S, int grid, cudaStream_t st) { k_classify<D><<<grid, K_THREADS, 0, st>>>(S); }
 
 void CutEngine::launch_classify_dim(int gcls)
@@ -378,12 +399,6 @@ void CutEngine::launch_part_b(bool rerun)
 	k_finish<<<1, 32, 0, STREAM>>>(S_);
 	stats_.kernel_launches += 10;
 	CK(cudaGetLastError());
-}
-
-template <int D> static void launch_classify_lists(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, int grid, cudaStream_t st)
-{
-	if (dv) k_classify_lists<D, true><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi);
-	else k_classify_lists<D, false><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0);
 }
 
 // small-cut path: streaming K1 + single-CTA tail (+ multi-block K4 pair test for medium cuts)
@@ -674,11 +689,17 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 			launch_part_c(header_only);
 		}
 	};
+	const double t_a = now_us();
 	launch_all();
+	const double t_b = now_us();
 	fetch_delta();
+	const double t_c = now_us();
+	stats_.host_us[0] += t_b - t_a;
+	stats_.host_us[1] += t_c - t_b;
 	const u32 redo = ST_OVF_A | ST_OVF_B | ST_OVF_STAGE | ST_NEED_BIG | ST_K4_PENDING;
 	for (int guard = 0; hdr_.status & redo; guard++) {
 		if (guard > 16) fail("bensolve_b200: capacity negotiation did not converge");
+		stats_.redo_loops++;
 		if (hdr_.status & ST_NEED_BIG) {            // nothing was mutated: rerun through the multi-kernel path
 			small = false;
 			prefer_big_ = true;
@@ -704,6 +725,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 	}
 	expect_m_ = hdr_.n_new;
 	expect_vis_ = hdr_.n_vis;
+	stats_.host_us[2] += now_us() - t_c;
 	if (prefer_big_ && hdr_.n_vis < B200_VIS_MAX / 4) prefer_big_ = false;
 #ifndef B200_EMULATE
 	if (flags_ & 1) {
@@ -754,9 +776,11 @@ void CutEngine::account(const CutParams &P, u32 n_live_before, u32 nrows_before)
 
 void CutEngine::cut(const CutParams &P, CutDelta &out)
 {
+	const double t_in = now_us();
 	out = CutDelta();
 	const u32 n_live_before = hdr_.n_live, nrows_before = hdr_.nrows;
 	run_cut(P, false);
+	const double t_run = now_us();
 	account(P, n_live_before, nrows_before);
 	if (hdr_.status & ST_REDUNDANT) { out.redundant = 1; return; }
 	// ---- unpack the delta record
@@ -778,6 +802,8 @@ void CutEngine::cut(const CutParams &P, CutDelta &out)
 	const u32 *df = (const u32 *)(pinned_stage_ + L.dead_facets);
 	out.dead_facets.assign(df, df + hdr_.n_dead_facets);
 	maybe_compact();
+	stats_.host_us[3] += now_us() - t_run;
+	stats_.host_us[4] += now_us() - t_in;
 }
 
 int CutEngine::cut_from_device(const double *d_vals, const unsigned char *d_ideal, u64 i, u32 facet, u32 batch_first)
@@ -848,25 +874,39 @@ double CutEngine::classify_bench(const CutParams &P, int iters, int flush_l2)
 {
 #ifndef B200_EMULATE
 	CK(cudaSetDevice(g_device));
+	ensure_facets(P.facet + 1);
 	const size_t flush_bytes = (size_t)256 << 20;     // > 126 MB L2
 	if (flush_l2 && !flush_buf_) flush_buf_ = dalloc(flush_bytes);
 	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
-	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
+	const u32 groups = ntiles * ((d_ >= 2 && d_ <= 8) ? 1 : B200_TILE / (2 * K_THREADS));
+	const int g = (int)std::max<u32>(1, std::min<u32>(groups, (u32)num_sms_ * 8));
 	double total = 0;
 	for (int it = 0; it < iters; it++) {
-		k_begin<<<1, 32, 0, STREAM>>>(S_, P);
+		CK(cudaMemsetAsync(S_.tile_cnt, 0, (size_t)S_.cap_tiles * 4, STREAM));
+		k_reset_small<<<1, 32, 0, STREAM>>>(S_);
 		if (flush_l2) CK(cudaMemsetAsync(flush_buf_, it & 0xff, flush_bytes, STREAM));
 		CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
-		launch_classify_dim(gcls);
+		switch (d_) {       // the streaming K1 of the cut path, exactly as launch_small() launches it
+		case 2: launch_classify_lists<2>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		case 3: launch_classify_lists<3>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		case 4: launch_classify_lists<4>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		case 5: launch_classify_lists<5>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		case 6: launch_classify_lists<6>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		case 7: launch_classify_lists<7>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		case 8: launch_classify_lists<8>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		default: launch_classify_lists<0>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
+		}
 		CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 		CK(cudaEventSynchronize((cudaEvent_t)ev_[1]));
 		float ms = 0;
 		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[0], (cudaEvent_t)ev_[1]));
 		total += ms;
 	}
-	// the probe halfspace is not a facet: undo what k_begin registered
+	// the probe halfspace is not a facet: undo what K1 registered, and have the next cut clear the
+	// tile lists and trigger counters it left behind
 	CK(cudaMemsetAsync(S_.facet_alive + P.facet, 0, 4, STREAM));
 	CK(cudaStreamSynchronize(STREAM));
+	small_dirty_ = true;
 	return iters > 0 ? total / iters : 0.0;
 #else
 	(void)P; (void)iters; (void)flush_l2;
@@ -905,20 +945,28 @@ void CutEngine::compact()
 	k_gscan_reduce<<<ltiles, K_THREADS, 0, STREAM>>>(la, n_live, S_.tile_cnt);
 	k_gscan_tiles<<<1, SCAN_THREADS, 0, STREAM>>>(S_.tile_cnt, ltiles, S_.tile_base, totals + 2);
 	k_gscan_apply<<<ltiles, K_THREADS, 0, STREAM>>>(la, n_live, S_.tile_base, new_adj_off);
-	// 3. gather into fresh arrays of the same capacity, then swap
-	GcTarget T;
+	// 3. gather into the shadow set of persistent arrays (allocated once per capacity), then swap
 	const u32 cap = S_.cap_rows;
-	T.coord = (double *)dalloc((size_t)cap * d_ * sizeof(double));
-	T.row_slot = (u32 *)dalloc((size_t)cap * 4);
-	T.root = (u32 *)dalloc((size_t)cap * 4);
-	T.live = (u32 *)dalloc((size_t)cap / 8);
-	T.ideal = (u32 *)dalloc((size_t)cap / 8);
-	T.inc_off = (u32 *)dalloc((size_t)cap * 4);
-	T.inc_len = (u32 *)dalloc((size_t)cap * 4);
-	T.adj_off = (u32 *)dalloc((size_t)cap * 4);
-	T.adj_len = (u32 *)dalloc((size_t)cap * 4);
-	T.inc_pool = (u32 *)dalloc((size_t)S_.cap_inc * 4);
-	T.adj_pool = (u32 *)dalloc((size_t)S_.cap_adj * 4);
+	if (!shadow_valid_ || shadow_rows_ != cap || shadow_inc_ != S_.cap_inc || shadow_adj_ != S_.cap_adj) {
+		drop_shadow();
+		shadow_[0] = dalloc((size_t)cap * d_ * sizeof(double));
+		for (int k = 1; k <= 2; k++) shadow_[k] = dalloc((size_t)cap * 4);          // row_slot, root
+		for (int k = 3; k <= 4; k++) shadow_[k] = dalloc((size_t)cap / 8);           // live, ideal
+		for (int k = 5; k <= 8; k++) shadow_[k] = dalloc((size_t)cap * 4);          // inc_off, inc_len, adj_off, adj_len
+		shadow_[9] = dalloc((size_t)S_.cap_inc * 4);
+		shadow_[10] = dalloc((size_t)S_.cap_adj * 4);
+		shadow_rows_ = cap; shadow_inc_ = S_.cap_inc; shadow_adj_ = S_.cap_adj;
+		shadow_valid_ = true;
+	} else {                                   // only the bitsets rely on zero fill beyond the live rows
+		CK(cudaMemsetAsync(shadow_[3], 0, (size_t)cap / 8, STREAM));
+		CK(cudaMemsetAsync(shadow_[4], 0, (size_t)cap / 8, STREAM));
+	}
+	GcTarget T;
+	T.coord = (double *)shadow_[0];
+	T.row_slot = (u32 *)shadow_[1]; T.root = (u32 *)shadow_[2];
+	T.live = (u32 *)shadow_[3]; T.ideal = (u32 *)shadow_[4];
+	T.inc_off = (u32 *)shadow_[5]; T.inc_len = (u32 *)shadow_[6]; T.adj_off = (u32 *)shadow_[7]; T.adj_len = (u32 *)shadow_[8];
+	T.inc_pool = (u32 *)shadow_[9]; T.adj_pool = (u32 *)shadow_[10];
 	k_gc_gather<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, T, n_live, remap, old_of, new_inc_off, new_adj_off);
 	k_gc_finish<<<1, 32, 0, STREAM>>>(S_, n_live, totals + 1, totals + 2);
 	CK(cudaGetLastError());
@@ -926,8 +974,8 @@ void CutEngine::compact()
 	CK(cudaStreamSynchronize(STREAM));
 	hdr_ = *pinned_hdr_;
 	if (hdr_.nrows != n_live) fail("bensolve_b200: compaction lost rows");
-	void *old[] = {S_.coord, S_.row_slot, S_.root, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len, S_.inc_pool, S_.adj_pool};
-	for (void *p : old) dfree(p);
+	void *old[11] = {S_.coord, S_.row_slot, S_.root, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len, S_.inc_pool, S_.adj_pool};
+	for (int k = 0; k < 11; k++) shadow_[k] = old[k];      // the previous arrays become the next shadow set
 	dfree(totals);
 	S_.coord = T.coord; S_.row_slot = T.row_slot; S_.root = T.root; S_.live = T.live; S_.ideal = T.ideal;
 	S_.inc_off = T.inc_off; S_.inc_len = T.inc_len; S_.adj_off = T.adj_off; S_.adj_len = T.adj_len;

@@ -36,6 +36,8 @@ struct EngineStats {
 	u64 pair_tests = 0, new_adjacent_pairs = 0, algorithmic_bytes = 0, kernel_launches = 0, compactions = 0;
 	double classify_ms = 0, cut_ms = 0;
 	u64 phase_ns[16] = {0};
+	double host_us[8] = {0};
+	u64 redo_loops = 0;
 };
 
 class CutEngine {
@@ -76,6 +78,7 @@ public:
 	u32 rows() const { return hdr_.nrows; }
 
 private:
+	void drop_shadow();
 	void ensure_rows(u32 need);
 	void ensure_inc(u32 need);
 	void ensure_adj(u32 need);
@@ -115,6 +118,9 @@ private:
 	const unsigned char *dev_ideal_ = nullptr;
 	u64 dev_index_ = 0;
 	void *flush_buf_ = nullptr;
+	void *shadow_[11] = {nullptr};      // second set of persistent arrays: target of the next compaction
+	bool shadow_valid_ = false;
+	u32 shadow_rows_ = 0, shadow_inc_ = 0, shadow_adj_ = 0;
 	EngineStats stats_;
 };
 

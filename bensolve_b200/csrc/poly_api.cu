@@ -33,6 +33,7 @@ struct Handle {                 // hung off the dead `ip` field of both polytope
 	size_t get_cursor = 0;        // every slot below is dead or already marked sltn (f2)
 	std::vector<size_t> slab_pinc, slab_padj, slab_dinc, slab_dadj; // backing store of the host lists
 	unsigned flags = 0;
+	size_t lists_cap_p = 0, lists_cap_d = 0;   // slots the host poly_list arrays are sized for
 };
 
 static size_t g_default_dim; // fnc_dim, bslv_poly.c:28: read by the default callback
@@ -62,9 +63,8 @@ static void mirror_alloc(polytope *p)
 	p->blcks = 1;
 	p->data = (double *)malloc(cap * std::max<size_t>(p->dim, 1) * sizeof(double));
 	p->data_primg = (double *)malloc(cap * std::max<size_t>(p->dim_primg, 1) * sizeof(double));
-	p->adjacence = (poly_list *)malloc(cap * sizeof(poly_list));
-	p->incidence = (poly_list *)malloc(cap * sizeof(poly_list));
-	for (size_t i = 0; i < cap; i++) { list_reset(p->adjacence + i); list_reset(p->incidence + i); }
+	p->adjacence = NULL;                  // the list arrays are allocated when they are first materialised
+	p->incidence = NULL;
 	p->used = (vrtx_strg *)calloc(1, sizeof(vrtx_strg));
 	p->ideal = (vrtx_strg *)calloc(1, sizeof(vrtx_strg));
 	p->sltn = (vrtx_strg *)calloc(1, sizeof(vrtx_strg));
@@ -79,14 +79,24 @@ static void mirror_reserve(polytope *p, size_t slots)
 	const size_t ncap = nb * SLOTS_PER_BLOCK;
 	p->data = (double *)realloc(p->data, ncap * std::max<size_t>(p->dim, 1) * sizeof(double));
 	p->data_primg = (double *)realloc(p->data_primg, ncap * std::max<size_t>(p->dim_primg, 1) * sizeof(double));
-	p->adjacence = (poly_list *)realloc(p->adjacence, ncap * sizeof(poly_list));
-	p->incidence = (poly_list *)realloc(p->incidence, ncap * sizeof(poly_list));
-	for (size_t i = cap; i < ncap; i++) { list_reset(p->adjacence + i); list_reset(p->incidence + i); }
 	p->used = (vrtx_strg *)realloc(p->used, nb * sizeof(vrtx_strg));
 	p->ideal = (vrtx_strg *)realloc(p->ideal, nb * sizeof(vrtx_strg));
 	p->sltn = (vrtx_strg *)realloc(p->sltn, nb * sizeof(vrtx_strg));
 	for (size_t i = p->blcks; i < nb; i++) p->used[i] = p->ideal[i] = p->sltn[i] = 0;
 	p->blcks = nb;
+}
+
+// the poly_list arrays are only read inside this library (writers, polyck, update_adjacence, swap,
+// plot -- bslv_algs.c never touches them), so they are (re)sized when lists are materialised
+static void mirror_lists_reserve(polytope *p, Handle *h, bool is_primal)
+{
+	size_t &have = is_primal ? h->lists_cap_p : h->lists_cap_d;
+	const size_t need = p->blcks * SLOTS_PER_BLOCK;
+	if (have >= need && p->adjacence) return;
+	p->adjacence = (poly_list *)realloc(p->adjacence, need * sizeof(poly_list));
+	p->incidence = (poly_list *)realloc(p->incidence, need * sizeof(poly_list));
+	for (size_t i = have; i < need; i++) { list_reset(p->adjacence + i); list_reset(p->incidence + i); }
+	have = need;
 }
 
 static size_t mirror_append(polytope *p)      // add_vrtx, bslv_poly.c:416-447
@@ -421,10 +431,13 @@ extern "C" int b200_poly_materialise(poly_args *a)
 {
 	GUARD_BEGIN
 	Handle *h = handle_of(&a->primal);
-	if (!h->engine || h->lists_current) return 0;
+	if (!h->engine) { mirror_lists_reserve(&a->primal, h, true); mirror_lists_reserve(&a->dual, h, false); return 0; }
+	if (h->lists_current && h->lists_cap_p >= a->primal.blcks * SLOTS_PER_BLOCK && h->lists_cap_d >= a->dual.blcks * SLOTS_PER_BLOCK) return 0;
 	HostStructure hs;
 	h->engine->download_structure(hs);
 	polytope *P = &a->primal, *D = &a->dual;
+	mirror_lists_reserve(P, h, true);
+	mirror_lists_reserve(D, h, false);
 	const size_t S = P->cnt, F = D->cnt;
 	std::vector<size_t> ioff(S + 1, 0), aoff(S + 1, 0), foff(F + 1, 0);
 	auto live = [&](u32 r) { return (hs.live_words[r >> 5] >> (r & 31)) & 1u; };
@@ -835,6 +848,7 @@ extern "C" double b200_poly_classify_bench(poly_args *a, const double *hp, int i
 	CutParams P;
 	make_params(hp, a->dim, (u32)a->dual.cnt, P);     // an id one past the last facet: scratch only
 	P.batch_first = (u32)a->primal.cnt;
+	h->engine->compact();            // measure on dense rows, as right after a compaction
 	return h->engine->classify_bench(P, iters, flush_l2);
 	GUARD_END("b200_poly_classify_bench")
 }

@@ -30,12 +30,15 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--timing", type=int, default=1)
     ap.add_argument("--every", type=int, default=0)
+    ap.add_argument("--reserve", type=int, default=0, help="rows to pre-size (0 = grow on demand)")
     a = ap.parse_args()
     lib = capi.load_product()
     tr = P.tangent_polytope(a.dim, a.n, a.seed)
     e = capi.PolyEngine(lib, a.dim)
     lib.b200_poly_set_flags.argtypes = [C.POINTER(capi.PolyArgs), C.c_uint]
     lib.b200_poly_set_flags(C.byref(e.args), a.timing)
+    if a.reserve:
+        e.reserve(a.reserve, a.reserve * (a.dim + 2), a.reserve * (a.dim + 2))
     t0 = time.perf_counter()
     last = [t0, 0.0, 0.0]
 
