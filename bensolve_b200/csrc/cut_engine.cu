@@ -47,6 +47,7 @@ static inline double now_us() { return std::chrono::duration<double, std::micro>
 	} while (0)
 
 static int g_device = -1;
+static int g_k1_it = 1;     // tile iterations whose loads a K1 thread keeps in flight (env B200_K1_IT = 1, 2 or 4)
 int b200_num_devices()
 {
 	int n = 0;
@@ -118,6 +119,7 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	stream_ = st;
 	for (int i = 0; i < 4; i++) { cudaEvent_t e; CK(cudaEventCreate(&e)); ev_[i] = e; }
 	CK(cudaMallocHost((void **)&pinned_hdr_, sizeof(CutCtl)));
+	if (const char *e = getenv("B200_K1_IT")) g_k1_it = atoi(e);
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, g_device));
 	num_sms_ = prop.multiProcessorCount;
@@ -338,12 +340,27 @@ void CutEngine::upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
 
 // ------------------------------------------------------------------ the pipeline
 #ifndef B200_EMULATE
-template <int D> static void launch_classify_lists(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, int grid, cudaStream_t st)
+template <int D, int IT> static void launch_classify_lists_it(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, u32 nrows, int grid, cudaStream_t st)
 {
-	if (dv) k_classify_lists<D, true><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi);
-	else k_classify_lists<D, false><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0);
+	if (dv) k_classify_lists<D, true, IT><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi, nrows);
+	else k_classify_lists<D, false, IT><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0, nrows);
 }
-
+// grid: one block per group of IT*512 rows, capped at the number of co-resident blocks (persistent
+// grid-stride loop beyond that), so the last wave is never a partial one
+template <int D> static void launch_classify_lists(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, u32 nrows, int num_sms, cudaStream_t st)
+{
+	const bool fixed = D >= 2 && D <= 8;
+	const int it = fixed ? g_k1_it : 1;
+	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE;
+	const u32 groups = ntiles * (B200_TILE / (2 * K_THREADS) / it);
+	const int per_sm = it >= 4 ? 2 : it == 2 ? 4 : 8;
+	// every block gets the same number of groups (+-1): no partial last wave
+	const u32 resident = (u32)(num_sms * per_sm), rounds = std::max<u32>(1, (groups + resident - 1) / resident);
+	const int grid = (int)std::max<u32>(1, (groups + rounds - 1) / rounds);
+	if (it >= 4) launch_classify_lists_it<D, 4>(S, P, dv, di, vi, nrows, grid, st);
+	else if (it == 2) launch_classify_lists_it<D, 2>(S, P, dv, di, vi, nrows, grid, st);
+	else launch_classify_lists_it<D, 1>(S, P, dv, di, vi, nrows, grid, st);
+}
 template <int D> static void launch_classify(const DevState &S, int grid, cudaStream_t st) { k_classify<D><<<grid, K_THREADS, 0, st>>>(S); }
 
 void CutEngine::launch_classify_dim(int gcls)
@@ -401,6 +418,20 @@ void CutEngine::launch_part_b(bool rerun)
 	CK(cudaGetLastError());
 }
 
+void CutEngine::launch_k1_lists(const CutParams &P, const double *dv, const unsigned char *di, u64 vi)
+{
+	switch (d_) {
+	case 2: launch_classify_lists<2>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	case 3: launch_classify_lists<3>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	case 4: launch_classify_lists<4>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	case 5: launch_classify_lists<5>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	case 6: launch_classify_lists<6>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	case 7: launch_classify_lists<7>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	case 8: launch_classify_lists<8>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	default: launch_classify_lists<0>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	}
+}
+
 // small-cut path: streaming K1 + single-CTA tail (+ multi-block K4 pair test for medium cuts)
 void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 {
@@ -410,20 +441,8 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 		small_dirty_ = false;
 		stats_.kernel_launches++;
 	}
-	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
-	const u32 groups = ntiles * ((d_ >= 2 && d_ <= 8) ? 1 : B200_TILE / (2 * K_THREADS));
-	const int g = (int)std::max<u32>(1, std::min<u32>(groups, (u32)num_sms_ * 8));
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
-	switch (d_) {
-	case 2: launch_classify_lists<2>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	case 3: launch_classify_lists<3>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	case 4: launch_classify_lists<4>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	case 5: launch_classify_lists<5>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	case 6: launch_classify_lists<6>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	case 7: launch_classify_lists<7>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	case 8: launch_classify_lists<8>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	default: launch_classify_lists<0>(S_, P, dev_vals_, dev_ideal_, dev_index_, g, STREAM); break;
-	}
+	launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_);
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 	// tiny cuts run the tail in one CTA (block barriers); larger ones in an 8-CTA cluster
 	const bool tiny = expect_vis_ <= 96 && expect_m_ <= B200_K4_SMALL / 2;
@@ -877,25 +896,13 @@ double CutEngine::classify_bench(const CutParams &P, int iters, int flush_l2)
 	ensure_facets(P.facet + 1);
 	const size_t flush_bytes = (size_t)256 << 20;     // > 126 MB L2
 	if (flush_l2 && !flush_buf_) flush_buf_ = dalloc(flush_bytes);
-	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
-	const u32 groups = ntiles * ((d_ >= 2 && d_ <= 8) ? 1 : B200_TILE / (2 * K_THREADS));
-	const int g = (int)std::max<u32>(1, std::min<u32>(groups, (u32)num_sms_ * 8));
 	double total = 0;
 	for (int it = 0; it < iters; it++) {
 		CK(cudaMemsetAsync(S_.tile_cnt, 0, (size_t)S_.cap_tiles * 4, STREAM));
 		k_reset_small<<<1, 32, 0, STREAM>>>(S_);
-		if (flush_l2) CK(cudaMemsetAsync(flush_buf_, it & 0xff, flush_bytes, STREAM));
+		if (flush_l2) k_flush_read<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>((const uint4 *)flush_buf_, flush_bytes / 16, (unsigned *)S_.dbg + 60);
 		CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
-		switch (d_) {       // the streaming K1 of the cut path, exactly as launch_small() launches it
-		case 2: launch_classify_lists<2>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		case 3: launch_classify_lists<3>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		case 4: launch_classify_lists<4>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		case 5: launch_classify_lists<5>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		case 6: launch_classify_lists<6>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		case 7: launch_classify_lists<7>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		case 8: launch_classify_lists<8>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		default: launch_classify_lists<0>(S_, P, nullptr, nullptr, 0, g, STREAM); break;
-		}
+		launch_k1_lists(P, nullptr, nullptr, 0);     // the streaming K1 of the cut path, exactly as launch_small() launches it
 		CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 		CK(cudaEventSynchronize((cudaEvent_t)ev_[1]));
 		float ms = 0;

@@ -88,6 +88,7 @@ private:
 	void ensure_facets(u32 need);
 	void launch_part_a(const CutParams &P);
 	void launch_classify_dim(int gcls);
+	void launch_k1_lists(const CutParams &P, const double *dv, const unsigned char *di, u64 vi);
 	void launch_small(const CutParams &P, int mode, bool header_only);
 	void launch_k4_and_tail2(bool header_only);
 	bool use_small_path() const;

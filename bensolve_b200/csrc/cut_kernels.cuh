@@ -642,9 +642,9 @@ __global__ void k_gc_finish(DevState S, u32 n_live, const u32 *inc_total, const 
 // K1, streaming form: all loads of a tile are independent (no liveness test before the coordinate
 // loads), classes are written as before, and the rare non-PLUS rows go to a per-tile list through
 // one atomic each -- no shared memory, no barrier.
-template <int D, bool FROMDEV>
-__global__ void __launch_bounds__(K_THREADS) k_classify_lists(DevState S, CutParams Parg, const double *vals,
-                                                              const unsigned char *ideal, u64 vi)
+template <int D, bool FROMDEV, int ITREQ>
+__global__ void __launch_bounds__(K_THREADS, (ITREQ >= 4 ? 2 : ITREQ == 2 ? 4 : 8)) k_classify_lists(DevState S, CutParams Parg, const double *vals,
+                                                              const unsigned char *ideal, u64 vi, u32 nrows_host)
 {
 	const int d = D > 0 ? D : S.d;
 	double h[D > 0 ? D : B200_MAXD];
@@ -672,11 +672,11 @@ __global__ void __launch_bounds__(K_THREADS) k_classify_lists(DevState S, CutPar
 		S.facet_cnt[P.facet] = 0;
 		S.facet_alive[P.facet] = 1;
 	}
-	const u32 nrows = S.ctl->nrows;
+	const u32 nrows = nrows_host;   // the host's copy of ctl->nrows (exact: it reads the header after every cut)
 	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE;
 	const size_t cap = S.cap_rows;
 	constexpr int NIT = B200_TILE / (2 * K_THREADS);
-	constexpr int IT = (D > 0 && D <= 8) ? NIT : 1;       // loads kept in flight per thread: IT * D double2
+	constexpr int IT = (D > 0 && D <= 8) ? (ITREQ < NIT ? ITREQ : NIT) : 1;   // loads kept in flight per thread: IT * D double2
 	for (u32 tg = blockIdx.x; tg < ntiles * (NIT / IT); tg += gridDim.x) {
 		const u32 tile = tg / (NIT / IT), it0 = (tg % (NIT / IT)) * IT;
 		u32 lw[IT], iw[IT];
@@ -1025,4 +1025,16 @@ __global__ void k_reset_small(DevState S)
 	S.ctl->n_strict = 0;
 	S.ctl->min_strict_row = B200_NONE;
 	S.ctl->n_zp = 0;
+}
+
+// L2 flush for measurements: a read-only sweep over a buffer larger than L2 leaves clean lines behind
+// (a memset would leave dirty ones whose write-back then competes with the timed kernel's reads)
+__global__ void __launch_bounds__(K_THREADS) k_flush_read(const uint4 *buf, size_t n, unsigned *sink)
+{
+	unsigned acc = 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const uint4 v = buf[i];
+		acc ^= v.x ^ v.y ^ v.z ^ v.w;
+	}
+	if (acc == 0x9e3779b9u) *sink = acc;
 }
