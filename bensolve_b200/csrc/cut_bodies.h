@@ -206,6 +206,7 @@ B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 
 	for (int t = 0; t < d; t++) S.coord[t * cap + nw] = B200_ADD(base[t], B200_MUL(mu, dir[t]));
 	if (both) set_bit_atomic(S.ideal, nw);
 	set_bit_atomic(S.live, nw);
+	S.cls[nw] = CLS_PLUS;                     // invariant: every live row reads PLUS between cuts
 	S.row_slot[nw] = ctl->slot_cnt + j;
 	S.new_parent[j] = B200_NONE;
 	S.root[nw] = B200_NONE;
@@ -258,6 +259,7 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 	for (int t = 0; t < S.d; t++) S.coord[t * cap + nw] = S.coord[t * cap + v];
 	if (bit_test(S.ideal, v)) set_bit_atomic(S.ideal, nw);
 	set_bit_atomic(S.live, nw);
+	S.cls[nw] = CLS_PLUS;
 	S.row_slot[nw] = ctl->slot_cnt + j;
 	S.new_parent[j] = S.row_slot[v];
 	S.root[nw] = S.row_slot[v] < P.batch_first ? S.row_slot[v] : S.root[v];
@@ -393,12 +395,15 @@ B200_HD void he_finish_vertex(const DevState &S, const CutParams &P, u32 i)
 	retire_row(S, v, i);
 }
 
+// redundant halfspace: nothing is cut, the non-PLUS rows K1 marked go back to PLUS
+B200_HD void reset_class(const DevState &S, u32 i) { S.cls[S.vis[i]] = CLS_PLUS; }
+
 // after all counts are final: a facet without live vertices dies (clean rule; the reference's
 // variant, bslv_poly.c:686-687/:705, leaves order-dependent ghosts -- SURVEY section 0)
 B200_HD void collect_dead_facets(const DevState &S, u32 i)
 {
-	if (S.dead_slots[i] == B200_NONE) return;
 	u32 v = S.vis[i];
+	if (S.dead_slots[i] == B200_NONE) { S.cls[v] = CLS_PLUS; return; }   // a ZERO+ row nobody reached stays as it is
 	const u32 *iv = S.inc_pool + S.inc_off[v];
 	for (u32 a = 0, n = S.inc_len[v]; a < n; a++) {
 		u32 fc = iv[a];

@@ -520,14 +520,20 @@ static bool emu_classify(DevState &S, const CutParams &P)
 	for (u32 r = 0; r < c->nrows; r++) {
 		bool strict, zp;
 		u8 cl = classify_row(S, P, r, strict, zp);
-		S.cls[r] = cl;
 		if (cl == CLS_DEAD) continue;
+		if (cl != CLS_PLUS) S.cls[r] = cl;           // PLUS rows already read PLUS (invariant between cuts)
+		else if (S.cls[r] != CLS_PLUS) fail("class invariant broken: live row does not read PLUS between cuts");
 		c->n_live_scanned++;
 		if (strict) { c->n_strict++; if (r < c->min_strict_row) c->min_strict_row = r; }
 		if (zp) c->n_zp++;
 		if (cl != CLS_PLUS) S.vis[c->n_vis++] = r;
 	}
-	if (c->n_strict == 0) { c->status |= ST_REDUNDANT; S.facet_alive[P.facet] = 0; return false; }
+	if (c->n_strict == 0) {
+		c->status |= ST_REDUNDANT;
+		S.facet_alive[P.facet] = 0;
+		for (u32 i = 0; i < c->n_vis; i++) reset_class(S, i);
+		return false;
+	}
 	c->min_strict_slot = S.row_slot[c->min_strict_row];
 	return true;
 }
@@ -975,6 +981,7 @@ void CutEngine::compact()
 	T.inc_off = (u32 *)shadow_[5]; T.inc_len = (u32 *)shadow_[6]; T.adj_off = (u32 *)shadow_[7]; T.adj_len = (u32 *)shadow_[8];
 	T.inc_pool = (u32 *)shadow_[9]; T.adj_pool = (u32 *)shadow_[10];
 	k_gc_gather<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, T, n_live, remap, old_of, new_inc_off, new_adj_off);
+	CK(cudaMemsetAsync(S_.cls, 0, nrows, STREAM));     // rows moved: every live row reads PLUS again
 	k_gc_finish<<<1, 32, 0, STREAM>>>(S_, n_live, totals + 1, totals + 2);
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(pinned_hdr_, S_.ctl, sizeof(CutCtl), cudaMemcpyDeviceToHost, STREAM));
@@ -1021,6 +1028,7 @@ void CutEngine::compact()
 	for (void *p : old) dfree(p);
 	S.coord = coord; S.row_slot = row_slot; S.root = root; S.live = live; S.ideal = ideal; S.inc_off = inc_off; S.inc_len = inc_len;
 	S.adj_off = adj_off; S.adj_len = adj_len; S.inc_pool = inc_pool; S.adj_pool = adj_pool;
+	memset(S.cls, 0, nrows);
 	S.ctl->nrows = S.ctl->n_live = n_live;
 	S.ctl->inc_used = iu;
 	S.ctl->adj_used = au;

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(DevState S)
 __global__ void __launch_bounds__(K_THREADS) k_scatter(DevState S)
 {
 	__shared__ u32 ws[33];
-	if (S.ctl->status & ST_SKIP_A) return;
+	if (S.ctl->status & (ST_SKIP_A & ~(u32)ST_REDUNDANT)) return;   // also runs for a redundant halfspace: its marks are undone below
 	const u32 nrows = S.ctl->nrows;
 	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE;
 	for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -324,6 +324,10 @@ __global__ void __launch_bounds__(K_THREADS) k_emit(DevState S)
 
 __global__ void __launch_bounds__(K_THREADS) k_dead_facets(DevState S)
 {
+	if (S.ctl->status & ST_REDUNDANT) {
+		B200_GRID_STRIDE(i, S.ctl->n_vis) reset_class(S, (u32)i);
+		return;
+	}
 	if (S.ctl->status & ST_SKIP_A) return;
 	B200_GRID_STRIDE(i, S.ctl->n_vis) collect_dead_facets(S, (u32)i);
 }
@@ -706,14 +710,14 @@ __global__ void __launch_bounds__(K_THREADS, (ITREQ >= 4 ? 2 : ITREQ == 2 ? 4 : 
 				const bool id = (iw[it] >> s) & 1u;
 				const double hi = id ? hi1 : hi0, mid = id ? mid1 : mid0, lo = id ? lo1 : lo0;
 				c[s] = t[s] > hi ? CLS_PLUS : t[s] > mid ? CLS_ZP : t[s] > lo ? CLS_ZERO : CLS_MINUS;
-				if (c[s] != CLS_PLUS) {                  // rare
+				if (c[s] != CLS_PLUS) {                  // rare; PLUS rows already read PLUS (invariant between cuts)
+					S.cls[r + s] = c[s];
 					const u32 pos = atomicAdd(&S.tile_cnt[tile], 1u);
 					if (pos < B200_TLIST) S.tile_list[(size_t)tile * B200_TLIST + pos] = r + s;
 					if (c[s] == CLS_ZP) atomicAdd(&S.ctl->n_zp, 1u);
 					if (t[s] < lo) { atomicAdd(&S.ctl->n_strict, 1u); atomicMin(&S.ctl->min_strict_row, r + s); }
 				}
 			}
-			*reinterpret_cast<uchar2 *>(S.cls + r) = make_uchar2(c[0], c[1]);
 		}
 	}
 }
@@ -859,7 +863,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	{
 		// one warp per tile: each lane places its entries at their rank within the tile's list
 		// (rows are distinct), so the visited list comes out ascending without a sort
-		const bool gather = !(c->status & (ST_REDUNDANT | ST_NEED_BIG));
+		const bool gather = !(c->status & ST_NEED_BIG);
 		const u32 lane = threadIdx.x & 31;
 		for (u32 t = ctid >> 5; t < ntiles; t += NC * TAIL_THREADS / 32) {
 			const u32 cnt = S.tile_cnt[t];
@@ -879,6 +883,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	}
 	TAIL_SYNC();
 	if (c->status & (ST_REDUNDANT | ST_NEED_BIG)) {
+		if (!(c->status & ST_NEED_BIG)) TAIL_LOOP(i, c->n_vis) reset_class(S, i);
 		if (rank == 0) tail_stage_header(S, 0, header_only);
 		TAIL_SYNC();
 		if (ctid == 0) tail_reset_for_next_cut(S);
