@@ -96,6 +96,101 @@ static void h2d(void *dst, const void *src, size_t n) { if (n) memcpy(dst, src, 
 static void d2h(void *dst, const void *src, size_t n) { if (n) memcpy(dst, src, n); }
 #endif
 
+
+// ------------------------------------------------------------------ multi-GPU communicator (one per process)
+// NCCL is resolved at run time from the library the host process already loaded (torch bundles
+// libnccl.so.2), so the cut engine has no link-time dependency on it.
+struct Comm {
+	int rank = 0, nranks = 1;
+	void *nccl_comm = nullptr;
+	b200_allgather_fn callback = nullptr;     // host all-gather (test double only)
+};
+static Comm g_comm;
+int b200_comm_rank() { return g_comm.rank; }
+int b200_comm_size() { return g_comm.nranks; }
+
+#ifndef B200_EMULATE
+#include <dlfcn.h>
+typedef struct { char internal[128]; } nccl_unique_id;
+typedef int (*nccl_get_unique_id_t)(nccl_unique_id *);
+typedef int (*nccl_comm_init_rank_t)(void **, int, nccl_unique_id, int);
+typedef int (*nccl_all_gather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*nccl_comm_destroy_t)(void *);
+typedef const char *(*nccl_get_error_string_t)(int);
+static struct {
+	void *handle = nullptr;
+	nccl_get_unique_id_t get_unique_id = nullptr;
+	nccl_comm_init_rank_t comm_init_rank = nullptr;
+	nccl_all_gather_t all_gather = nullptr;
+	nccl_comm_destroy_t comm_destroy = nullptr;
+	nccl_get_error_string_t get_error_string = nullptr;
+} g_nccl;
+static void load_nccl()
+{
+	if (g_nccl.handle) return;
+	const char *names[] = {getenv("B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+	for (const char *n : names) {
+		if (!n) continue;
+		g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+		if (g_nccl.handle) break;
+	}
+	if (!g_nccl.handle) fail("bensolve_b200: cannot load libnccl.so.2 (import torch first, or set B200_NCCL_LIB)");
+	g_nccl.get_unique_id = (nccl_get_unique_id_t)dlsym(g_nccl.handle, "ncclGetUniqueId");
+	g_nccl.comm_init_rank = (nccl_comm_init_rank_t)dlsym(g_nccl.handle, "ncclCommInitRank");
+	g_nccl.all_gather = (nccl_all_gather_t)dlsym(g_nccl.handle, "ncclAllGather");
+	g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(g_nccl.handle, "ncclCommDestroy");
+	g_nccl.get_error_string = (nccl_get_error_string_t)dlsym(g_nccl.handle, "ncclGetErrorString");
+	if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.all_gather || !g_nccl.comm_destroy) fail("bensolve_b200: libnccl lacks a required symbol");
+}
+static void nccl_check(int rc, const char *what)
+{
+	if (rc != 0) fail(std::string("NCCL error in ") + what + ": " + (g_nccl.get_error_string ? g_nccl.get_error_string(rc) : "?"));
+}
+int b200_comm_make_id(char out[128])
+{
+	try {
+		load_nccl();
+		nccl_unique_id id;
+		nccl_check(g_nccl.get_unique_id(&id), "ncclGetUniqueId");
+		memcpy(out, id.internal, 128);
+		return 0;
+	} catch (const std::exception &) { return 1; }
+}
+int b200_comm_start(int rank, int nranks, const char id_bytes[128])
+{
+	try {
+		if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) fail("b200_comm_init: bad rank / size");
+		if (nranks > 1) {
+			load_nccl();
+			bind_device();
+			nccl_unique_id id;
+			memcpy(id.internal, id_bytes, 128);
+			nccl_check(g_nccl.comm_init_rank(&g_comm.nccl_comm, nranks, id, rank), "ncclCommInitRank");
+		}
+		g_comm.rank = rank;
+		g_comm.nranks = nranks;
+		return 0;
+	} catch (const std::exception &) { return 1; }
+}
+void b200_comm_stop()
+{
+	if (g_comm.nccl_comm) g_nccl.comm_destroy(g_comm.nccl_comm);
+	g_comm = Comm();
+}
+int b200_comm_set_callback(b200_allgather_fn) { b200_set_error("the product library exchanges over NCCL only"); return 1; }
+#else
+int b200_comm_make_id(char out[128]) { memset(out, 0, 128); return 0; }
+int b200_comm_start(int rank, int nranks, const char *)
+{
+	if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return 1;
+	g_comm.rank = rank;
+	g_comm.nranks = nranks;
+	return 0;
+}
+void b200_comm_stop() { g_comm = Comm(); }
+int b200_comm_set_callback(b200_allgather_fn fn) { g_comm.callback = fn; return 0; }
+#endif
+
 template <class T> static void regrow(T *&p, size_t new_n, size_t keep_n)
 {
 	T *q = (T *)dalloc(new_n * sizeof(T));
@@ -130,6 +225,10 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	S_.ctl = (CutCtl *)dalloc(sizeof(CutCtl));
 	S_.cur = (CutParams *)dalloc(sizeof(CutParams));
 	S_.dbg = (u64 *)dalloc(32 * sizeof(u64));
+	nranks_ = g_comm.nranks;
+	rank_ = g_comm.rank;
+	S_.xchg_send = (u32 *)dalloc((size_t)B200_XCHG_WORDS * 4);
+	S_.xchg_recv = (u32 *)dalloc((size_t)B200_XCHG_WORDS * 4 * nranks_);
 	S_.he_off = (u32 *)dalloc((B200_VIS_MAX + 1) * sizeof(u32));
 	S_.he_own = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
 	S_.he_inc = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
@@ -160,7 +259,7 @@ CutEngine::~CutEngine()
 	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
 	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.tile_list, S_.dbg, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.tile_list, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 	drop_shadow();
 #ifndef B200_EMULATE
@@ -340,26 +439,25 @@ void CutEngine::upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
 
 // ------------------------------------------------------------------ the pipeline
 #ifndef B200_EMULATE
-template <int D, int IT> static void launch_classify_lists_it(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, u32 nrows, int grid, cudaStream_t st)
+template <int D, int IT> static void launch_classify_lists_it(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, u32 nrows, u32 tlo, u32 thi, int grid, cudaStream_t st)
 {
-	if (dv) k_classify_lists<D, true, IT><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi, nrows);
-	else k_classify_lists<D, false, IT><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0, nrows);
+	if (dv) k_classify_lists<D, true, IT><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi, nrows, tlo, thi);
+	else k_classify_lists<D, false, IT><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0, nrows, tlo, thi);
 }
 // grid: one block per group of IT*512 rows, capped at the number of co-resident blocks (persistent
 // grid-stride loop beyond that), so the last wave is never a partial one
-template <int D> static void launch_classify_lists(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, u32 nrows, int num_sms, cudaStream_t st)
+template <int D> static void launch_classify_lists(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, u32 nrows, u32 tlo, u32 thi, int num_sms, cudaStream_t st)
 {
 	const bool fixed = D >= 2 && D <= 8;
 	const int it = fixed ? g_k1_it : 1;
-	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE;
-	const u32 groups = ntiles * (B200_TILE / (2 * K_THREADS) / it);
+	const u32 groups = (thi - tlo) * (B200_TILE / (2 * K_THREADS) / it);
 	const int per_sm = it >= 4 ? 2 : it == 2 ? 4 : 8;
 	// every block gets the same number of groups (+-1): no partial last wave
 	const u32 resident = (u32)(num_sms * per_sm), rounds = std::max<u32>(1, (groups + resident - 1) / resident);
 	const int grid = (int)std::max<u32>(1, (groups + rounds - 1) / rounds);
-	if (it >= 4) launch_classify_lists_it<D, 4>(S, P, dv, di, vi, nrows, grid, st);
-	else if (it == 2) launch_classify_lists_it<D, 2>(S, P, dv, di, vi, nrows, grid, st);
-	else launch_classify_lists_it<D, 1>(S, P, dv, di, vi, nrows, grid, st);
+	if (it >= 4) launch_classify_lists_it<D, 4>(S, P, dv, di, vi, nrows, tlo, thi, grid, st);
+	else if (it == 2) launch_classify_lists_it<D, 2>(S, P, dv, di, vi, nrows, tlo, thi, grid, st);
+	else launch_classify_lists_it<D, 1>(S, P, dv, di, vi, nrows, tlo, thi, grid, st);
 }
 template <int D> static void launch_classify(const DevState &S, int grid, cudaStream_t st) { k_classify<D><<<grid, K_THREADS, 0, st>>>(S); }
 
@@ -418,17 +516,27 @@ void CutEngine::launch_part_b(bool rerun)
 	CK(cudaGetLastError());
 }
 
-void CutEngine::launch_k1_lists(const CutParams &P, const double *dv, const unsigned char *di, u64 vi)
+void CutEngine::launch_k1_lists(const CutParams &P, const double *dv, const unsigned char *di, u64 vi, bool sharded)
 {
-	switch (d_) {
-	case 2: launch_classify_lists<2>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
-	case 3: launch_classify_lists<3>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
-	case 4: launch_classify_lists<4>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
-	case 5: launch_classify_lists<5>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
-	case 6: launch_classify_lists<6>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
-	case 7: launch_classify_lists<7>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
-	case 8: launch_classify_lists<8>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
-	default: launch_classify_lists<0>(S_, P, dv, di, vi, hdr_.nrows, num_sms_, STREAM); break;
+	u32 lo, hi;
+	tile_range(sharded, lo, hi);
+	{   // launched even for an empty share: block 0 publishes the halfspace on this rank's device
+		switch (d_) {
+		case 2: launch_classify_lists<2>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		case 3: launch_classify_lists<3>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		case 4: launch_classify_lists<4>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		case 5: launch_classify_lists<5>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		case 6: launch_classify_lists<6>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		case 7: launch_classify_lists<7>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		case 8: launch_classify_lists<8>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		default: launch_classify_lists<0>(S_, P, dv, di, vi, hdr_.nrows, lo, hi, num_sms_, STREAM); break;
+		}
+	}
+	if (sharded && nranks_ > 1) {        // exchange: pack -> all-gather over NVLink -> merge
+		k_xchg_pack<<<1, TAIL_THREADS, 0, STREAM>>>(S_, lo, hi);
+		nccl_check(g_nccl.all_gather(S_.xchg_send, S_.xchg_recv, (size_t)B200_XCHG_WORDS * 4, 0 /* ncclChar */, g_comm.nccl_comm, STREAM), "ncclAllGather");
+		k_xchg_merge<<<1, TAIL_THREADS, 0, STREAM>>>(S_, (u32)nranks_);
+		stats_.kernel_launches += 3;
 	}
 }
 
@@ -442,7 +550,7 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 		stats_.kernel_launches++;
 	}
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
-	launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_);
+	launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_, true);
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 	// tiny cuts run the tail in one CTA (block barriers); larger ones in an 8-CTA cluster
 	const bool tiny = expect_vis_ <= 96 && expect_m_ <= B200_K4_SMALL / 2;
@@ -504,8 +612,10 @@ static CutParams emu_params(const DevState &S, const CutParams &Pin, const doubl
 	}
 	return P;
 }
-// K1 + ordered compaction + decision; returns false when the cut ends here (redundant)
-static bool emu_classify(DevState &S, const CutParams &P)
+// K1 over rows [row_lo, row_hi) + ordered compaction (multi-rank: exchange of the per-rank records
+// through the host all-gather callback, then merge) + decision; returns false when the cut ends
+// here (redundant)
+static bool emu_classify(DevState &S, const CutParams &P, u32 row_lo = 0, u32 row_hi = B200_NONE, int nranks = 1)
 {
 	CutCtl *c = S.ctl;
 	*S.cur = P;
@@ -517,7 +627,8 @@ static bool emu_classify(DevState &S, const CutParams &P)
 	c->n_local = c->wl = c->mpad = c->n_surv = 0;
 	S.facet_cnt[P.facet] = 0;
 	S.facet_alive[P.facet] = 1;
-	for (u32 r = 0; r < c->nrows; r++) {
+	row_hi = std::min<u32>(row_hi, c->nrows);
+	for (u32 r = row_lo; r < row_hi; r++) {
 		bool strict, zp;
 		u8 cl = classify_row(S, P, r, strict, zp);
 		if (cl == CLS_DEAD) continue;
@@ -527,6 +638,32 @@ static bool emu_classify(DevState &S, const CutParams &P)
 		if (strict) { c->n_strict++; if (r < c->min_strict_row) c->min_strict_row = r; }
 		if (zp) c->n_zp++;
 		if (cl != CLS_PLUS) S.vis[c->n_vis++] = r;
+	}
+	if (nranks > 1) {
+		if (!g_comm.callback) fail("multi-rank test double needs b200_comm_set_callback");
+		std::vector<u32> send(B200_XCHG_WORDS, 0), recv((size_t)B200_XCHG_WORDS * nranks, 0);
+		send[0] = c->n_strict; send[1] = c->min_strict_row; send[2] = c->n_zp;
+		send[3] = c->n_vis > B200_XCHG_CAP ? B200_NONE : c->n_vis;
+		for (u32 i = 0; i < c->n_vis && i < B200_XCHG_CAP; i++) send[4 + i] = S.vis[i] | ((u32)S.cls[S.vis[i]] << 30);
+		g_comm.callback(send.data(), recv.data(), (size_t)B200_XCHG_WORDS * 4);
+		c->n_strict = c->n_zp = c->n_vis = 0;
+		c->min_strict_row = B200_NONE;
+		bool over = false;
+		for (int g = 0; g < nranks; g++) {
+			const u32 *r = recv.data() + (size_t)g * B200_XCHG_WORDS;
+			c->n_strict += r[0];
+			c->min_strict_row = std::min(c->min_strict_row, r[1]);
+			c->n_zp += r[2];
+			if (r[3] == B200_NONE) { over = true; continue; }
+			for (u32 i = 0; i < r[3]; i++) {
+				const u32 row = r[4 + i] & 0x3FFFFFFFu;
+				S.vis[c->n_vis++] = row;
+				S.cls[row] = (u8)(r[4 + i] >> 30);
+			}
+		}
+		if (over) {            // as on the device: rerun unsharded through the multi-kernel path
+			if (c->n_strict) { c->status |= ST_NEED_BIG; c->min_strict_slot = S.row_slot[c->min_strict_row]; return false; }
+		}
 	}
 	if (c->n_strict == 0) {
 		c->status |= ST_REDUNDANT;
@@ -640,7 +777,9 @@ void CutEngine::launch_small(const CutParams &Pin, int mode, bool header_only)
 	DevState &S = S_;
 	CutCtl *c = S.ctl;
 	const CutParams P = emu_params(S, Pin, dev_vals_, dev_ideal_, dev_index_);
-	if (!emu_classify(S, P)) { launch_part_c(header_only); return; }
+	u32 tlo, thi;
+	tile_range(true, tlo, thi);
+	if (!emu_classify(S, P, tlo * B200_TILE, thi * B200_TILE, nranks_)) { launch_part_c(header_only); return; }
 	if (c->n_vis > B200_VIS_MAX) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
 	emu_zp(S, P);
 	u32 H = 0;
@@ -681,6 +820,18 @@ void CutEngine::fetch_delta()
 	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE | ST_NEED_BIG | ST_K4_PENDING))) memcpy(pinned_stage_, S_.stage, hdr_.stage_bytes);
 }
 #endif
+
+// this rank's share of the tiles (all of them on one GPU); ranges ascend with the rank
+void CutEngine::tile_range(bool sharded, u32 &lo, u32 &hi) const
+{
+	const u32 ntiles = (hdr_.nrows + B200_TILE - 1) / B200_TILE;
+	lo = 0;
+	hi = ntiles;
+	if (!sharded || nranks_ == 1) return;
+	const u32 per = (ntiles + nranks_ - 1) / nranks_;
+	lo = std::min<u32>(ntiles, per * rank_);
+	hi = std::min<u32>(ntiles, lo + per);
+}
 
 bool CutEngine::use_small_path() const
 {
@@ -908,7 +1059,7 @@ double CutEngine::classify_bench(const CutParams &P, int iters, int flush_l2)
 		k_reset_small<<<1, 32, 0, STREAM>>>(S_);
 		if (flush_l2) k_flush_read<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>((const uint4 *)flush_buf_, flush_bytes / 16, (unsigned *)S_.dbg + 60);
 		CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
-		launch_k1_lists(P, nullptr, nullptr, 0);     // the streaming K1 of the cut path, exactly as launch_small() launches it
+		launch_k1_lists(P, nullptr, nullptr, 0, false);     // the streaming K1 of the cut path, exactly as launch_small() launches it
 		CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 		CK(cudaEventSynchronize((cudaEvent_t)ev_[1]));
 		float ms = 0;

@@ -88,7 +88,8 @@ private:
 	void ensure_facets(u32 need);
 	void launch_part_a(const CutParams &P);
 	void launch_classify_dim(int gcls);
-	void launch_k1_lists(const CutParams &P, const double *dv, const unsigned char *di, u64 vi);
+	void launch_k1_lists(const CutParams &P, const double *dv, const unsigned char *di, u64 vi, bool sharded);
+	void tile_range(bool sharded, u32 &lo, u32 &hi) const;
 	void launch_small(const CutParams &P, int mode, bool header_only);
 	void launch_k4_and_tail2(bool header_only);
 	bool use_small_path() const;
@@ -115,6 +116,7 @@ private:
 	void *stream_ = nullptr;
 	void *ev_[4] = {nullptr, nullptr, nullptr, nullptr};
 	int num_sms_ = 148;
+	int nranks_ = 1, rank_ = 0;          // communicator at construction time
 	const double *dev_vals_ = nullptr;      // set while a device-resident batch is running
 	const unsigned char *dev_ideal_ = nullptr;
 	u64 dev_index_ = 0;
@@ -124,6 +126,15 @@ private:
 	u32 shadow_rows_ = 0, shadow_inc_ = 0, shadow_adj_ = 0;
 	EngineStats stats_;
 };
+
+// multi-GPU communicator (cut_engine.cu); the callback form exists in the host test double only
+typedef void (*b200_allgather_fn)(const void *send, void *recv, size_t bytes_per_rank);
+int b200_comm_make_id(char out[128]);
+int b200_comm_start(int rank, int nranks, const char id_bytes[128]);
+void b200_comm_stop();
+int b200_comm_set_callback(b200_allgather_fn fn);
+int b200_comm_rank();
+int b200_comm_size();
 
 // library-wide helpers (cut_engine.cu)
 void b200_set_error(const std::string &msg);

@@ -61,6 +61,7 @@ __global__ void k_begin(DevState S, CutParams P)
 	c->n_pairs = c->adj_new = c->n_dead_facets = 0;
 	c->n_live_scanned = 0;
 	c->n_local = c->wl = c->mpad = c->n_surv = 0;
+	c->vis_ready = 0;
 	S.facet_cnt[P.facet] = 0;
 	S.facet_alive[P.facet] = 1;
 }
@@ -99,6 +100,7 @@ __global__ void k_begin_dev(DevState S, const double *vals, const unsigned char 
 	c->n_pairs = c->adj_new = c->n_dead_facets = 0;
 	c->n_live_scanned = 0;
 	c->n_local = c->wl = c->mpad = c->n_surv = 0;
+	c->vis_ready = 0;
 	S.facet_cnt[facet] = 0;
 	S.facet_alive[facet] = 1;
 }
@@ -648,7 +650,7 @@ __global__ void k_gc_finish(DevState S, u32 n_live, const u32 *inc_total, const 
 // one atomic each -- no shared memory, no barrier.
 template <int D, bool FROMDEV, int ITREQ>
 __global__ void __launch_bounds__(K_THREADS, (ITREQ >= 4 ? 2 : ITREQ == 2 ? 4 : 8)) k_classify_lists(DevState S, CutParams Parg, const double *vals,
-                                                              const unsigned char *ideal, u64 vi, u32 nrows_host)
+                                                              const unsigned char *ideal, u64 vi, u32 nrows_host, u32 tile_lo, u32 tile_hi)
 {
 	const int d = D > 0 ? D : S.d;
 	double h[D > 0 ? D : B200_MAXD];
@@ -676,13 +678,13 @@ __global__ void __launch_bounds__(K_THREADS, (ITREQ >= 4 ? 2 : ITREQ == 2 ? 4 : 
 		S.facet_cnt[P.facet] = 0;
 		S.facet_alive[P.facet] = 1;
 	}
-	const u32 nrows = nrows_host;   // the host's copy of ctl->nrows (exact: it reads the header after every cut)
-	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE;
+	// rows [tile_lo, tile_hi) * 2048: the whole polytope on one GPU, this rank's share when sharded
+	(void)nrows_host;
 	const size_t cap = S.cap_rows;
 	constexpr int NIT = B200_TILE / (2 * K_THREADS);
 	constexpr int IT = (D > 0 && D <= 8) ? (ITREQ < NIT ? ITREQ : NIT) : 1;   // loads kept in flight per thread: IT * D double2
-	for (u32 tg = blockIdx.x; tg < ntiles * (NIT / IT); tg += gridDim.x) {
-		const u32 tile = tg / (NIT / IT), it0 = (tg % (NIT / IT)) * IT;
+	for (u32 tg = blockIdx.x; tg < (tile_hi - tile_lo) * (NIT / IT); tg += gridDim.x) {
+		const u32 tile = tile_lo + tg / (NIT / IT), it0 = (tg % (NIT / IT)) * IT;
 		u32 lw[IT], iw[IT];
 		double2 x[IT][D > 0 ? D : B200_MAXD];
 #pragma unroll
@@ -761,6 +763,7 @@ __device__ __forceinline__ void tail_reset_for_next_cut(const DevState &S)
 	S.ctl->n_strict = 0;
 	S.ctl->min_strict_row = B200_NONE;
 	S.ctl->n_zp = 0;
+	S.ctl->vis_ready = 0;
 }
 
 // phases after K4: adjacency build, commit, delta record (also the body of k_tail2)
@@ -839,8 +842,10 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 			c->n_local = c->wl = c->mpad = c->n_surv = 0;
 			c->scratch_flag = 0;
 		}
-		u32 carry = 0, over = 0;
-		for (u32 base = 0; base < ntiles; base += TAIL_THREADS) {
+		const u32 merged = c->vis_ready;              // multi-GPU: k_xchg_merge already built the visited list
+		u32 carry = 0, over = (merged == 2);
+		if (merged) carry = c->n_vis_merged;
+		for (u32 base = 0; base < ntiles && !merged; base += TAIL_THREADS) {
 			u32 t = base + threadIdx.x, v = t < ntiles ? S.tile_cnt[t] : 0, tot;
 			over |= (v > B200_TLIST);
 			u32 e = block_excl_scan(v, ws, tot);
@@ -865,7 +870,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 		// (rows are distinct), so the visited list comes out ascending without a sort
 		const bool gather = !(c->status & ST_NEED_BIG);
 		const u32 lane = threadIdx.x & 31;
-		for (u32 t = ctid >> 5; t < ntiles; t += NC * TAIL_THREADS / 32) {
+		for (u32 t = ctid >> 5; t < ntiles && !c->vis_ready; t += NC * TAIL_THREADS / 32) {
 			const u32 cnt = S.tile_cnt[t];
 			if (!cnt) continue;
 			__syncwarp();
@@ -1030,6 +1035,7 @@ __global__ void k_reset_small(DevState S)
 	S.ctl->n_strict = 0;
 	S.ctl->min_strict_row = B200_NONE;
 	S.ctl->n_zp = 0;
+	S.ctl->vis_ready = 0;
 }
 
 // L2 flush for measurements: a read-only sweep over a buffer larger than L2 leaves clean lines behind
@@ -1042,4 +1048,90 @@ __global__ void __launch_bounds__(K_THREADS) k_flush_read(const uint4 *buf, size
 		acc ^= v.x ^ v.y ^ v.z ^ v.w;
 	}
 	if (acc == 0x9e3779b9u) *sink = acc;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange
+// State is replicated, K1 is sharded by row range.  After its share of K1 a rank packs what it
+// found -- trigger counters and its non-PLUS rows with their classes, ascending -- into a fixed-size
+// record; one all-gather later every rank merges the records (rank ranges are ascending, so the
+// concatenation is the ordered visited list) and runs the rest of the cut identically.
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_xchg_pack(DevState S, u32 tile_lo, u32 tile_hi)
+{
+	__shared__ u32 ws[33];
+	CutCtl *c = S.ctl;
+	u32 *out = S.xchg_send;
+	const u32 nt = tile_hi - tile_lo;
+	u32 carry = 0, over = 0;
+	for (u32 base = 0; base < nt; base += TAIL_THREADS) {
+		u32 t = base + threadIdx.x, v = t < nt ? S.tile_cnt[tile_lo + t] : 0, tot;
+		over |= (v > B200_TLIST);
+		u32 e = block_excl_scan(v, ws, tot);
+		if (t < nt) S.tile_base[tile_lo + t] = carry + e;
+		carry += tot;
+	}
+	over = __syncthreads_or(over) || carry > B200_XCHG_CAP;
+	const u32 lane = threadIdx.x & 31;
+	for (u32 t = threadIdx.x >> 5; t < nt; t += TAIL_THREADS / 32) {
+		const u32 cnt = S.tile_cnt[tile_lo + t];
+		if (!cnt) continue;
+		__syncwarp();
+		if (lane == 0) S.tile_cnt[tile_lo + t] = 0;
+		if (over) continue;
+		u32 *dst = out + 4 + S.tile_base[tile_lo + t];
+		const u32 *src = S.tile_list + (size_t)(tile_lo + t) * B200_TLIST;
+		for (u32 q = lane; q < cnt; q += 32) {
+			const u32 key = src[q];
+			u32 rk = 0;
+			for (u32 x = 0; x < cnt; x++) rk += (src[x] < key);
+			dst[rk] = key | ((u32)S.cls[key] << 30);
+		}
+	}
+	if (threadIdx.x == 0) {
+		out[0] = c->n_strict;
+		out[1] = c->min_strict_row;
+		out[2] = c->n_zp;
+		out[3] = over ? B200_NONE : carry;
+		c->n_strict = 0;                 // local accumulators: the merged values are written by k_xchg_merge
+		c->min_strict_row = B200_NONE;
+		c->n_zp = 0;
+	}
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_xchg_merge(DevState S, u32 nranks)
+{
+	__shared__ u32 off[65];
+	CutCtl *c = S.ctl;
+	if (threadIdx.x == 0) {
+		u32 ns = 0, mr = B200_NONE, nz = 0, tot = 0, over = 0;
+		for (u32 g = 0; g < nranks; g++) {
+			const u32 *r = S.xchg_recv + (size_t)g * B200_XCHG_WORDS;
+			ns += r[0];
+			mr = min(mr, r[1]);
+			nz += r[2];
+			off[g] = tot;
+			if (r[3] == B200_NONE) over = 1; else tot += r[3];
+		}
+		off[nranks] = tot;
+		c->n_strict = ns;
+		c->min_strict_row = mr;
+		c->n_zp = nz;
+		c->n_vis_merged = over ? 0 : tot;
+		c->vis_ready = over ? 2 : 1;
+		off[64] = over;
+	}
+	__syncthreads();
+	if (off[64]) {
+		// a record overflowed: classes of remote rows are unknown; the multi-kernel path will
+		// re-classify everything unsharded.  Undo the marks of the local share first.
+		return;
+	}
+	for (u32 g = 0; g < nranks; g++) {
+		const u32 *r = S.xchg_recv + (size_t)g * B200_XCHG_WORDS + 4;
+		const u32 n = off[g + 1] - off[g];
+		for (u32 i = threadIdx.x; i < n; i += TAIL_THREADS) {
+			const u32 e = r[i], row = e & 0x3FFFFFFFu;
+			S.vis[off[g] + i] = row;
+			S.cls[row] = (u8)(e >> 30);
+		}
+	}
 }

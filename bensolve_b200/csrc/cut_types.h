@@ -87,7 +87,8 @@ struct CutCtl {
 	u32 n_surv;         // pairs that pass the AND+POPC filter
 	u32 stage_bytes;    // size of the packed delta record (header included)
 	u32 scratch_flag;   // cluster-wide 'something changed' flag of the ZERO+ closure
-	u32 reserved[1];
+	u32 n_vis_merged;   // multi-GPU: length of the merged visited list
+	u32 vis_ready;      // multi-GPU: the visited list was merged from all ranks' exchange records (1), or a record overflowed (2)
 };
 #define B200_STAGE_HDR 128u   // the packed delta starts with a copy of CutCtl, padded to this size
 
@@ -125,6 +126,9 @@ struct DevState {
 	u64 cap_stage;
 	CutCtl *ctl;
 	CutParams *cur;
+	// multi-GPU exchange (state replicated, K1 sharded by row range): per-rank record = XchgHeader + entries
+	u32 *xchg_send;      // [B200_XCHG_WORDS]
+	u32 *xchg_recv;      // [nranks * B200_XCHG_WORDS]
 	u64 *dbg;            // [32] phase time stamps of the tail kernel (diagnostics, flags bit0)
 };
 
@@ -132,4 +136,6 @@ struct DevState {
 #define B200_TLIST 256u  // capacity of one tile's list of non-PLUS rows (small-cut path)
 #define B200_VIS_MAX 4096u // most visited vertices the single-CTA tail handles
 #define B200_HE_CAP 65536u // most half-edges the single-CTA tail handles
-#define B200_K4_SMALL 256u // most new vertices whose pair test the single-CTA tail does itself
+#define B200_K4_SMALL 256u
+#define B200_XCHG_CAP 4096u   // most non-PLUS rows one rank can report per cut (else the multi-kernel path runs unsharded)
+#define B200_XCHG_WORDS (4u + B200_XCHG_CAP)  // header {n_strict, min_strict_row, n_zp, n_entries} + entries (row | class << 30) // most new vertices whose pair test the single-CTA tail does itself

@@ -853,6 +853,13 @@ extern "C" double b200_poly_classify_bench(poly_args *a, const double *hp, int i
 	GUARD_END("b200_poly_classify_bench")
 }
 
+// multi-GPU set-up (one process per GPU): rank 0 makes an id, the launcher broadcasts it, every rank
+// calls b200_comm_init BEFORE poly__initialise.  All ranks then issue the same call sequence.
+extern "C" int b200_comm_unique_id(char out[128]) { return b200_comm_make_id(out); }
+extern "C" int b200_comm_init(int rank, int nranks, const char id[128]) { return b200_comm_start(rank, nranks, id); }
+extern "C" void b200_comm_finalize(void) { b200_comm_stop(); }
+extern "C" int b200_comm_set_allgather_callback(void (*fn)(const void *, void *, size_t)) { return b200_comm_set_callback(fn); }
+
 extern "C" int b200_set_device(int device) { return b200_select_device(device); }
 extern "C" int b200_device_count(void) { return b200_num_devices(); }
 extern "C" const char *b200_version(void) { return "bensolve_b200 0.1 (sm_100a)"; }

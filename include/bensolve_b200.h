@@ -147,6 +147,16 @@ int b200_poly_get_stats(poly_args *, b200_stats *out);
  *        bit2 = always use the multi-kernel path, never the single-CTA tail (test hook) */
 int b200_poly_set_flags(poly_args *, unsigned flags);
 
+/* Multi-GPU (one process per GPU, state replicated, K1 sharded by row range, visited lists merged by
+ * an NCCL all-gather per cut).  Rank 0 calls b200_comm_unique_id, the launcher broadcasts the 128
+ * bytes, every rank calls b200_comm_init before poly__initialise; afterwards all ranks issue the
+ * same poly__* call sequence with the same arguments and hold identical state.
+ * b200_comm_set_allgather_callback exists for the host-side test double only (the product returns 1). */
+int b200_comm_unique_id(char out[128]);
+int b200_comm_init(int rank, int nranks, const char id[128]);
+void b200_comm_finalize(void);
+int b200_comm_set_allgather_callback(void (*fn)(const void *send, void *recv, size_t bytes_per_rank));
+
 /* Library-wide: device selection (before the first poly__initialise), version, last error text. */
 int b200_set_device(int device);
 int b200_device_count(void);

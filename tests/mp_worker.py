@@ -1,0 +1,38 @@
+"""Worker of the world_size-2 CPU test: both ranks replay the same traces through the sharded
+small-cut path of the host test double (K1 over this rank's rows, exchange through a gloo
+all-gather callback) and compare with the oracle."""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+import torch.distributed as dist  # noqa: E402
+
+from bensolve_b200 import build, capi, dist as bdist, polytopes as P  # noqa: E402
+from traces import small_traces  # noqa: E402
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank = dist.get_rank()
+    emul = capi.load_lib(build.build_emulation())
+    oracle = capi.load_lib(capi.ORACLE_SO)
+    assert bdist.init_comm(emul, emulate=True) == dist.get_world_size()
+    traces = small_traces()[::2] + [P.tangent_polytope(4, 700, 3), P.tangent_polytope(3, 3000, 3)]
+    for tr in traces:
+        a = capi.PolyEngine(oracle, tr.dim)
+        b = capi.PolyEngine(emul, tr.dim, flags=8 | (2 if tr.dim == 4 else 0))    # tail phases (+ eager compaction)
+        ra, rb = P.replay(a, tr), P.replay(b, tr)
+        assert ra == rb, tr.name
+        capi.compare_states(a.state(), b.state(), exact_coords=True)
+        a.kill(); b.kill()
+    bdist.finalize_comm(emul)
+    dist.barrier()
+    print(f"rank {rank}: {len(traces)} traces OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
