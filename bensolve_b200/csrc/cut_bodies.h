@@ -492,13 +492,13 @@ B200_HD void k4_push_pair(const DevState &S, u32 a, u32 b)
 	if (p < S.cap_pairs) { S.pair_a[p] = a; S.pair_b[p] = b; }
 }
 // scalar forms (host test double; the kernels use the tiled / warp-cooperative forms)
-B200_HD void k4_filter_pair(const DevState &S, u32 a, u32 b)
+B200_HD void k4_filter_pair_in(const DevState &S, const u64 *bits, u32 wl, u32 mpad, u32 a, u32 b)
 {
-	const CutCtl *c = S.ctl;
 	u32 n = 0;
-	for (u32 w = 0; w < c->wl; w++) n += popc64(S.bits[(size_t)w * c->mpad + a] & S.bits[(size_t)w * c->mpad + b]);
+	for (u32 w = 0; w < wl; w++) n += popc64(bits[(size_t)w * mpad + a] & bits[(size_t)w * mpad + b]);
 	if (n + 2 >= (u32)S.d) k4_push_survivor(S, a, b);
 }
+B200_HD void k4_filter_pair(const DevState &S, u32 a, u32 b) { k4_filter_pair_in(S, S.bits, S.ctl->wl, S.ctl->mpad, a, b); }
 B200_HD void k4_contain_pair(const DevState &S, u32 s)
 {
 	const CutCtl *c = S.ctl;

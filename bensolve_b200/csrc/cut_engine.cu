@@ -248,7 +248,7 @@ CutEngine::~CutEngine()
 {
 	if (getenv("B200_PHASES")) {
 		fprintf(stderr, "[b200] tail phase ns:");
-		for (int k = 0; k < 10; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
+		for (int k = 0; k < 13; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, " (per cut, %llu cuts)\n", (unsigned long long)stats_.cuts);
 		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions);
 	}
@@ -576,7 +576,17 @@ void CutEngine::launch_k4_and_tail2(bool header_only)
 {
 	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
 	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
-	k_tail2<1><<<1, TAIL_THREADS, 0, STREAM>>>(S_, header_only ? 1 : 0);
+	{
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(TAIL_CTAS);
+		cfg.blockDim = dim3(TAIL_THREADS);
+		cfg.stream = STREAM;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeClusterDimension;
+		at[0].val.clusterDim.x = TAIL_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+		cfg.attrs = at; cfg.numAttrs = 1;
+		CK(cudaLaunchKernelEx(&cfg, k_tail2<TAIL_CTAS>, S_, header_only ? 1 : 0));
+	}
 	stats_.kernel_launches += 3;
 }
 
@@ -915,7 +925,8 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 		{
 			u64 tp[16];
 			d2h(tp, S_.dbg, sizeof tp);
-			for (int k = 0; k < 10; k++) if (tp[k + 1] > tp[k] && tp[10] > tp[0]) stats_.phase_ns[k] += tp[k + 1] - tp[k];
+			for (int k = 0; k < 12; k++) if (tp[k] >= tp[0] && tp[k + 1] > tp[k] && k != 10) stats_.phase_ns[k] += tp[k + 1] - tp[k];
+			if (tp[11] >= tp[0] && tp[7] >= tp[0] && tp[11] > tp[7] && tp[9] < tp[0]) stats_.phase_ns[12] += tp[11] - tp[7];   // k4_filter + k4_contain + launch gaps
 		}
 		static const char *trace = getenv("B200_TRACE");
 		if (trace && ms > atof(trace))

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S)
 // inc(a) & inc(b) (edge_test, bslv_poly.c:487-505).  Lanes scan 32 candidate rows per step; only the
 // non-zero words of the mask are compared (a mask holds >= d-2 bits, rarely more than a few words).
 #define K4_NZ 8
-__device__ __forceinline__ void k4_contain_warp(const DevState &S, u32 s, u32 lane, u32 M, u32 wl, u32 mpad)
+__device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bits, u32 s, u32 lane, u32 M, u32 wl, u32 mpad)
 {
 	const u32 a = S.surv_a[s], b = S.surv_b[s];
 	bool adjacent = true;
@@ -422,7 +422,7 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, u32 s, u32 la
 		bool generic = false;
 		for (u32 w0 = 0; w0 < wl && !generic; w0 += 32) {
 			const u32 w = w0 + lane;
-			const u64 m = w < wl ? (S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b]) : 0;
+			const u64 m = w < wl ? (bits[(size_t)w * mpad + a] & bits[(size_t)w * mpad + b]) : 0;
 			u32 bal = __ballot_sync(0xffffffffu, m != 0);
 			while (bal) {
 				const int src = __ffs(bal) - 1;
@@ -433,22 +433,28 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, u32 s, u32 la
 			}
 			if (nz > K4_NZ) generic = true;
 		}
-		for (u32 x0 = 0; x0 < M; x0 += 32) {
-			const u32 x = x0 + lane;
-			bool cont = x < M && x != a && x != b;
-			if (cont) {
-				if (!generic) {
+		// 64 candidate rows per vote (two per lane) so that two independent load chains are in flight
+		for (u32 x0 = 0; x0 < M; x0 += 64) {
+			bool any = false;
 #pragma unroll
-					for (int q = 0; q < K4_NZ; q++)
-						if (q < (int)nz && (S.bits[(size_t)mi[q] * mpad + x] & mw[q]) != mw[q]) cont = false;
-				} else {
-					for (u32 w = 0; w < wl && cont; w++) {
-						const u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];
-						cont = (S.bits[(size_t)w * mpad + x] & m) == m;
+			for (int h = 0; h < 2; h++) {
+				const u32 x = x0 + 32 * h + lane;
+				bool cont = x < M && x != a && x != b;
+				if (cont) {
+					if (!generic) {
+#pragma unroll
+						for (int q = 0; q < K4_NZ; q++)
+							if (q < (int)nz && (bits[(size_t)mi[q] * mpad + x] & mw[q]) != mw[q]) cont = false;
+					} else {
+						for (u32 w = 0; w < wl && cont; w++) {
+							const u64 m = bits[(size_t)w * mpad + a] & bits[(size_t)w * mpad + b];
+							cont = (bits[(size_t)w * mpad + x] & m) == m;
+						}
 					}
 				}
+				any |= cont;
 			}
-			if (__any_sync(0xffffffffu, cont)) { adjacent = false; break; }
+			if (__any_sync(0xffffffffu, any)) { adjacent = false; break; }
 		}
 	}
 	if (adjacent && lane == 0) k4_push_pair(S, a, b);
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad, ns = c->n_surv;
 	const u32 lane = threadIdx.x & 31;
 	const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (u32 s = warp; s < ns; s += nwarps) k4_contain_warp(S, s, lane, M, wl, mpad);
+	for (u32 s = warp; s < ns; s += nwarps) k4_contain_warp(S, S.bits, s, lane, M, wl, mpad);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_adj_scan(DevState S)
@@ -822,9 +828,11 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 
 // mode 0: the whole rest of the cut; mode 1: stop after building K4's bit matrix (the multi-block
 // k4_filter / k4_contain and k_tail2 follow)
+#define TAIL_SBITS 2048u      // 16 KB of shared memory for K4's bit matrix inside the tail cluster
 template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, int header_only)
 {
 	__shared__ u32 ws[33];
+	__shared__ u64 sbits[NC > 1 ? TAIL_SBITS : 1];
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
 	CutCtl *c = S.ctl;
 	TP(0);
@@ -980,43 +988,65 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 		return;
 	}
 	TP(4);
-	// ---- P5: new rows, rewiring, retirement, dead facets
+	// ---- P5: new rows + rewiring (per half-edge) and copies + retirement (per vertex): independent
 	TAIL_LOOP(e, H) he_emit(S, P, e);
-	TAIL_SYNC();
-	TP(5);
 	TAIL_LOOP(i, n_vis) he_finish_vertex(S, P, i);
 	TAIL_SYNC();
-	TAIL_LOOP(i, n_vis) collect_dead_facets(S, i);
-	TP(6);
-	// ---- P6: K4 bit matrix
+	TP(5);
+	// ---- P6: dead facets (needs the final facet counts) and K4's column relabelling: independent
 	const u32 M = c->n_new;
+	TAIL_LOOP(i, n_vis) collect_dead_facets(S, i);
 	TAIL_LOOP(j, M) k4_assign_columns(S, j);
 	TAIL_SYNC();
+	TP(6);
+	// every thread derives the matrix shape itself (no barrier between plan and build)
+	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 31) & ~31u;
+	const bool bits_ovf = (u64)wl * mpad > S.cap_bits;
 	if (ctid == 0) k4_plan(S);
-	TAIL_SYNC();
-	if (!(c->status & ST_OVF_BITS)) {
-		TAIL_LOOP(j, M) k4_build_row(S, j);
+	if (!bits_ovf) {
+		TAIL_LOOP(j, M) {
+			for (u32 w = 0; w < wl; w++) S.bits[(size_t)w * mpad + j] = 0;
+			const u32 r = c->nrows + j, f = P.facet;
+			const u32 *l = S.inc_pool + S.inc_off[r];
+			for (u32 q = 0, n = S.inc_len[r]; q < n; q++) {
+				const u32 fc = l[q];
+				if (fc == f) continue;
+				const u32 col = S.facet_local[fc];
+				S.bits[(size_t)(col >> 6) * mpad + j] |= (u64)1 << (col & 63);
+			}
+		}
 		TAIL_SYNC();
 		TP(7);
 		if (mode == 1) return;                            // k4_filter, k4_contain, k_tail2 follow
+		// the pair test is M^2 integer work: 8 SMs only pay off for small M, beyond that the
+		// multi-block k4_filter / k4_contain (all 148 SMs) follow
+		const bool in_smem = NC > 1 && (u64)wl * mpad <= TAIL_SBITS;
 		if (M > (NC == 1 ? B200_K4_SMALL / 2 : B200_K4_SMALL)) {
 			if (rank == 0) tail_stage_header(S, ST_K4_PENDING, header_only);
 			return;
 		}
-		// ---- P7: pair test inside the cluster (the bit matrix is a few KB: cache-resident)
+		// ---- P7: pair test inside the cluster; each CTA stages the whole bit matrix in shared memory
+		const u64 *bits = S.bits;
+		if (in_smem) {
+			for (u32 x = threadIdx.x; x < wl * mpad; x += TAIL_THREADS) sbits[x] = S.bits[x];
+			__syncthreads();
+			bits = sbits;
+		}
 		for (u32 p = ctid; p < M * M; p += NC * TAIL_THREADS) {
 			const u32 a = p / M, b = p % M;
-			if (a < b) k4_filter_pair(S, a, b);
+			if (a < b) k4_filter_pair_in(S, bits, wl, mpad, a, b);
 		}
 		TAIL_SYNC();
 		TP(8);
 		if (c->n_surv <= S.cap_pairs) {
-			const u32 ns = c->n_surv, wl = c->wl, mpad = c->mpad;
-			for (u32 s = ctid >> 5; s < ns; s += NC * TAIL_THREADS / 32) k4_contain_warp(S, s, threadIdx.x & 31, M, wl, mpad);
+			const u32 ns = c->n_surv;
+			for (u32 s = ctid >> 5; s < ns; s += NC * TAIL_THREADS / 32) k4_contain_warp(S, bits, s, threadIdx.x & 31, M, wl, mpad);
 		}
 		TAIL_SYNC();
-	} else if (mode == 1)
-		return;
+	} else {
+		TAIL_SYNC();
+		if (mode == 1) return;
+	}
 	TP(9);
 	// ---- P8: adjacency, commit, delta record
 	tail_adjacency_and_pack<NC>(S, ws, header_only);
@@ -1026,7 +1056,10 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail2(DevState S, int header_only)
 {
 	__shared__ u32 ws[33];
+	const u32 ctid = tail_rank<NC>() * TAIL_THREADS + threadIdx.x;
+	TP(11);
 	tail_adjacency_and_pack<NC>(S, ws, header_only);
+	TP(12);
 }
 
 __global__ void k_reset_small(DevState S)
