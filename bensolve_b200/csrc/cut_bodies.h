@@ -538,7 +538,21 @@ B200_HD void adj_sort(const DevState &S, u32 j)
 {
 	const u32 nw = S.ctl->nrows + j;
 	u32 *l = S.adj_pool + S.adj_off[nw];
-	const u32 lo = S.new_padj_len[j], n = S.adj_len[nw];
+	const u32 lo = S.new_padj_len[j], n = S.adj_len[nw], m = n - lo;
+	if (m <= 24) {      // the usual case: rank-sort in registers (entries are distinct), one load and one store each
+		u32 buf[24];
+#pragma unroll
+		for (u32 x = 0; x < 24; x++) buf[x] = x < m ? l[lo + x] : B200_NONE;
+#pragma unroll
+		for (u32 x = 0; x < 24; x++) {
+			if (x >= m) break;
+			u32 rk = 0;
+#pragma unroll
+			for (u32 y = 0; y < 24; y++) rk += (buf[y] < buf[x]);
+			l[lo + rk] = buf[x];
+		}
+		return;
+	}
 	for (u32 x = lo + 1; x < n; x++) {
 		u32 key = l[x], y = x;
 		while (y > lo && l[y - 1] > key) { l[y] = l[y - 1]; y--; }
@@ -564,11 +578,10 @@ B200_HD StageLayout stage_layout(const CutCtl &c, int d)
 	return L;
 }
 // item e of the packing pass; n_items = n_new*d + n_new + n_vis + n_dead  (ideal rides with parent)
-B200_HD void pack_delta_item(const DevState &S, const StageLayout &L, u64 e)
+B200_HD void pack_delta_item(const DevState &S, const StageLayout &L, u64 e, u32 first_row)
 {
 	const CutCtl *c = S.ctl;
 	const u64 n_new = c->n_new, d = (u64)S.d;
-	const u32 first_row = c->nrows - c->n_new;      // k_finish has already advanced nrows
 	if (e < n_new * d) {
 		const u64 r = e / d, j = e % d;
 		((double *)(S.stage + L.coords))[e] = S.coord[j * S.cap_rows + first_row + r];

@@ -229,6 +229,7 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	rank_ = g_comm.rank;
 	S_.xchg_send = (u32 *)dalloc((size_t)B200_XCHG_WORDS * 4);
 	S_.xchg_recv = (u32 *)dalloc((size_t)B200_XCHG_WORDS * 4 * nranks_);
+	S_.nplist = (u32 *)dalloc((size_t)B200_VIS_MAX * sizeof(u32));
 	S_.he_off = (u32 *)dalloc((B200_VIS_MAX + 1) * sizeof(u32));
 	S_.he_own = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
 	S_.he_inc = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
@@ -259,7 +260,7 @@ CutEngine::~CutEngine()
 	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
 	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.tile_list, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 	drop_shadow();
 #ifndef B200_EMULATE
@@ -316,7 +317,6 @@ void CutEngine::ensure_rows(u32 need)
 	S_.cap_tiles = cap / B200_TILE;
 	regrow(S_.tile_cnt, S_.cap_tiles, 0);
 	regrow(S_.tile_base, S_.cap_tiles, 0);
-	regrow(S_.tile_list, (size_t)S_.cap_tiles * B200_TLIST, 0);
 	small_dirty_ = true;
 	S_.cap_rows = cap;
 }
@@ -533,7 +533,7 @@ void CutEngine::launch_k1_lists(const CutParams &P, const double *dv, const unsi
 		}
 	}
 	if (sharded && nranks_ > 1) {        // exchange: pack -> all-gather over NVLink -> merge
-		k_xchg_pack<<<1, TAIL_THREADS, 0, STREAM>>>(S_, lo, hi);
+		k_xchg_pack<<<1, TAIL_THREADS, 0, STREAM>>>(S_);
 		nccl_check(g_nccl.all_gather(S_.xchg_send, S_.xchg_recv, (size_t)B200_XCHG_WORDS * 4, 0 /* ncclChar */, g_comm.nccl_comm, STREAM), "ncclAllGather");
 		k_xchg_merge<<<1, TAIL_THREADS, 0, STREAM>>>(S_, (u32)nranks_);
 		stats_.kernel_launches += 3;
@@ -544,7 +544,6 @@ void CutEngine::launch_k1_lists(const CutParams &P, const double *dv, const unsi
 void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 {
 	if (small_dirty_) {
-		CK(cudaMemsetAsync(S_.tile_cnt, 0, (size_t)S_.cap_tiles * 4, STREAM));
 		k_reset_small<<<1, 32, 0, STREAM>>>(S_);
 		small_dirty_ = false;
 		stats_.kernel_launches++;
@@ -553,7 +552,8 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 	launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_, true);
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 	// tiny cuts run the tail in one CTA (block barriers); larger ones in an 8-CTA cluster
-	const bool tiny = expect_vis_ <= 96 && expect_m_ <= B200_K4_SMALL / 2;
+	static const u32 one_cta_max = getenv("B200_TAIL1_MAX_VIS") ? (u32)atoi(getenv("B200_TAIL1_MAX_VIS")) : 96u;
+	const bool tiny = expect_vis_ <= one_cta_max && (expect_m_ <= B200_K4_SMALL / 2 || mode == 1);
 	if (tiny) {
 		k_tail<1><<<1, TAIL_THREADS, 0, STREAM>>>(S_, mode, header_only ? 1 : 0);
 	} else {
@@ -779,7 +779,7 @@ void CutEngine::launch_part_c(bool header_only)
 	memcpy(S_.stage, &h, sizeof h);
 	if (header_only || (h.status & ST_OVF_STAGE) || (c->status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE))) return;
 	const u64 n = (u64)c->n_new * S_.d + c->n_new + c->n_vis + c->n_dead_facets;
-	for (u64 e = 0; e < n; e++) pack_delta_item(S_, L, e);
+	for (u64 e = 0; e < n; e++) pack_delta_item(S_, L, e, c->nrows - c->n_new);
 }
 // the single-CTA tail of the small-cut path, phase by phase (half-edge-parallel stage bodies)
 void CutEngine::launch_small(const CutParams &Pin, int mode, bool header_only)
@@ -1066,7 +1066,6 @@ double CutEngine::classify_bench(const CutParams &P, int iters, int flush_l2)
 	if (flush_l2 && !flush_buf_) flush_buf_ = dalloc(flush_bytes);
 	double total = 0;
 	for (int it = 0; it < iters; it++) {
-		CK(cudaMemsetAsync(S_.tile_cnt, 0, (size_t)S_.cap_tiles * 4, STREAM));
 		k_reset_small<<<1, 32, 0, STREAM>>>(S_);
 		if (flush_l2) k_flush_read<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>((const uint4 *)flush_buf_, flush_bytes / 16, (unsigned *)S_.dbg + 60);
 		CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
@@ -1158,7 +1157,7 @@ void CutEngine::compact()
 	S_.inc_pool = T.inc_pool; S_.adj_pool = T.adj_pool;
 	stats_.compactions++;
 	stats_.kernel_launches += 12;
-	small_dirty_ = true;      // the scans above used the tile counters as scratch
+
 }
 #else
 void CutEngine::compact()

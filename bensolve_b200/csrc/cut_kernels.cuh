@@ -433,11 +433,11 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bi
 			}
 			if (nz > K4_NZ) generic = true;
 		}
-		// 64 candidate rows per vote (two per lane) so that two independent load chains are in flight
-		for (u32 x0 = 0; x0 < M; x0 += 64) {
+		// 128 candidate rows per vote (four per lane) so that four independent load chains are in flight
+		for (u32 x0 = 0; x0 < M; x0 += 128) {
 			bool any = false;
 #pragma unroll
-			for (int h = 0; h < 2; h++) {
+			for (int h = 0; h < 4; h++) {
 				const u32 x = x0 + 32 * h + lane;
 				bool cont = x < M && x != a && x != b;
 				if (cont) {
@@ -459,15 +459,24 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bi
 	}
 	if (adjacent && lane == 0) k4_push_pair(S, a, b);
 }
+#define K4_CONTAIN_SBITS 6016u      // 47 KB: the whole bit matrix of a medium cut (M = 2000, 3 words per row)
 __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 {
+	__shared__ u64 sb[K4_CONTAIN_SBITS];
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	if (c->n_surv > S.cap_pairs) return;             // overflow is flagged by k_adj_scan
 	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad, ns = c->n_surv;
 	const u32 lane = threadIdx.x & 31;
 	const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (u32 s = warp; s < ns; s += nwarps) k4_contain_warp(S, S.bits, s, lane, M, wl, mpad);
+	if (blockIdx.x * (blockDim.x >> 5) >= ns) return;   // no survivor for this block
+	const u64 *bits = S.bits;
+	if ((u64)wl * mpad <= K4_CONTAIN_SBITS) {        // every candidate row is read from shared memory
+		for (u32 x = threadIdx.x; x < wl * mpad; x += K_THREADS) sb[x] = S.bits[x];
+		__syncthreads();
+		bits = sb;
+	}
+	for (u32 s = warp; s < ns; s += nwarps) k4_contain_warp(S, bits, s, lane, M, wl, mpad);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_adj_scan(DevState S)
@@ -537,7 +546,7 @@ __global__ void __launch_bounds__(K_THREADS) k_pack_delta(DevState S, int header
 	}
 	if (header_only || !fits || (c->status & (ST_SKIP_B))) return;
 	const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
-	B200_GRID_STRIDE(e, n) pack_delta_item(S, L, e);
+	B200_GRID_STRIDE(e, n) pack_delta_item(S, L, e, c->nrows - c->n_new);   // k_finish has already advanced nrows
 }
 
 // ------------------------------------------------------------------ compaction of dead rows (GC)
@@ -652,8 +661,8 @@ __global__ void k_gc_finish(DevState S, u32 n_live, const u32 *inc_total, const 
 // ====================================================================================================
 
 // K1, streaming form: all loads of a tile are independent (no liveness test before the coordinate
-// loads), classes are written as before, and the rare non-PLUS rows go to a per-tile list through
-// one atomic each -- no shared memory, no barrier.
+// loads); the rare non-PLUS rows get their class byte written and are appended to one unordered
+// list through an atomic each -- no shared memory, no barrier.  The tail sorts the list.
 template <int D, bool FROMDEV, int ITREQ>
 __global__ void __launch_bounds__(K_THREADS, (ITREQ >= 4 ? 2 : ITREQ == 2 ? 4 : 8)) k_classify_lists(DevState S, CutParams Parg, const double *vals,
                                                               const unsigned char *ideal, u64 vi, u32 nrows_host, u32 tile_lo, u32 tile_hi)
@@ -720,8 +729,8 @@ __global__ void __launch_bounds__(K_THREADS, (ITREQ >= 4 ? 2 : ITREQ == 2 ? 4 : 
 				c[s] = t[s] > hi ? CLS_PLUS : t[s] > mid ? CLS_ZP : t[s] > lo ? CLS_ZERO : CLS_MINUS;
 				if (c[s] != CLS_PLUS) {                  // rare; PLUS rows already read PLUS (invariant between cuts)
 					S.cls[r + s] = c[s];
-					const u32 pos = atomicAdd(&S.tile_cnt[tile], 1u);
-					if (pos < B200_TLIST) S.tile_list[(size_t)tile * B200_TLIST + pos] = r + s;
+					const u32 pos = atomicAdd(&S.ctl->n_list, 1u);
+					if (pos < B200_VIS_MAX) S.nplist[pos] = r + s;
 					if (c[s] == CLS_ZP) atomicAdd(&S.ctl->n_zp, 1u);
 					if (t[s] < lo) { atomicAdd(&S.ctl->n_strict, 1u); atomicMin(&S.ctl->min_strict_row, r + s); }
 				}
@@ -769,7 +778,7 @@ __device__ __forceinline__ void tail_reset_for_next_cut(const DevState &S)
 	S.ctl->n_strict = 0;
 	S.ctl->min_strict_row = B200_NONE;
 	S.ctl->n_zp = 0;
-	S.ctl->vis_ready = 0;
+	S.ctl->n_list = 0;
 }
 
 // phases after K4: adjacency build, commit, delta record (also the body of k_tail2)
@@ -800,12 +809,19 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 		}
 		TAIL_SYNC();
 		if (!(c->status & ST_SKIP_B)) {
+			// adjacency offsets are known: place the PLUS neighbours and, independently, pack the
+			// delta record (the commit below does not change what it reads)
 			TAIL_LOOP(j, c->n_new) adj_place(S, j);
+			const StageLayout L = stage_layout(*c, S.d);
+			if (!header_only && L.total <= S.cap_stage) {
+				const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
+				const u32 first_row = c->nrows;             // not committed yet
+				for (u64 e = ctid; e < n; e += NC * TAIL_THREADS) pack_delta_item(S, L, e, first_row);
+			}
 			TAIL_SYNC();
 			TAIL_LOOP(p, c->n_pairs) adj_pair_fill(S, p);
 			TAIL_SYNC();
 			TAIL_LOOP(j, c->n_new) adj_sort(S, j);
-			TAIL_SYNC();
 			if (ctid == 0) {
 				c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
 				c->nrows += c->n_new;
@@ -816,14 +832,11 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 		}
 	}
 	TAIL_SYNC();
-	if (rank == 0) tail_stage_header(S, 0, header_only);
-	const StageLayout L = stage_layout(*c, S.d);
-	if (!header_only && L.total <= S.cap_stage && !(c->status & ST_SKIP_B)) {
-		const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
-		for (u64 e = ctid; e < n; e += NC * TAIL_THREADS) pack_delta_item(S, L, e);
+	if (rank == 0) {
+		tail_stage_header(S, 0, header_only);
+		__syncthreads();
+		if (threadIdx.x == 0) tail_reset_for_next_cut(S);
 	}
-	TAIL_SYNC();
-	if (ctid == 0) tail_reset_for_next_cut(S);
 }
 
 // mode 0: the whole rest of the cut; mode 1: stop after building K4's bit matrix (the multi-block
@@ -833,65 +846,50 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 {
 	__shared__ u32 ws[33];
 	__shared__ u64 sbits[NC > 1 ? TAIL_SBITS : 1];
+	__shared__ u32 slist[B200_VIS_MAX];
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
 	CutCtl *c = S.ctl;
 	TP(0);
-	// ---- P0: reset per-cut outputs, decide, gather the per-tile lists into the ordered visited list
-	const u32 ntiles = (c->nrows + B200_TILE - 1) / B200_TILE;
-	if (rank == 0) {
-		if (threadIdx.x == 0) {
-			c->status = 0;
-			c->min_strict_slot = B200_NONE;
-			c->n_zp_projected = 0;
-			c->n_vis = c->n_new = c->inc_new = c->padj_new = 0;
-			c->n_minus = c->n_zero = 0;
-			c->n_pairs = c->adj_new = c->n_dead_facets = 0;
-			c->n_live_scanned = c->n_live;
-			c->n_local = c->wl = c->mpad = c->n_surv = 0;
-			c->scratch_flag = 0;
-		}
-		const u32 merged = c->vis_ready;              // multi-GPU: k_xchg_merge already built the visited list
-		u32 carry = 0, over = (merged == 2);
-		if (merged) carry = c->n_vis_merged;
-		for (u32 base = 0; base < ntiles && !merged; base += TAIL_THREADS) {
-			u32 t = base + threadIdx.x, v = t < ntiles ? S.tile_cnt[t] : 0, tot;
-			over |= (v > B200_TLIST);
-			u32 e = block_excl_scan(v, ws, tot);
-			if (t < ntiles) S.tile_base[t] = carry + e;
-			carry += tot;
-		}
-		over = __syncthreads_or(over);
-		if (threadIdx.x == 0) {
-			c->n_vis = carry;
-			if (c->n_strict == 0) {                      // nothing to cut: redundant (bslv_poly.c:132-136)
-				c->status |= ST_REDUNDANT;
-				S.facet_alive[S.cur->facet] = 0;
-			} else {
-				c->min_strict_slot = S.row_slot[c->min_strict_row];
-				if (over || carry > B200_VIS_MAX) c->status |= ST_NEED_BIG;
-			}
+	// ---- P0: reset per-cut outputs, decide, sort K1's unordered list into the ascending visited list
+	const u32 n_list = c->n_list;
+	if (ctid == 0) {
+		c->status = 0;
+		c->min_strict_slot = B200_NONE;
+		c->n_zp_projected = 0;
+		c->n_new = c->inc_new = c->padj_new = 0;
+		c->n_minus = c->n_zero = 0;
+		c->n_pairs = c->adj_new = c->n_dead_facets = 0;
+		c->n_live_scanned = c->n_live;
+		c->n_local = c->wl = c->mpad = c->n_surv = 0;
+		c->scratch_flag = 0;
+		c->n_vis = n_list <= B200_VIS_MAX ? n_list : 0;
+		if (c->n_strict == 0) {                          // nothing to cut: redundant (bslv_poly.c:132-136)
+			c->status |= ST_REDUNDANT;
+			S.facet_alive[S.cur->facet] = 0;
+			if (n_list > B200_VIS_MAX) c->status |= ST_NEED_BIG;   // cannot even undo the class marks from the list
+		} else {
+			c->min_strict_slot = S.row_slot[c->min_strict_row];
+			if (n_list > B200_VIS_MAX) c->status |= ST_NEED_BIG;
 		}
 	}
-	TAIL_SYNC();
-	{
-		// one warp per tile: each lane places its entries at their rank within the tile's list
-		// (rows are distinct), so the visited list comes out ascending without a sort
-		const bool gather = !(c->status & ST_NEED_BIG);
-		const u32 lane = threadIdx.x & 31;
-		for (u32 t = ctid >> 5; t < ntiles && !c->vis_ready; t += NC * TAIL_THREADS / 32) {
-			const u32 cnt = S.tile_cnt[t];
-			if (!cnt) continue;
-			__syncwarp();
-			if (lane == 0) S.tile_cnt[t] = 0;
-			if (!gather) continue;
-			u32 *dst = S.vis + S.tile_base[t];
-			const u32 *src = S.tile_list + (size_t)t * B200_TLIST;
-			for (u32 q = lane; q < cnt; q += 32) {
-				const u32 key = src[q];
-				u32 rk = 0;
-				for (u32 x = 0; x < cnt; x++) rk += (src[x] < key);
-				dst[rk] = key;
-			}
+	if (n_list <= B200_VIS_MAX) {
+		// every CTA stages the list in shared memory; an element's position in the sorted order is
+		// the number of smaller elements (rows are distinct)
+		for (u32 x = threadIdx.x; x < n_list; x += TAIL_THREADS) slist[x] = S.nplist[x];
+		__syncthreads();
+		// CTA `rank` ranks its slice of the elements; 8 consecutive lanes share one element and count
+		// over interleaved eighths of the list (n^2 / (8192 threads) comparisons each)
+		const u32 per = (n_list + NC - 1) / NC, e0 = rank * per, e1 = min(n_list, e0 + per);
+		const u32 part = threadIdx.x & 7;
+		for (u32 eb = e0; eb < e1; eb += TAIL_THREADS / 8) {      // block-uniform trip count
+			const u32 i = eb + (threadIdx.x >> 3);
+			const u32 key = i < e1 ? slist[i] : 0;
+			u32 rk = 0;
+			for (u32 x = part; x < n_list; x += 8) rk += (slist[x] < key);
+			rk += __shfl_xor_sync(0xffffffffu, rk, 1);
+			rk += __shfl_xor_sync(0xffffffffu, rk, 2);
+			rk += __shfl_xor_sync(0xffffffffu, rk, 4);
+			if (part == 0 && i < e1) S.vis[rk] = key;
 		}
 	}
 	TAIL_SYNC();
@@ -1068,7 +1066,7 @@ __global__ void k_reset_small(DevState S)
 	S.ctl->n_strict = 0;
 	S.ctl->min_strict_row = B200_NONE;
 	S.ctl->n_zp = 0;
-	S.ctl->vis_ready = 0;
+	S.ctl->n_list = 0;
 }
 
 // L2 flush for measurements: a read-only sweep over a buffer larger than L2 leaves clean lines behind
@@ -1088,51 +1086,31 @@ __global__ void __launch_bounds__(K_THREADS) k_flush_read(const uint4 *buf, size
 // found -- trigger counters and its non-PLUS rows with their classes, ascending -- into a fixed-size
 // record; one all-gather later every rank merges the records (rank ranges are ascending, so the
 // concatenation is the ordered visited list) and runs the rest of the cut identically.
-__global__ void __launch_bounds__(TAIL_THREADS, 1) k_xchg_pack(DevState S, u32 tile_lo, u32 tile_hi)
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_xchg_pack(DevState S)
 {
-	__shared__ u32 ws[33];
 	CutCtl *c = S.ctl;
 	u32 *out = S.xchg_send;
-	const u32 nt = tile_hi - tile_lo;
-	u32 carry = 0, over = 0;
-	for (u32 base = 0; base < nt; base += TAIL_THREADS) {
-		u32 t = base + threadIdx.x, v = t < nt ? S.tile_cnt[tile_lo + t] : 0, tot;
-		over |= (v > B200_TLIST);
-		u32 e = block_excl_scan(v, ws, tot);
-		if (t < nt) S.tile_base[tile_lo + t] = carry + e;
-		carry += tot;
+	const u32 n = c->n_list, over = n > B200_XCHG_CAP;
+	for (u32 i = threadIdx.x; i < n && !over; i += TAIL_THREADS) {
+		const u32 row = S.nplist[i];
+		out[4 + i] = row | ((u32)S.cls[row] << 30);
 	}
-	over = __syncthreads_or(over) || carry > B200_XCHG_CAP;
-	const u32 lane = threadIdx.x & 31;
-	for (u32 t = threadIdx.x >> 5; t < nt; t += TAIL_THREADS / 32) {
-		const u32 cnt = S.tile_cnt[tile_lo + t];
-		if (!cnt) continue;
-		__syncwarp();
-		if (lane == 0) S.tile_cnt[tile_lo + t] = 0;
-		if (over) continue;
-		u32 *dst = out + 4 + S.tile_base[tile_lo + t];
-		const u32 *src = S.tile_list + (size_t)(tile_lo + t) * B200_TLIST;
-		for (u32 q = lane; q < cnt; q += 32) {
-			const u32 key = src[q];
-			u32 rk = 0;
-			for (u32 x = 0; x < cnt; x++) rk += (src[x] < key);
-			dst[rk] = key | ((u32)S.cls[key] << 30);
-		}
-	}
+	__syncthreads();
 	if (threadIdx.x == 0) {
 		out[0] = c->n_strict;
 		out[1] = c->min_strict_row;
 		out[2] = c->n_zp;
-		out[3] = over ? B200_NONE : carry;
+		out[3] = over ? B200_NONE : n;
 		c->n_strict = 0;                 // local accumulators: the merged values are written by k_xchg_merge
 		c->min_strict_row = B200_NONE;
 		c->n_zp = 0;
+		c->n_list = 0;
 	}
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1) k_xchg_merge(DevState S, u32 nranks)
 {
-	__shared__ u32 off[65];
+	__shared__ u32 off[66];
 	CutCtl *c = S.ctl;
 	if (threadIdx.x == 0) {
 		u32 ns = 0, mr = B200_NONE, nz = 0, tot = 0, over = 0;
@@ -1145,25 +1123,21 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_xchg_merge(DevState S, u32 
 			if (r[3] == B200_NONE) over = 1; else tot += r[3];
 		}
 		off[nranks] = tot;
+		if (tot > B200_VIS_MAX) over = 1;
 		c->n_strict = ns;
 		c->min_strict_row = mr;
 		c->n_zp = nz;
-		c->n_vis_merged = over ? 0 : tot;
-		c->vis_ready = over ? 2 : 1;
-		off[64] = over;
+		c->n_list = over ? B200_VIS_MAX + 1 : tot;     // overflow: the multi-kernel path re-classifies everything unsharded
+		off[65] = over;
 	}
 	__syncthreads();
-	if (off[64]) {
-		// a record overflowed: classes of remote rows are unknown; the multi-kernel path will
-		// re-classify everything unsharded.  Undo the marks of the local share first.
-		return;
-	}
+	if (off[65]) return;
 	for (u32 g = 0; g < nranks; g++) {
 		const u32 *r = S.xchg_recv + (size_t)g * B200_XCHG_WORDS + 4;
 		const u32 n = off[g + 1] - off[g];
 		for (u32 i = threadIdx.x; i < n; i += TAIL_THREADS) {
 			const u32 e = r[i], row = e & 0x3FFFFFFFu;
-			S.vis[off[g] + i] = row;
+			S.nplist[off[g] + i] = row;
 			S.cls[row] = (u8)(e >> 30);
 		}
 	}

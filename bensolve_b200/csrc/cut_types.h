@@ -87,8 +87,8 @@ struct CutCtl {
 	u32 n_surv;         // pairs that pass the AND+POPC filter
 	u32 stage_bytes;    // size of the packed delta record (header included)
 	u32 scratch_flag;   // cluster-wide 'something changed' flag of the ZERO+ closure
-	u32 n_vis_merged;   // multi-GPU: length of the merged visited list
-	u32 vis_ready;      // multi-GPU: the visited list was merged from all ranks' exchange records (1), or a record overflowed (2)
+	u32 n_list;         // non-PLUS rows K1 appended to `nplist` (unordered; > B200_VIS_MAX = overflow)
+	u32 vis_ready;      // unused
 };
 #define B200_STAGE_HDR 128u   // the packed delta starts with a copy of CutCtl, padded to this size
 
@@ -116,7 +116,7 @@ struct DevState {
 	u32 *dead_slots;     // [cap_rows] by visited index
 	// tail-kernel scratch (small cuts): per-tile lists of non-PLUS rows written by the streaming K1,
 	// and the half-edge work items (visited vertex, adjacency slot)
-	u32 *tile_list;      // [cap_tiles * B200_TLIST]
+	u32 *nplist;         // [B200_VIS_MAX] non-PLUS rows in the order K1's atomics produced; the tail rank-sorts them into `vis`
 	u32 *he_off;         // [B200_VIS_MAX + 1]
 	u32 *he_own, *he_inc; // [B200_HE_CAP]
 	u8 *he_flag;         // [B200_HE_CAP]
