@@ -72,3 +72,66 @@ def run_pair(lib_a, lib_b, tr, stepwise=False, exact=True, flags_b=0):
     finally:
         a.kill()
         b.kill()
+
+
+# ---------------------------------------------------------------- Benson traces (real bensolve runs)
+def benson_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "benson_*.json")))
+
+
+def load_benson(path):
+    with open(path) as f:
+        return json.load(f)
+
+
+def replay_benson_instance(lib, inst, flags=0):
+    """Replay one recorded poly_args instance: same val sequence, the caller's callback replaced by a
+    lookup of the halfspace it produced in the recorded run.  Returns (engine, rcs)."""
+    import ctypes as C
+    d = inst["dim"]
+    table = {}
+    for ev in inst["events"]:
+        if ev[0] == "add":
+            val = tuple(float.fromhex(x) for x in ev[1])
+            table[(val, int(ev[2]))] = [float.fromhex(x) for x in ev[3]]
+
+    def callback(dual_point, is_dir, hp_out):
+        key = (tuple(dual_point[k] for k in range(d)), int(is_dir))
+        hp = table[key]
+        for k in range(d + 1):
+            hp_out[k] = hp[k]
+
+    e = capi.PolyEngine(lib, d, callback=callback, flags=flags)
+    rcs = []
+    for ev in inst["events"]:
+        if ev[0] == "add":
+            rc = e.add([float.fromhex(x) for x in ev[1]], int(ev[2]))
+            rcs.append(rc)
+            assert rc == ev[4], f"poly__add_vrtx returned {rc}, the reference run returned {ev[4]}"
+        else:
+            # dual slot 0 as the caller left it before poly__intl_apprx (bslv_algs.c:338-339)
+            if ev[1]:
+                e.args.dual.ideal[0] |= 1
+            else:
+                e.args.dual.ideal[0] &= ~1
+            for k in range(d):
+                e.args.dual.data[k] = float.fromhex(ev[2][k])
+            rc = e.init_approx()
+            assert rc == ev[3]
+    return e, rcs
+
+
+def check_benson_fixture(lib, path, checker=None, flags=0):
+    fx = load_benson(path)
+    for inst in fx["instances"]:
+        e, _ = replay_benson_instance(lib, inst, flags)
+        s = e.state()
+        fin = inst.get("final")
+        if fin:
+            assert (s.n_points, s.n_dirs, s.n_slots, s.n_dual_slots) == (fin["points"], fin["dirs"], fin["slots"], fin["dual_slots"]), \
+                f"{fx['example']}: counts {(s.n_points, s.n_dirs, s.n_slots, s.n_dual_slots)} != reference run {fin}"
+        if checker is not None:
+            c, _ = replay_benson_instance(checker, inst)
+            capi.compare_states(c.state(), s, exact_coords=True)
+            c.kill()
+        e.kill()
