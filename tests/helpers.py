@@ -10,7 +10,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.json")))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json")) if not os.path.basename(p).startswith("benson_"))
 
 
 def load_golden(path):

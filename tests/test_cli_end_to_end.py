@@ -1,0 +1,55 @@
+"""The unmodified bensolve host code (bslv_main/vlp/algs/lists/lp, compiled from /root/reference into
+oracle/_ref/libbensolve_host.so by tools/run_bensolve.py) driving our engine through the poly__* ABI
+in the closed Benson loop, on a synthetic VLP (BASELINE config 3 shape, scaled to what the HiGHS
+stand-in for GLPK finishes in seconds).  Results are compared with the same host code driving the
+reference engine, after the canonicalisation of tools/compare_sol.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "tools"))
+HOST_SO = os.path.join(REPO, "oracle", "_ref", "libbensolve_host.so")
+REF_SO = os.path.join(REPO, "oracle", "_ref", "libref_poly.so")
+
+
+def _run(engine, vlp, workdir):
+    res = subprocess.run([sys.executable, os.path.join(REPO, "tools", "run_bensolve.py"), "--engine", engine, "--workdir", workdir, vlp],
+                         capture_output=True, text=True, timeout=1200)
+    assert "Number of LPs solved" in res.stdout, (res.stdout + res.stderr)[-2000:]
+    lps = [l for l in res.stdout.splitlines() if "Number of LPs solved" in l][0]
+    return lps
+
+
+def _case(tmp_path, engine, q=3, m=40, n=20):
+    import compare_sol
+    from bensolve_b200 import vlpgen
+    if not (os.path.exists(HOST_SO) or os.path.exists("/root/reference/bslv_algs.c")) or not os.path.exists(REF_SO):
+        pytest.skip("reference host objects not available (oracle/_ref)")
+    B, P, box = vlpgen.random_vlp(q, m, n, seed=5)
+    vlp = str(tmp_path / "syn.vlp")
+    vlpgen.write_vlp(vlp, B, P, box)
+    la = _run("ref", vlp, str(tmp_path / "ref"))
+    lb = _run(engine, vlp, str(tmp_path / engine))
+    assert la == lb                                   # same number of LPs: same Benson trajectory
+    diffs = compare_sol.compare(str(tmp_path / "ref" / "syn"), str(tmp_path / engine / "syn"))
+    assert not diffs, diffs
+    rows = open(tmp_path / engine / "syn_img_p.sol").read().count("\n")
+    assert rows > 50
+
+
+def test_cli_closed_loop_host_logic(tmp_path, built):
+    built.build_emulation()
+    _case(tmp_path, "emul")
+
+
+@pytest.mark.gpu
+def test_cli_closed_loop_gpu(tmp_path):
+    _case(tmp_path, "b200", q=3, m=60, n=30)
+
+
+@pytest.mark.gpu
+def test_cli_closed_loop_gpu_q4(tmp_path):
+    _case(tmp_path, "b200", q=4, m=30, n=15)
