@@ -129,7 +129,7 @@ B200_HD void count_outputs(const DevState &S, u32 i)
 	if (is_visited_class(c)) {
 		const u32 *iv = S.inc_pool + S.inc_off[v];
 		const u32 niv = S.inc_len[v];
-		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
+		u64 mask[B200_MAXINC / 64] = {0};
 		if (c == CLS_ZERO && niv > B200_MAXINC) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
 		for (u32 q = 0, off = S.adj_off[v], n = S.adj_len[v]; q < n; q++) {
 			u32 k = S.adj_pool[off + q];
@@ -303,7 +303,7 @@ B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
 	u32 np = 0;
 	if (c == CLS_ZERO) {
 		const u32 nw = ctl->nrows + jrow;
-		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
+		u64 mask[B200_MAXINC / 64] = {0};
 		for (u32 q = 0; q < an; q++) {
 			const u32 k = S.adj_pool[aoff + q];
 			if (S.cls[k] != CLS_PLUS) continue;
@@ -341,7 +341,7 @@ B200_HD void he_eval(const DevState &S, u32 e)
 	if (S.cls[v] == CLS_MINUS) {
 		S.he_inc[e] = 1 + isect_count(S.inc_pool + S.inc_off[v], S.inc_len[v], S.inc_pool + S.inc_off[k], S.inc_len[k]);
 	} else {
-		u64 mask[B200_MAXINC / 64] = {0, 0, 0, 0};
+		u64 mask[B200_MAXINC / 64] = {0};
 		shared_facet_mask(S, v, k, mask);
 		for (int w = 0; w < B200_MAXINC / 64; w++)
 			if (mask[w]) B200_ATOMIC_OR64(&S.zmask[(size_t)i * (B200_MAXINC / 64) + w], mask[w]);

@@ -17,7 +17,7 @@ typedef uint64_t u64;
 typedef uint8_t u8;
 
 #define B200_MAXD 16        // highest supported dimension q of the image space
-#define B200_MAXINC 256     // longest incidence list a ZERO vertex may have (degenerate inputs)
+#define B200_MAXINC 1024    // longest incidence list an on-plane (ZERO) vertex may have (degenerate inputs)
 #define B200_NONE 0xFFFFFFFFu
 
 #if defined(__CUDACC__) && !defined(B200_EMULATE)

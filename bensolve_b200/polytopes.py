@@ -61,6 +61,28 @@ def cube_with_cuts(dim: int) -> Trace:
     return Trace(dim, vals, np.zeros(len(vals), np.uint8), dim, f"cubecuts_d{dim}")
 
 
+def cube_zero_plus(dim: int, gap: float = 5e-10) -> Trace:
+    """Cube, then a halfspace that cuts off the vertex (1,...,1) and passes `gap` ABOVE its dim
+    neighbours: they fall in the reference's projection band (1e-11 < s <= 1e-9, bslv_poly.c:666-674),
+    are moved onto the hyperplane in place and then copied like on-plane vertices."""
+    t = cube(dim)
+    d = -(1.0 - gap) / (dim - 2.0) * np.ones(dim)      # neighbours of (1,..,1) have coordinate sum dim-2
+    vals = np.concatenate([t.vals, d[None]])
+    return Trace(dim, vals, np.zeros(len(vals), np.uint8), dim, f"cubezp_d{dim}")
+
+
+def pyramid(k: int, tilt: float = 0.5) -> Trace:
+    """R^3 pyramid over a regular k-gon: its apex lies on k facets (highly degenerate vertex).  The last
+    halfspace passes exactly through the apex and cuts the base, so the apex is an on-plane vertex whose
+    copy inherits a subset of k incidences (bslv_poly.c:634-652)."""
+    th = 2 * np.pi * (np.arange(k) + 0.5) / k
+    sides = np.stack([np.cos(th), np.sin(th), np.ones(k)], axis=1)     # n.y <= 1, tight at the apex (0,0,1)
+    base = np.array([[0.0, 0.0, -1.0]])                                 # z >= -1
+    cut = np.array([[tilt, 0.0, 1.0]])                                  # through the apex, cuts the base
+    vals = np.concatenate([-sides[:3], -base, -sides[3:], -cut])
+    return Trace(3, vals, np.zeros(len(vals), np.uint8), 3, f"pyramid_k{k}")
+
+
 def lattice_polytope(dim: int, n: int, seed: int = 1, kmax: int = 2, bmax: int = 3) -> Trace:
     """Degenerate companion: small-integer normals and offsets, so many
     vertices lie exactly on later hyperplanes (ZERO copies, reduced incidence, ghost facets)."""

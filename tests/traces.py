@@ -3,7 +3,7 @@ from bensolve_b200 import polytopes as P
 
 
 def small_traces():
-    ts = [P.cube(3), P.cube(4), P.cube_with_cuts(3), P.cube_with_cuts(4), P.cube_with_cuts(5),
+    ts = [P.cube(3), P.cube(4), P.cube_zero_plus(3), P.cube_zero_plus(4), P.cube_zero_plus(5), P.pyramid(12), P.pyramid(70), P.pyramid(300), P.cube_with_cuts(3), P.cube_with_cuts(4), P.cube_with_cuts(5),
           P.tangent_polytope(2, 30), P.tangent_polytope(3, 50), P.tangent_polytope(4, 80),
           P.tangent_polytope(5, 60), P.tangent_polytope(6, 40)]
     for s in range(1, 4):
@@ -15,7 +15,7 @@ def small_traces():
 
 def stepwise_traces():
     """Compared after EVERY cut (trace replay)."""
-    return [P.cube_with_cuts(4), P.tangent_polytope(3, 25), P.tangent_polytope(4, 30), P.lattice_polytope(4, 30, 2),
+    return [P.cube_with_cuts(4), P.cube_zero_plus(4), P.tangent_polytope(3, 25), P.tangent_polytope(4, 30), P.lattice_polytope(4, 30, 2),
             P.lattice_polytope(5, 20, 1), P.mixed_polyhedron(3, 30, 1), P.random_cone(4, 16, 2)]
 
 
