@@ -335,6 +335,7 @@ B200_HD void he_eval(const DevState &S, u32 e)
 {
 	const u32 i = S.he_own[e], v = S.vis[i], k = S.adj_pool[S.adj_off[v] + (e - S.he_off[i])];
 	const bool plus = S.cls[k] == CLS_PLUS;
+	S.he_k[e] = k;
 	S.he_flag[e] = plus ? 1 : 0;
 	S.he_inc[e] = 0;
 	if (!plus) return;
@@ -343,7 +344,8 @@ B200_HD void he_eval(const DevState &S, u32 e)
 	} else {
 		u64 mask[B200_MAXINC / 64] = {0};
 		shared_facet_mask(S, v, k, mask);
-		for (int w = 0; w < B200_MAXINC / 64; w++)
+		const int nw = (int)((S.inc_len[v] + 63) / 64) < B200_MAXINC / 64 ? (int)((S.inc_len[v] + 63) / 64) : B200_MAXINC / 64;
+		for (int w = 0; w < nw; w++)
 			if (mask[w]) B200_ATOMIC_OR64(&S.zmask[(size_t)i * (B200_MAXINC / 64) + w], mask[w]);
 	}
 }
@@ -353,12 +355,18 @@ B200_HD void he_count(const DevState &S, u32 i)
 	const u8 c = S.cls[v];
 	u32 n_out = 0, inc_sz = 0, nplus = 0;
 	if (is_visited_class(c)) {
-		for (u32 e = S.he_off[i]; e < S.he_off[i + 1]; e++) { nplus += S.he_flag[e]; inc_sz += S.he_inc[e]; }
+		for (u32 e = S.he_off[i]; e < S.he_off[i + 1]; e++) {       // also each half-edge's position among the PLUS ones
+			S.he_rank[e] = nplus;
+			S.he_incpre[e] = inc_sz;
+			nplus += S.he_flag[e];
+			inc_sz += S.he_inc[e];
+		}
 		if (c == CLS_ZERO) {
 			if (S.inc_len[v] > B200_MAXINC) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
 			n_out = 1;
 			inc_sz = 1;
-			for (int w = 0; w < B200_MAXINC / 64; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
+			const int nw = (int)((S.inc_len[v] + 63) / 64) < B200_MAXINC / 64 ? (int)((S.inc_len[v] + 63) / 64) : B200_MAXINC / 64;
+			for (int w = 0; w < nw; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
 		} else
 			n_out = nplus;
 	}
@@ -369,10 +377,7 @@ B200_HD void he_count(const DevState &S, u32 i)
 B200_HD void he_emit(const DevState &S, const CutParams &P, u32 e)
 {
 	if (!S.he_flag[e]) return;
-	const u32 i = S.he_own[e], v = S.vis[i], e0 = S.he_off[i];
-	const u32 k = S.adj_pool[S.adj_off[v] + (e - e0)];
-	u32 rank = 0, incpre = 0;
-	for (u32 x = e0; x < e; x++) { rank += S.he_flag[x]; incpre += S.he_inc[x]; }
+	const u32 i = S.he_own[e], k = S.he_k[e], rank = S.he_rank[e], incpre = S.he_incpre[e], v = S.vis[i];
 	const u32 jrow = S.base3[3 * (size_t)i + 0], ibase = S.ctl->inc_used + S.base3[3 * (size_t)i + 1], ppos = S.base3[3 * (size_t)i + 2];
 	if (S.cls[v] == CLS_MINUS)
 		emit_edge_vertex(S, P, v, k, jrow + rank, ibase + incpre, ppos + rank);
@@ -492,13 +497,32 @@ B200_HD void k4_push_pair(const DevState &S, u32 a, u32 b)
 	if (p < S.cap_pairs) { S.pair_a[p] = a; S.pair_b[p] = b; }
 }
 // scalar forms (host test double; the kernels use the tiled / warp-cooperative forms)
-B200_HD void k4_filter_pair_in(const DevState &S, const u64 *bits, u32 wl, u32 mpad, u32 a, u32 b)
+B200_HD void k4_filter_pair_in(const DevState &S, const u64 *bits, u32 wl, u32 mpad, u32 a, u32 b, u32 thr)
 {
 	u32 n = 0;
 	for (u32 w = 0; w < wl; w++) n += popc64(bits[(size_t)w * mpad + a] & bits[(size_t)w * mpad + b]);
-	if (n + 2 >= (u32)S.d) k4_push_survivor(S, a, b);
+	if (n >= thr) k4_push_survivor(S, a, b);
 }
-B200_HD void k4_filter_pair(const DevState &S, u32 a, u32 b) { k4_filter_pair_in(S, S.bits, S.ctl->wl, S.ctl->mpad, a, b); }
+// threshold of the popcount filter: d-1 common facets (bslv_poly.c:484); inside a cut the new facet is
+// common to every row and left out of the matrix, hence d-2 there
+B200_HD u32 k4_threshold(const DevState &S, bool new_facet_excluded)
+{
+	const u32 need = S.d >= 1 ? (u32)S.d - 1 : 0;
+	return new_facet_excluded ? (need ? need - 1 : 0) : need;
+}
+B200_HD void k4_filter_pair(const DevState &S, u32 a, u32 b) { k4_filter_pair_in(S, S.bits, S.ctl->wl, S.ctl->mpad, a, b, k4_threshold(S, true)); }
+
+// K6: the same pair test on the DUAL polytope -- rows = live facets, columns = live
+// vertices (poly__update_adjacence(&dual), bslv_poly.c:992-1010 with edge_test on the dual).
+B200_HD void k6_set_row_bits(const DevState &S, u32 r, u32 mpad)
+{
+	if (!bit_test(S.live, r)) return;
+	const u32 *l = S.inc_pool + S.inc_off[r];
+	for (u32 q = 0, n = S.inc_len[r]; q < n; q++) {
+		const u32 col = S.facet_local[l[q]];
+		if (col != B200_NONE) B200_ATOMIC_OR64(&S.bits[(size_t)(r >> 6) * mpad + col], (u64)1 << (r & 63));
+	}
+}
 B200_HD void k4_contain_pair(const DevState &S, u32 s)
 {
 	const CutCtl *c = S.ctl;

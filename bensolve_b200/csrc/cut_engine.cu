@@ -47,6 +47,8 @@ static inline double now_us() { return std::chrono::duration<double, std::micro>
 	} while (0)
 
 static int g_device = -1;
+static int g_pdl = 1;            // programmatic dependent launch between the kernels of one cut (env B200_PDL=0 disables)
+static int g_tail_ctas = 8;      // cluster size of the tail kernels (env B200_TAIL_CTAS = 4, 8 or 16)
 static int g_k1_it = 1;     // tile iterations whose loads a K1 thread keeps in flight (env B200_K1_IT = 1, 2 or 4)
 int b200_num_devices()
 {
@@ -215,6 +217,12 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	for (int i = 0; i < 4; i++) { cudaEvent_t e; CK(cudaEventCreate(&e)); ev_[i] = e; }
 	CK(cudaMallocHost((void **)&pinned_hdr_, sizeof(CutCtl)));
 	if (const char *e = getenv("B200_K1_IT")) g_k1_it = atoi(e);
+	if (const char *e = getenv("B200_TAIL_CTAS")) g_tail_ctas = atoi(e);
+	if (const char *e = getenv("B200_PDL")) g_pdl = atoi(e);
+	if (g_tail_ctas == 16) {
+		CK(cudaFuncSetAttribute(k_tail<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+		CK(cudaFuncSetAttribute(k_tail2<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	}
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, g_device));
 	num_sms_ = prop.multiProcessorCount;
@@ -233,6 +241,9 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	S_.he_off = (u32 *)dalloc((B200_VIS_MAX + 1) * sizeof(u32));
 	S_.he_own = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
 	S_.he_inc = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
+	S_.he_k = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
+	S_.he_rank = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
+	S_.he_incpre = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
 	S_.he_flag = (u8 *)dalloc(B200_HE_CAP);
 	S_.zmask = (u64 *)dalloc((size_t)B200_VIS_MAX * (B200_MAXINC / 64) * sizeof(u64));
 	ensure_rows(4 * B200_TILE);
@@ -260,7 +271,7 @@ CutEngine::~CutEngine()
 	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
 	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 	drop_shadow();
 #ifndef B200_EMULATE
@@ -505,7 +516,7 @@ void CutEngine::launch_part_b(bool rerun)
 	k4_assign<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k4_plan_kernel<<<1, 32, 0, STREAM>>>(S_);
 	k4_build<<<gmap, K_THREADS, 0, STREAM>>>(S_);
-	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
+	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, true));
 	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
 	k_adj_scan<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
 	k_adj_place<<<gmap, K_THREADS, 0, STREAM>>>(S_);
@@ -540,6 +551,40 @@ void CutEngine::launch_k1_lists(const CutParams &P, const double *dv, const unsi
 	}
 }
 
+template <class K, class... A> static void launch_cluster(K kernel, int ctas, cudaStream_t st, A... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(ctas);
+	cfg.blockDim = dim3(TAIL_THREADS);
+	cfg.stream = st;
+	cudaLaunchAttribute at[2];
+	int na = 0;
+	if (ctas > 1) {
+		at[na].id = cudaLaunchAttributeClusterDimension;
+		at[na].val.clusterDim.x = ctas; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+		na++;
+	}
+	if (g_pdl) {     // let this grid's launch overlap the tail of the previous one; the kernel waits in cudaGridDependencySynchronize()
+		at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[na].val.programmaticStreamSerializationAllowed = 1;
+		na++;
+	}
+	cfg.attrs = at; cfg.numAttrs = na;
+	CK(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+template <class K, class... A> static void launch_dependent(K kernel, int grid, int block, cudaStream_t st, A... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(block);
+	cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+	CK(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
 // small-cut path: streaming K1 + single-CTA tail (+ multi-block K4 pair test for medium cuts)
 void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 {
@@ -555,17 +600,13 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 	static const u32 one_cta_max = getenv("B200_TAIL1_MAX_VIS") ? (u32)atoi(getenv("B200_TAIL1_MAX_VIS")) : 96u;
 	const bool tiny = expect_vis_ <= one_cta_max && (expect_m_ <= B200_K4_SMALL / 2 || mode == 1);
 	if (tiny) {
-		k_tail<1><<<1, TAIL_THREADS, 0, STREAM>>>(S_, mode, header_only ? 1 : 0);
+		launch_cluster(k_tail<1>, 1, STREAM, S_, mode, header_only ? 1 : 0);
+	} else if (g_tail_ctas == 4) {
+		launch_cluster(k_tail<4>, 4, STREAM, S_, mode, header_only ? 1 : 0);
+	} else if (g_tail_ctas == 16) {
+		launch_cluster(k_tail<16>, 16, STREAM, S_, mode, header_only ? 1 : 0);
 	} else {
-		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3(TAIL_CTAS);
-		cfg.blockDim = dim3(TAIL_THREADS);
-		cfg.stream = STREAM;
-		cudaLaunchAttribute at[1];
-		at[0].id = cudaLaunchAttributeClusterDimension;
-		at[0].val.clusterDim.x = TAIL_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-		cfg.attrs = at; cfg.numAttrs = 1;
-		CK(cudaLaunchKernelEx(&cfg, k_tail<TAIL_CTAS>, S_, mode, header_only ? 1 : 0));
+		launch_cluster(k_tail<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, mode, header_only ? 1 : 0);
 	}
 	stats_.kernel_launches += 2;
 	if (mode == 1) launch_k4_and_tail2(header_only);
@@ -574,19 +615,11 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 
 void CutEngine::launch_k4_and_tail2(bool header_only)
 {
-	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
-	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
-	{
-		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3(TAIL_CTAS);
-		cfg.blockDim = dim3(TAIL_THREADS);
-		cfg.stream = STREAM;
-		cudaLaunchAttribute at[1];
-		at[0].id = cudaLaunchAttributeClusterDimension;
-		at[0].val.clusterDim.x = TAIL_CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-		cfg.attrs = at; cfg.numAttrs = 1;
-		CK(cudaLaunchKernelEx(&cfg, k_tail2<TAIL_CTAS>, S_, header_only ? 1 : 0));
-	}
+	launch_dependent(k4_filter, num_sms_ * 4, K_THREADS, STREAM, S_, k4_threshold(S_, true));
+	launch_dependent(k4_contain, num_sms_ * 4, K_THREADS, STREAM, S_);
+	if (g_tail_ctas == 4) launch_cluster(k_tail2<4>, 4, STREAM, S_, header_only ? 1 : 0);
+	else if (g_tail_ctas == 16) launch_cluster(k_tail2<16>, 16, STREAM, S_, header_only ? 1 : 0);
+	else launch_cluster(k_tail2<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, header_only ? 1 : 0);
 	stats_.kernel_launches += 3;
 }
 
@@ -797,7 +830,7 @@ void CutEngine::launch_small(const CutParams &Pin, int mode, bool header_only)
 		const u32 r = S.vis[i];
 		S.he_off[i] = H;
 		H += is_visited_class(S.cls[r]) ? S.adj_len[r] : 0;
-		for (int w = 0; w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
+		for (u32 w = 0; w < (S.inc_len[r] + 63) / 64 && w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
 	}
 	S.he_off[c->n_vis] = H;
 	if (H > B200_HE_CAP) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
@@ -1044,6 +1077,64 @@ void CutEngine::download_mirror(MirrorDump &o, u32 n_facets)
 	for (int j = 0; j < d_; j++) d2h(o.coords_soa.data() + (size_t)j * n, S_.coord + (size_t)j * S_.cap_rows, (size_t)n * sizeof(double));
 	ensure_facets(n_facets);
 	d2h(o.facet_alive.data(), S_.facet_alive, (size_t)n_facets * 4);
+}
+
+// K6: adjacency among the live facets (dual polytope), by the same AND+POPC filter and containment
+// test as K4 on the transposed incidence: rows = live facets (ranked 0..M-1 through `facet_rank`),
+// columns = live vertices (device rows after a compaction).  Returns pairs of facet RANKS.
+void CutEngine::dual_adjacency(const std::vector<u32> &facet_rank, u32 M, std::vector<u32> &pair_a, std::vector<u32> &pair_b)
+{
+	compact();                                   // columns = dense live rows
+	const u32 N = hdr_.nrows, wl = (N + 63) / 64, mpad = (M + 31) & ~31u;
+	ensure_facets((u32)facet_rank.size());
+	ensure_rows(std::max<u32>(hdr_.nrows, M) + 64);    // deg[] is indexed by facet rank here
+	ensure_bits((u64)wl * mpad);
+	h2d(S_.facet_local, facet_rank.data(), facet_rank.size() * 4);
+	pair_a.clear();
+	pair_b.clear();
+	if (M < 2) return;
+	for (int guard = 0;; guard++) {
+		if (guard > 8) fail("bensolve_b200: dual adjacency buffers did not converge");
+#ifndef B200_EMULATE
+		CK(cudaSetDevice(g_device));
+		CK(cudaMemsetAsync(S_.bits, 0, (size_t)wl * mpad * 8, STREAM));
+		CK(cudaMemsetAsync(S_.deg, 0, (size_t)M * 4, STREAM));
+		k6_begin<<<1, 32, 0, STREAM>>>(S_, M, wl, mpad);
+		k6_build<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, mpad);
+		k4_filter<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, false));
+		k4_contain<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_);
+		stats_.kernel_launches += 4;
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(pinned_hdr_, S_.ctl, sizeof(CutCtl), cudaMemcpyDeviceToHost, STREAM));
+		CK(cudaStreamSynchronize(STREAM));
+		const CutCtl h = *pinned_hdr_;
+#else
+		memset(S_.bits, 0, (size_t)wl * mpad * 8);
+		memset(S_.deg, 0, (size_t)M * 4);
+		CutCtl *c = S_.ctl;
+		c->status = 0; c->n_new = M; c->wl = wl; c->mpad = mpad; c->n_surv = c->n_pairs = 0;
+		for (u32 r = 0; r < N; r++) k6_set_row_bits(S_, r, mpad);
+		for (u32 a = 0; a < M; a++)
+			for (u32 b = a + 1; b < M; b++) k4_filter_pair_in(S_, S_.bits, wl, mpad, a, b, k4_threshold(S_, false));
+		if (c->n_surv <= S_.cap_pairs)
+			for (u32 sv = 0; sv < c->n_surv; sv++) k4_contain_pair(S_, sv);
+		const CutCtl h = *c;
+#endif
+		if (h.n_surv > S_.cap_pairs || h.n_pairs > S_.cap_pairs) { ensure_pairs(std::max(h.n_surv, h.n_pairs)); continue; }
+		pair_a.resize(h.n_pairs);
+		pair_b.resize(h.n_pairs);
+		d2h(pair_a.data(), S_.pair_a, (size_t)h.n_pairs * 4);
+		d2h(pair_b.data(), S_.pair_b, (size_t)h.n_pairs * 4);
+		break;
+	}
+	// the cut path owns these control fields again
+#ifndef B200_EMULATE
+	CK(cudaMemcpyAsync(S_.ctl, &hdr_, sizeof(CutCtl), cudaMemcpyHostToDevice, STREAM));
+	CK(cudaStreamSynchronize(STREAM));
+#else
+	*S_.ctl = hdr_;
+#endif
+	small_dirty_ = true;
 }
 
 void *CutEngine::device_alloc(size_t bytes) { return dalloc(bytes); }

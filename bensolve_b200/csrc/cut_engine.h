@@ -58,6 +58,7 @@ public:
 	// meaning), no delta transfer; only the 128-byte header comes back.  Returns 1 if redundant.
 	int cut_from_device(const double *d_vals, const unsigned char *d_ideal, u64 i, u32 facet, u32 batch_first);
 	void download_mirror(MirrorDump &out, u32 n_facets);
+	void dual_adjacency(const std::vector<u32> &facet_rank, u32 n_live_facets, std::vector<u32> &pair_a, std::vector<u32> &pair_b);
 	void reserve(u64 rows, u64 inc_entries, u64 adj_entries);
 	// Launch K1 alone `iters` times against halfspace P (no mutation), optionally flushing L2
 	// before each launch; returns the mean CUDA-event time of one launch in ms.

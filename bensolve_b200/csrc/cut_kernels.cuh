@@ -368,14 +368,14 @@ __global__ void __launch_bounds__(K_THREADS) k4_build(DevState S)
 // (i0 + 4k, j), so a warp reads 32 consecutive B words (conflict-free) and one broadcast A word.
 #define K4_T 64
 #define K4_WCH 16
-__global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S)
+__global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr)
 {
 	__shared__ u64 sa[K4_WCH][K4_T], sb[K4_WCH][K4_T];
+	cudaGridDependencySynchronize();      // programmatic dependent launch: wait for the producer grid here
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad;
 	const u32 nt = (M + K4_T - 1) / K4_T;
-	const u32 thr = S.d >= 2 ? (u32)(S.d - 2) : 0;
 	const u32 j = threadIdx.x & (K4_T - 1), i0 = threadIdx.x >> 6;
 	for (u32 tp = blockIdx.x; tp < nt * nt; tp += gridDim.x) {
 		const u32 ta = tp / nt, tb = tp % nt;
@@ -417,10 +417,12 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bi
 	const u32 a = S.surv_a[s], b = S.surv_b[s];
 	bool adjacent = true;
 	if (S.d != 1) {
-		u64 mw[K4_NZ];
-		u32 mi[K4_NZ], nz = 0;
-		bool generic = false;
-		for (u32 w0 = 0; w0 < wl && !generic; w0 += 32) {
+		// the non-zero words of the mask inc(a) & inc(b): the first K4_NZ in registers of every lane
+		// (the cut path needs no more), up to 32 spread one per lane (dual polytope: a ridge holds many
+		// vertices), beyond that every word is compared
+		u64 mw[K4_NZ], lane_m = 0;
+		u32 mi[K4_NZ], lane_i = 0, nz = 0;
+		for (u32 w0 = 0; w0 < wl && nz <= 32; w0 += 32) {
 			const u32 w = w0 + lane;
 			const u64 m = w < wl ? (bits[(size_t)w * mpad + a] & bits[(size_t)w * mpad + b]) : 0;
 			u32 bal = __ballot_sync(0xffffffffu, m != 0);
@@ -429,9 +431,9 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bi
 				bal &= bal - 1;
 				const u64 mv = __shfl_sync(0xffffffffu, m, src);
 				if (nz < K4_NZ) { mw[nz] = mv; mi[nz] = w0 + src; }
+				if (nz < 32 && lane == nz) { lane_m = mv; lane_i = w0 + src; }
 				nz++;
 			}
-			if (nz > K4_NZ) generic = true;
 		}
 		// 128 candidate rows per vote (four per lane) so that four independent load chains are in flight
 		for (u32 x0 = 0; x0 < M; x0 += 128) {
@@ -440,16 +442,22 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bi
 			for (int h = 0; h < 4; h++) {
 				const u32 x = x0 + 32 * h + lane;
 				bool cont = x < M && x != a && x != b;
-				if (cont) {
-					if (!generic) {
+				if (nz <= K4_NZ) {
+					if (cont) {
 #pragma unroll
 						for (int q = 0; q < K4_NZ; q++)
 							if (q < (int)nz && (bits[(size_t)mi[q] * mpad + x] & mw[q]) != mw[q]) cont = false;
-					} else {
-						for (u32 w = 0; w < wl && cont; w++) {
-							const u64 m = bits[(size_t)w * mpad + a] & bits[(size_t)w * mpad + b];
-							cont = (bits[(size_t)w * mpad + x] & m) == m;
-						}
+					}
+				} else if (nz <= 32) {
+					for (u32 q = 0; q < nz; q++) {          // warp-uniform trip count: shuffles are safe
+						const u64 mq = __shfl_sync(0xffffffffu, lane_m, q);
+						const u32 iq = __shfl_sync(0xffffffffu, lane_i, q);
+						if (cont && (bits[(size_t)iq * mpad + x] & mq) != mq) cont = false;
+					}
+				} else if (cont) {
+					for (u32 w = 0; w < wl && cont; w++) {
+						const u64 m = bits[(size_t)w * mpad + a] & bits[(size_t)w * mpad + b];
+						cont = (bits[(size_t)w * mpad + x] & m) == m;
 					}
 				}
 				any |= cont;
@@ -463,6 +471,7 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bi
 __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 {
 	__shared__ u64 sb[K4_CONTAIN_SBITS];
+	cudaGridDependencySynchronize();
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	if (c->n_surv > S.cap_pairs) return;             // overflow is flagged by k_adj_scan
@@ -848,6 +857,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	__shared__ u64 sbits[NC > 1 ? TAIL_SBITS : 1];
 	__shared__ u32 slist[B200_VIS_MAX];
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
+	cudaGridDependencySynchronize();      // K1 (and the exchange kernels) precede this launch
 	CutCtl *c = S.ctl;
 	TP(0);
 	// ---- P0: reset per-cut outputs, decide, sort K1's unordered list into the ascending visited list
@@ -925,8 +935,10 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 			u32 i = base + threadIdx.x, v = 0, tot;
 			if (i < n_vis) {
 				const u32 r = S.vis[i];
-				v = is_visited_class(S.cls[r]) ? S.adj_len[r] : 0;
-				for (int w = 0; w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
+				const u8 cl = S.cls[r];
+				v = is_visited_class(cl) ? S.adj_len[r] : 0;
+				if (cl == CLS_ZERO)                        // shared-facet mask of an on-plane vertex: only the words its list needs
+					for (u32 w = 0; w < (S.inc_len[r] + 63) / 64 && w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
 			}
 			u32 e = block_excl_scan(v, ws, tot);
 			if (i < n_vis) S.he_off[i] = carry + e;
@@ -1032,7 +1044,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 		}
 		for (u32 p = ctid; p < M * M; p += NC * TAIL_THREADS) {
 			const u32 a = p / M, b = p % M;
-			if (a < b) k4_filter_pair_in(S, bits, wl, mpad, a, b);
+			if (a < b) k4_filter_pair_in(S, bits, wl, mpad, a, b, k4_threshold(S, true));
 		}
 		TAIL_SYNC();
 		TP(8);
@@ -1055,6 +1067,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail2(Dev
 {
 	__shared__ u32 ws[33];
 	const u32 ctid = tail_rank<NC>() * TAIL_THREADS + threadIdx.x;
+	cudaGridDependencySynchronize();
 	TP(11);
 	tail_adjacency_and_pack<NC>(S, ws, header_only);
 	TP(12);
@@ -1141,4 +1154,20 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) k_xchg_merge(DevState S, u32 
 			S.cls[row] = (u8)(e >> 30);
 		}
 	}
+}
+
+// ------------------------------------------------------------------ K6: dual all-pairs adjacency
+__global__ void __launch_bounds__(K_THREADS) k6_build(DevState S, u32 mpad)
+{
+	B200_GRID_STRIDE(r, S.ctl->nrows) k6_set_row_bits(S, (u32)r, mpad);
+}
+__global__ void k6_begin(DevState S, u32 M, u32 wl, u32 mpad)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	CutCtl *c = S.ctl;
+	c->status = 0;
+	c->n_new = M;
+	c->wl = wl;
+	c->mpad = mpad;
+	c->n_surv = c->n_pairs = 0;
 }

@@ -119,6 +119,7 @@ struct DevState {
 	u32 *nplist;         // [B200_VIS_MAX] non-PLUS rows in the order K1's atomics produced; the tail rank-sorts them into `vis`
 	u32 *he_off;         // [B200_VIS_MAX + 1]
 	u32 *he_own, *he_inc; // [B200_HE_CAP]
+	u32 *he_k, *he_rank, *he_incpre; // [B200_HE_CAP] neighbour row; rank / incidence offset among the vertex's PLUS half-edges
 	u8 *he_flag;         // [B200_HE_CAP]
 	u64 *zmask;          // [B200_VIS_MAX * B200_MAXINC/64] shared-facet masks of ZERO vertices
 	u32 *dead_facets;    // [cap_facets]

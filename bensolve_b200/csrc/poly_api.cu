@@ -513,12 +513,28 @@ extern "C" void poly__update_adjacence(polytope *p)
 	std::vector<std::vector<size_t>> nb(p->cnt);
 	for (size_t s : live)                 // the reference appends to whatever is there (:1003-1004)
 		nb[s].assign(p->adjacence[s].data, p->adjacence[s].data + p->adjacence[s].cnt);
-	for (size_t i = 0; i < live.size(); i++)
-		for (size_t j = i + 1; j < live.size(); j++)
-			if (adjacent_by_incidence(p, live[i], live[j])) {
-				nb[live[i]].push_back(live[j]);
-				nb[live[j]].push_back(live[i]);
-			}
+	if (p == &a->dual && h->engine) {
+		// K6 on the device: rows = live facets, columns = live vertices.  A used facet without a live
+		// vertex cannot occur here (clean facet rule), but one with a stale `used` bit is simply isolated.
+		std::vector<u32> rank(p->cnt, B200_NONE);
+		for (size_t i = 0; i < live.size(); i++) rank[live[i]] = (u32)i;
+		std::vector<u32> pa, pb;
+		h->engine->dual_adjacency(rank, (u32)live.size(), pa, pb);
+		for (size_t q = 0; q < pa.size(); q++) {
+			nb[live[pa[q]]].push_back(live[pb[q]]);
+			nb[live[pb[q]]].push_back(live[pa[q]]);
+		}
+		for (size_t s : live) std::sort(nb[s].begin() + p->adjacence[s].cnt, nb[s].end());
+		h->lists_current = false;         // the engine compacted its rows: host lists are rebuilt on next use
+		b200_poly_materialise(a);
+	} else {
+		for (size_t i = 0; i < live.size(); i++)
+			for (size_t j = i + 1; j < live.size(); j++)
+				if (adjacent_by_incidence(p, live[i], live[j])) {
+					nb[live[i]].push_back(live[j]);
+					nb[live[j]].push_back(live[i]);
+				}
+	}
 	std::vector<size_t> off(p->cnt + 1, 0);
 	for (size_t s = 0; s < p->cnt; s++) off[s + 1] = off[s] + nb[s].size();
 	std::vector<size_t> &slab = (p == &a->dual) ? h->slab_dadj : h->slab_padj;

@@ -135,3 +135,17 @@ def check_benson_fixture(lib, path, checker=None, flags=0):
             capi.compare_states(c.state(), s, exact_coords=True)
             c.kill()
         e.kill()
+
+
+def dual_adjacency_of(lib, tr, flags=0):
+    """poly__update_adjacence(&dual) after replaying a trace: {facet: sorted neighbour facets} over the
+    facets that hold at least one live vertex (the reference's ghost facets are dropped)."""
+    e = capi.PolyEngine(lib, tr.dim, flags=flags)
+    try:
+        P.replay(e, tr)
+        e.update_dual_adjacence()
+        r = e.raw()
+        real = {f for f, v in r["dual"]["inc"].items() if len(v)}
+        return {f: sorted(x for x in r["dual"]["adj"][f] if x in real) for f in real}
+    finally:
+        e.kill()

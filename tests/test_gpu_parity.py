@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from bensolve_b200 import capi, polytopes as P
-from helpers import check_against_golden, golden_files, run_pair
+from helpers import check_against_golden, dual_adjacency_of, golden_files, run_pair
 from traces import medium_traces, small_traces, stepwise_traces
 
 pytestmark = pytest.mark.gpu
@@ -203,3 +203,9 @@ def test_gpu_multi_kernel_path(product_lib, checker, tr):
 @pytest.mark.parametrize("tr", stepwise_traces()[:4], ids=lambda t: t.name)
 def test_gpu_multi_kernel_path_after_every_cut(product_lib, checker, tr):
     run_pair(checker, product_lib, tr, stepwise=True, exact=True, flags_b=FLAG_MULTI_KERNEL | FLAG_EAGER_GC)
+
+
+@pytest.mark.parametrize("tr", [t for t in small_traces() if "pyramid_k300" not in t.name][::2] + medium_traces()[:4], ids=lambda t: t.name)
+def test_gpu_dual_adjacency_k6(product_lib, checker, tr):
+    """K6 on the device (bit matrix facets x vertices, same AND+POPC filter and containment kernels as K4)."""
+    assert dual_adjacency_of(checker, tr) == dual_adjacency_of(product_lib, tr)

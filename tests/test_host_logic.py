@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from bensolve_b200 import build, capi, polytopes as P
-from helpers import check_against_golden, golden_files, run_pair
+from helpers import check_against_golden, dual_adjacency_of, golden_files, run_pair
 from traces import medium_traces, small_traces, stepwise_traces
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -238,3 +238,9 @@ def test_host_logic_tail_phases_after_every_cut(ref_lib, emul_lib, tr):
 @pytest.mark.parametrize("tr", medium_traces()[:4], ids=lambda t: t.name)
 def test_host_logic_tail_phases_medium(oracle_lib, emul_lib, tr):
     run_pair(oracle_lib, emul_lib, tr, exact=True, flags_b=FLAG_TAIL_PHASES)
+
+
+@pytest.mark.parametrize("tr", [t for t in small_traces() if "pyramid_k300" not in t.name][::2], ids=lambda t: t.name)
+def test_host_logic_dual_adjacency(ref_lib, emul_lib, tr):
+    """K6 (poly__update_adjacence on the dual, bslv_poly.c:992-1010) against the reference."""
+    assert dual_adjacency_of(ref_lib, tr) == dual_adjacency_of(emul_lib, tr)
