@@ -148,6 +148,10 @@ def run_reference(a, trace):
 
 
 # ---------------------------------------------------------------------------------- B200 arm
+# DRAM bytes of one K1 launch from the ncu --set full capture in profiles/ (same workload only)
+PROFILED_K1_TRAFFIC = {(6, 6400, 20261018): 49.2e6}
+
+
 def measured_peak():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -285,7 +289,7 @@ def run_b200(a, trace):
                 "ms_per_step": 1e3 * t_e2e / a.steps},
         "gpu_launches": int(launches_v + launches_e),
         "roofline": {"bound": "hbm", "kernel": f"k_classify_lists<{d},false>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "traffic": PROFILED_K1_TRAFFIC.get((d, n, a.seed)), "traffic_source": "profiles/r01_k1_summary.md (ncu dram__bytes_read.sum + dram__bytes_write.sum)" if (d, n, a.seed) in PROFILED_K1_TRAFFIC else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                      "ms_per_launch": ms_flush, "ms_per_launch_l2_resident": ms_l2,
                      "achieved_l2_resident": alg_bytes / (ms_l2 * 1e-3) / 1e9 if ms_l2 > 0 else None,
                      "sequence_algorithmic_bytes": int(per_step["algorithmic_bytes"]),

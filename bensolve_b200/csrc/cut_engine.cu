@@ -246,6 +246,18 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	S_.he_incpre = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
 	S_.he_flag = (u8 *)dalloc(B200_HE_CAP);
 	S_.zmask = (u64 *)dalloc((size_t)B200_VIS_MAX * (B200_MAXINC / 64) * sizeof(u64));
+	tiny_caps_ = getenv("B200_TINY_CAPS") != nullptr;
+	if (tiny_caps_) {                        // test hook: start so small that every capacity negotiation path runs
+		ensure_rows(B200_TILE);
+		ensure_inc(64);
+		ensure_adj(64);
+		ensure_padj(16);
+		ensure_pairs(16);
+		ensure_bits(16);
+		ensure_stage(B200_STAGE_HDR + 64);
+		ensure_facets(8);
+		return;
+	}
 	ensure_rows(4 * B200_TILE);
 	ensure_inc(1u << 16);
 	ensure_adj(1u << 16);
@@ -893,7 +905,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 	header_only_ = header_only;
 	ensure_facets(P.facet + 1);
 	// head-room for the appends; exact needs are checked on the device before any mutation
-	ensure_rows(hdr_.nrows + std::max<u32>(4096, hdr_.n_live / 2 + 64));
+	if (!tiny_caps_) ensure_rows(hdr_.nrows + std::max<u32>(4096, hdr_.n_live / 2 + 64));
 #ifndef B200_EMULATE
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[2], STREAM));
 #endif

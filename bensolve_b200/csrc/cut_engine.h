@@ -105,6 +105,7 @@ private:
 	int d_;
 	unsigned flags_ = 0;
 	bool header_only_ = false;
+	bool tiny_caps_ = false;
 	bool small_dirty_ = true;      // tile counters / K1 accumulators must be cleared before the small-cut path runs
 	bool prefer_big_ = false;      // the last cut did not fit the single-CTA tail
 	u32 emu_extra_status_ = 0;

@@ -209,3 +209,28 @@ def test_gpu_multi_kernel_path_after_every_cut(product_lib, checker, tr):
 def test_gpu_dual_adjacency_k6(product_lib, checker, tr):
     """K6 on the device (bit matrix facets x vertices, same AND+POPC filter and containment kernels as K4)."""
     assert dual_adjacency_of(checker, tr) == dual_adjacency_of(product_lib, tr)
+
+
+@pytest.fixture
+def tiny_caps(monkeypatch):
+    monkeypatch.setenv("B200_TINY_CAPS", "1")
+
+
+@pytest.mark.parametrize("tr", small_traces()[::3] + medium_traces()[:3], ids=lambda t: t.name)
+@pytest.mark.parametrize("flags", [0, FLAG_MULTI_KERNEL, FLAG_EAGER_GC])
+def test_gpu_capacity_negotiation(product_lib, checker, tiny_caps, tr, flags):
+    """Start from near-zero device capacities: rows, pools, pair buffers, bit matrix and staging all
+    overflow and are renegotiated (on the device before any mutation; K4 / adjacency re-runnable)."""
+    run_pair(checker, product_lib, tr, exact=True, flags_b=flags)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_gpu_random_mixed_stress(product_lib, oracle_lib, seed):
+    """Random dimension / generator / seed: unbounded, degenerate and redundant-heavy inputs."""
+    rng = np.random.default_rng(1000 + seed)
+    d = int(rng.integers(2, 7))
+    n = int(rng.integers(d + 2, 60 if d >= 5 else 150))
+    kind = int(rng.integers(0, 4))
+    tr = [P.mixed_polyhedron, P.lattice_polytope, P.random_offsets, P.tangent_polytope][kind](d, n, int(rng.integers(1, 10 ** 6))) \
+        if not (kind == 0 and d < 3) else P.tangent_polytope(d, n, seed)
+    run_pair(oracle_lib, product_lib, tr, exact=True, flags_b=[0, FLAG_EAGER_GC, FLAG_MULTI_KERNEL][seed % 3])

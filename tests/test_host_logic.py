@@ -244,3 +244,15 @@ def test_host_logic_tail_phases_medium(oracle_lib, emul_lib, tr):
 def test_host_logic_dual_adjacency(ref_lib, emul_lib, tr):
     """K6 (poly__update_adjacence on the dual, bslv_poly.c:992-1010) against the reference."""
     assert dual_adjacency_of(ref_lib, tr) == dual_adjacency_of(emul_lib, tr)
+
+
+@pytest.fixture
+def tiny_caps(monkeypatch):
+    """Engines created inside start with near-zero capacities: every overflow / re-run path executes."""
+    monkeypatch.setenv("B200_TINY_CAPS", "1")
+
+
+@pytest.mark.parametrize("tr", small_traces()[::3] + medium_traces()[:2], ids=lambda t: t.name)
+@pytest.mark.parametrize("flags", [0, 8, 2])
+def test_host_logic_capacity_negotiation(oracle_lib, emul_lib, tiny_caps, tr, flags):
+    run_pair(oracle_lib, emul_lib, tr, exact=True, flags_b=flags)
