@@ -209,6 +209,7 @@ class PolyEngine:
         self.lib = lib
         self.dim = dim
         self.args = PolyArgs()
+        self._args_ref = C.byref(self.args)
         lib.poly__set_default_args(C.byref(self.args), dim)
         self._cb = None
         if callback is not None:
@@ -224,10 +225,13 @@ class PolyEngine:
     # -- the calls bslv_algs.c makes -------------------------------------------------------
     def add(self, val, ideal: int = 0) -> int:
         """poly__add_vrtx: append a dual point (= halfspace via the callback) and cut."""
-        for k in range(self.dim):
-            self.args.val[k] = float(val[k])
+        if isinstance(val, np.ndarray) and val.dtype == np.float64 and val.flags.c_contiguous:
+            C.memmove(self.args.val, val.ctypes.data, 8 * self.dim)     # what a C caller's memcpy into args->val does
+        else:
+            for k in range(self.dim):
+                self.args.val[k] = float(val[k])
         self.args.ideal = int(ideal)
-        return self.lib.poly__add_vrtx(C.byref(self.args))
+        return self.lib.poly__add_vrtx(self._args_ref)
 
     def add_batch(self, vals, ideal=None):
         """b200_poly_add_batch: host arrays in, one device-resident pass, mirror coherent at return."""

@@ -417,38 +417,6 @@ B200_HD void collect_dead_facets(const DevState &S, u32 i)
 	}
 }
 
-// K4, list form: combinatorial adjacency of new rows a < b on the new facet
-// (edge_test, bslv_poly.c:467-512): |inc(a) n inc(b)| >= d-1 and no third new row contains it.
-B200_HD bool lists_adjacent(const DevState &S, u32 a, u32 b, u32 M)
-{
-	const u32 nrows = S.ctl->nrows;
-	const u32 ra = nrows + a, rb = nrows + b;
-	const u32 *ia = S.inc_pool + S.inc_off[ra], *ib = S.inc_pool + S.inc_off[rb];
-	const u32 na = S.inc_len[ra], nb = S.inc_len[rb];
-	if (S.d == 1) return true;
-	if (isect_count(ia, na, ib, nb) + 1 < (u32)S.d) return false;
-	for (u32 x = 0; x < M; x++) {
-		if (x == a || x == b) continue;
-		const u32 rx = nrows + x;
-		const u32 *ix = S.inc_pool + S.inc_off[rx];
-		const u32 nx = S.inc_len[rx];
-		// does inc(x) contain every element of inc(a) n inc(b)?  3-way sorted merge
-		u32 p = 0, q = 0, r = 0;
-		bool contains = true;
-		while (p < na && q < nb) {
-			u32 u = ia[p], w = ib[q];
-			if (u == w) {
-				while (r < nx && ix[r] < u) r++;
-				if (r == nx || ix[r] != u) { contains = false; break; }
-			}
-			p += (u <= w);
-			q += (w <= u);
-		}
-		if (contains) return false;
-	}
-	return true;
-}
-
 // ---- K4, bitset form (north_star (3)): the incidence lists of the M new rows are re-coded as rows of a
 // bit matrix over the facets they actually touch (the new facet itself is common to all and left
 // out, so the reference's |mutual| >= d-1, bslv_poly.c:484, becomes popcount >= d-2).

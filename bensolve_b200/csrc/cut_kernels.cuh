@@ -61,7 +61,6 @@ __global__ void k_begin(DevState S, CutParams P)
 	c->n_pairs = c->adj_new = c->n_dead_facets = 0;
 	c->n_live_scanned = 0;
 	c->n_local = c->wl = c->mpad = c->n_surv = 0;
-	c->vis_ready = 0;
 	S.facet_cnt[P.facet] = 0;
 	S.facet_alive[P.facet] = 1;
 }
@@ -100,7 +99,6 @@ __global__ void k_begin_dev(DevState S, const double *vals, const unsigned char 
 	c->n_pairs = c->adj_new = c->n_dead_facets = 0;
 	c->n_live_scanned = 0;
 	c->n_local = c->wl = c->mpad = c->n_surv = 0;
-	c->vis_ready = 0;
 	S.facet_cnt[facet] = 0;
 	S.facet_alive[facet] = 1;
 }

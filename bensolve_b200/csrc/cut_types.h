@@ -88,7 +88,7 @@ struct CutCtl {
 	u32 stage_bytes;    // size of the packed delta record (header included)
 	u32 scratch_flag;   // cluster-wide 'something changed' flag of the ZERO+ closure
 	u32 n_list;         // non-PLUS rows K1 appended to `nplist` (unordered; > B200_VIS_MAX = overflow)
-	u32 vis_ready;      // unused
+	u32 reserved0;
 };
 #define B200_STAGE_HDR 128u   // the packed delta starts with a copy of CutCtl, padded to this size
 
@@ -134,7 +134,6 @@ struct DevState {
 };
 
 #define B200_TILE 2048u  // rows per K1/K2 tile
-#define B200_TLIST 256u  // capacity of one tile's list of non-PLUS rows (small-cut path)
 #define B200_VIS_MAX 4096u // most visited vertices the single-CTA tail handles
 #define B200_HE_CAP 65536u // most half-edges the single-CTA tail handles
 #define B200_K4_SMALL 256u
