@@ -49,6 +49,7 @@ static inline double now_us() { return std::chrono::duration<double, std::micro>
 static int g_device = -1;
 static int g_pdl = 1;            // programmatic dependent launch between the kernels of one cut (env B200_PDL=0 disables)
 static int g_tail_ctas = 8;      // cluster size of the tail kernels (env B200_TAIL_CTAS = 4, 8 or 16)
+static int g_k1_grid = 0;        // K1 grid policy (env B200_K1_GRID): 0 balanced rounds, 1 one block per group, 2 capped at residency
 static int g_k1_it = 1;     // tile iterations whose loads a K1 thread keeps in flight (env B200_K1_IT = 1, 2 or 4)
 int b200_num_devices()
 {
@@ -217,6 +218,7 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	for (int i = 0; i < 4; i++) { cudaEvent_t e; CK(cudaEventCreate(&e)); ev_[i] = e; }
 	CK(cudaMallocHost((void **)&pinned_hdr_, sizeof(CutCtl)));
 	if (const char *e = getenv("B200_K1_IT")) g_k1_it = atoi(e);
+	if (const char *e = getenv("B200_K1_GRID")) g_k1_grid = atoi(e);
 	if (const char *e = getenv("B200_TAIL_CTAS")) g_tail_ctas = atoi(e);
 	if (const char *e = getenv("B200_PDL")) g_pdl = atoi(e);
 	if (g_tail_ctas == 16) {
@@ -272,7 +274,7 @@ CutEngine::~CutEngine()
 {
 	if (getenv("B200_PHASES")) {
 		fprintf(stderr, "[b200] tail phase ns:");
-		for (int k = 0; k < 13; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
+		for (int k = 0; k < 16; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, " (per cut, %llu cuts)\n", (unsigned long long)stats_.cuts);
 		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions);
 	}
@@ -477,7 +479,9 @@ template <int D> static void launch_classify_lists(const DevState &S, const CutP
 	const int per_sm = it >= 4 ? 2 : it == 2 ? 4 : 8;
 	// every block gets the same number of groups (+-1): no partial last wave
 	const u32 resident = (u32)(num_sms * per_sm), rounds = std::max<u32>(1, (groups + resident - 1) / resident);
-	const int grid = (int)std::max<u32>(1, (groups + rounds - 1) / rounds);
+	int grid = (int)std::max<u32>(1, (groups + rounds - 1) / rounds);
+	if (g_k1_grid == 1) grid = (int)std::max<u32>(1, groups);                 // one block per group: hardware scheduler staggers them
+	if (g_k1_grid == 2) grid = (int)std::max<u32>(1, std::min<u32>(groups, resident));
 	if (it >= 4) launch_classify_lists_it<D, 4>(S, P, dv, di, vi, nrows, tlo, thi, grid, st);
 	else if (it == 2) launch_classify_lists_it<D, 2>(S, P, dv, di, vi, nrows, tlo, thi, grid, st);
 	else launch_classify_lists_it<D, 1>(S, P, dv, di, vi, nrows, tlo, thi, grid, st);
@@ -968,10 +972,13 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[2], (cudaEvent_t)ev_[3]));
 		stats_.cut_ms += ms;
 		{
-			u64 tp[16];
+			u64 tp[16] = {0};
 			d2h(tp, S_.dbg, sizeof tp);
 			for (int k = 0; k < 12; k++) if (tp[k] >= tp[0] && tp[k + 1] > tp[k] && k != 10) stats_.phase_ns[k] += tp[k + 1] - tp[k];
-			if (tp[11] >= tp[0] && tp[7] >= tp[0] && tp[11] > tp[7] && tp[9] < tp[0]) stats_.phase_ns[12] += tp[11] - tp[7];   // k4_filter + k4_contain + launch gaps
+			if (tp[11] >= tp[0] && tp[7] >= tp[0] && tp[11] > tp[7] && tp[9] < tp[0]) {
+				stats_.phase_ns[12] += tp[11] - tp[7];   // k4_filter + k4_contain + launch gaps
+				if (tp[13] > tp[7] && tp[14] > tp[13] && tp[11] > tp[14]) { stats_.phase_ns[13] += tp[13] - tp[7]; stats_.phase_ns[14] += tp[14] - tp[13]; stats_.phase_ns[15] += tp[11] - tp[14]; }
+			}
 		}
 		static const char *trace = getenv("B200_TRACE");
 		if (trace && ms > atof(trace))

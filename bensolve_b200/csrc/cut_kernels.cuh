@@ -8,6 +8,7 @@
 
 #include "cut_bodies.h"
 
+__device__ __forceinline__ u64 b200_globaltimer() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define K_THREADS 256
 #define POLY_EPS_D 1e-9   // POLY_EPS, bslv_poly.h:47
 #define SCAN_THREADS 1024
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr)
 {
 	__shared__ u64 sa[K4_WCH][K4_T], sb[K4_WCH][K4_T];
 	cudaGridDependencySynchronize();      // programmatic dependent launch: wait for the producer grid here
+	if (blockIdx.x == 0 && threadIdx.x == 0) S.dbg[13] = b200_globaltimer();
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad;
@@ -470,6 +472,7 @@ __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 {
 	__shared__ u64 sb[K4_CONTAIN_SBITS];
 	cudaGridDependencySynchronize();
+	if (blockIdx.x == 0 && threadIdx.x == 0) S.dbg[14] = b200_globaltimer();
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	if (c->n_surv > S.cap_pairs) return;             // overflow is flagged by k_adj_scan
@@ -763,7 +766,6 @@ template <int NC> __device__ __forceinline__ void tail_sync()
 }
 #define TAIL_LOOP(i, n) for (u32 i = ctid; i < (u32)(n); i += NC * TAIL_THREADS)
 #define TAIL_SYNC() tail_sync<NC>()
-__device__ __forceinline__ u64 b200_globaltimer() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define TP(k) do { if (ctid == 0) S.dbg[k] = b200_globaltimer(); } while (0)
 
 __device__ __forceinline__ void tail_stage_header(const DevState &S, u32 extra_status, bool header_only)

@@ -256,3 +256,24 @@ def tiny_caps(monkeypatch):
 @pytest.mark.parametrize("flags", [0, 8, 2])
 def test_host_logic_capacity_negotiation(oracle_lib, emul_lib, tiny_caps, tr, flags):
     run_pair(oracle_lib, emul_lib, tr, exact=True, flags_b=flags)
+
+
+def test_product_fails_loudly_without_gpu(tmp_path):
+    """No CPU fallback for the cut: on a machine without a CUDA device the first call that needs the
+    device (poly__intl_apprx) prints a message and aborts; nothing is computed on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from bensolve_b200 import capi, polytopes as P\n"
+        "lib = capi.load_product()\n"
+        "e = capi.PolyEngine(lib, 3)\n"
+        "tr = P.cube(3)\n"
+        "[e.add(tr.vals[i], 0) for i in range(3)]\n"
+        "e.init_approx()\n"
+        "print('UNREACHABLE')\n" % REPO)
+    res = subprocess.run([__import__("sys").executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert res.returncode != 0
+    assert "UNREACHABLE" not in res.stdout
+    assert "no CUDA device" in res.stderr and "no CPU fallback" in res.stderr
