@@ -432,12 +432,19 @@ B200_HD void k4_assign_columns(const DevState &S, u32 j)
 		if (B200_ATOMIC_EXCH(&S.facet_epoch[fc], epoch) != epoch) S.facet_local[fc] = B200_ATOMIC_ADD(&S.ctl->n_local, 1u);
 	}
 }
+// K4 keeps two packed forms of the incidence of the M new rows over the L facets they touch:
+//   rows : bits[w*mpad + x]            bit c of word w  <=> row x lies on local facet 64w+c   (filter: AND + POPC of two rows)
+//   cols : tbits[col*(mpad/64) + x/64] bit x%64         <=> row x lies on local facet col     (containment: AND of columns)
+// tbits starts right after the row matrix in the same buffer.
+B200_HD u64 k4_words(u32 wl, u32 mpad, u32 n_local) { return (u64)wl * mpad + (u64)n_local * (mpad / 64); }
+B200_HD u64 *k4_tbits(const DevState &S, u32 wl, u32 mpad) { return S.bits + (size_t)wl * mpad; }
+
 B200_HD void k4_plan(const DevState &S)
 {
 	CutCtl *c = S.ctl;
 	c->wl = (c->n_local + 63) / 64;
-	c->mpad = (c->n_new + 31) & ~31u;
-	if ((u64)c->wl * c->mpad > S.cap_bits) c->status |= ST_OVF_BITS;
+	c->mpad = (c->n_new + 63) & ~63u;
+	if (k4_words(c->wl, c->mpad, c->n_local) > S.cap_bits) c->status |= ST_OVF_BITS;
 }
 B200_HD void k4_build_row(const DevState &S, u32 j)
 {
@@ -450,7 +457,37 @@ B200_HD void k4_build_row(const DevState &S, u32 j)
 		if (fc == f) continue;
 		const u32 col = S.facet_local[fc];
 		S.bits[(size_t)(col >> 6) * mpad + j] |= (u64)1 << (col & 63);
+		B200_ATOMIC_OR64(&k4_tbits(S, wl, mpad)[(size_t)col * (mpad / 64) + (j >> 6)], (u64)1 << (j & 63));   // zeroed by k4_zero_cols
 	}
+}
+// the column matrix is filled with atomics, so it is cleared first (one barrier / launch earlier)
+B200_HD void k4_zero_cols(const DevState &S, u64 x)
+{
+	k4_tbits(S, S.ctl->wl, S.ctl->mpad)[x] = 0;
+}
+// Containment by columns: a third row containing inc(a) & inc(b) exists iff the AND of the columns of
+// all mask facets has a bit other than a and b (edge_test, bslv_poly.c:487-505).  Scalar form.
+B200_HD bool k4_adjacent_by_columns(const DevState &S, u32 a, u32 b, u32 M, u32 wl, u32 mpad)
+{
+	if (S.d == 1) return true;
+	const u64 *tb = k4_tbits(S, wl, mpad);
+	const u32 mw = mpad / 64;
+	for (u32 xw = 0; xw < mw; xw++) {
+		u64 acc = (xw + 1) * 64 <= M ? ~(u64)0 : (M > xw * 64 ? (((u64)1 << (M - xw * 64)) - 1) : 0);   // valid rows only
+		for (u32 w = 0; w < wl && acc; w++) {
+			u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];
+			while (m && acc) {
+				u32 bit = 0;
+				while (!((m >> bit) & 1)) bit++;
+				m &= m - 1;
+				acc &= tb[(size_t)(w * 64 + bit) * mw + xw];
+			}
+		}
+		if ((a >> 6) == xw) acc &= ~((u64)1 << (a & 63));
+		if ((b >> 6) == xw) acc &= ~((u64)1 << (b & 63));
+		if (acc) return false;
+	}
+	return true;
 }
 B200_HD void k4_push_survivor(const DevState &S, u32 a, u32 b)
 {
@@ -492,6 +529,13 @@ B200_HD void k6_set_row_bits(const DevState &S, u32 r, u32 mpad)
 	}
 }
 B200_HD void k4_contain_pair(const DevState &S, u32 s)
+{
+	const CutCtl *c = S.ctl;
+	const u32 a = S.surv_a[s], b = S.surv_b[s];
+	if (k4_adjacent_by_columns(S, a, b, c->n_new, c->wl, c->mpad)) k4_push_pair(S, a, b);
+}
+// row-scan form (K6: the dual polytope has 10^6 columns, its column matrix is not built)
+B200_HD void k6_contain_pair(const DevState &S, u32 s)
 {
 	const CutCtl *c = S.ctl;
 	const u32 a = S.surv_a[s], b = S.surv_b[s], M = c->n_new;

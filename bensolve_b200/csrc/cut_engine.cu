@@ -531,6 +531,7 @@ void CutEngine::launch_part_b(bool rerun)
 	if (rerun) { k_pairs_reset<<<gmap, K_THREADS, 0, STREAM>>>(S_); stats_.kernel_launches++; }
 	k4_assign<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k4_plan_kernel<<<1, 32, 0, STREAM>>>(S_);
+	k4_zero<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k4_build<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, true));
 	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
@@ -539,7 +540,7 @@ void CutEngine::launch_part_b(bool rerun)
 	k_adj_pair_fill<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k_adj_sort<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k_finish<<<1, 32, 0, STREAM>>>(S_);
-	stats_.kernel_launches += 10;
+	stats_.kernel_launches += 11;
 	CK(cudaGetLastError());
 }
 
@@ -760,6 +761,7 @@ static void emu_k4_matrix(DevState &S)
 	for (u32 j = 0; j < c->n_new; j++) k4_assign_columns(S, j);
 	k4_plan(S);
 	if (c->status & ST_OVF_BITS) return;
+	for (u64 x = 0; x < (u64)c->n_local * (c->mpad / 64); x++) k4_zero_cols(S, x);
 	for (u32 j = 0; j < c->n_new; j++) k4_build_row(S, j);
 }
 static void emu_k4_pairs(DevState &S)
@@ -948,7 +950,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 			launch_all();
 		} else if (hdr_.status & ST_OVF_B) {
 			if (hdr_.status & ST_OVF_PAIRS) ensure_pairs(std::max(hdr_.n_pairs, hdr_.n_surv));
-			if (hdr_.status & ST_OVF_BITS) ensure_bits((u64)hdr_.wl * hdr_.mpad);
+			if (hdr_.status & ST_OVF_BITS) ensure_bits(k4_words(hdr_.wl, hdr_.mpad, hdr_.n_local));
 			if (hdr_.status & ST_OVF_ADJ) ensure_adj(hdr_.adj_used + hdr_.adj_new);
 			launch_part_b(true);
 			launch_part_c(header_only);
@@ -1121,7 +1123,7 @@ void CutEngine::dual_adjacency(const std::vector<u32> &facet_rank, u32 M, std::v
 		k6_begin<<<1, 32, 0, STREAM>>>(S_, M, wl, mpad);
 		k6_build<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, mpad);
 		k4_filter<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, false));
-		k4_contain<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_);
+		k6_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
 		stats_.kernel_launches += 4;
 		CK(cudaGetLastError());
 		CK(cudaMemcpyAsync(pinned_hdr_, S_.ctl, sizeof(CutCtl), cudaMemcpyDeviceToHost, STREAM));
@@ -1136,7 +1138,7 @@ void CutEngine::dual_adjacency(const std::vector<u32> &facet_rank, u32 M, std::v
 		for (u32 a = 0; a < M; a++)
 			for (u32 b = a + 1; b < M; b++) k4_filter_pair_in(S_, S_.bits, wl, mpad, a, b, k4_threshold(S_, false));
 		if (c->n_surv <= S_.cap_pairs)
-			for (u32 sv = 0; sv < c->n_surv; sv++) k4_contain_pair(S_, sv);
+			for (u32 sv = 0; sv < c->n_surv; sv++) k6_contain_pair(S_, sv);
 		const CutCtl h = *c;
 #endif
 		if (h.n_surv > S_.cap_pairs || h.n_pairs > S_.cap_pairs) { ensure_pairs(std::max(h.n_surv, h.n_pairs)); continue; }

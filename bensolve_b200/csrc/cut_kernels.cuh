@@ -356,6 +356,11 @@ __global__ void k4_plan_kernel(DevState S)
 	if (S.ctl->status & ST_SKIP_A) return;
 	k4_plan(S);
 }
+__global__ void __launch_bounds__(K_THREADS) k4_zero(DevState S)
+{
+	if (S.ctl->status & ST_SKIP_B) return;
+	B200_GRID_STRIDE(x, (u64)S.ctl->n_local * (S.ctl->mpad / 64)) k4_zero_cols(S, x);
+}
 __global__ void __launch_bounds__(K_THREADS) k4_build(DevState S)
 {
 	if (S.ctl->status & ST_SKIP_B) return;
@@ -367,9 +372,11 @@ __global__ void __launch_bounds__(K_THREADS) k4_build(DevState S)
 // (i0 + 4k, j), so a warp reads 32 consecutive B words (conflict-free) and one broadcast A word.
 #define K4_T 64
 #define K4_WCH 16
+#define K4_SV 512
 __global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr)
 {
 	__shared__ u64 sa[K4_WCH][K4_T], sb[K4_WCH][K4_T];
+	__shared__ u32 sva[K4_SV], svb[K4_SV], nsv, gbase;
 	cudaGridDependencySynchronize();      // programmatic dependent launch: wait for the producer grid here
 	if (blockIdx.x == 0 && threadIdx.x == 0) S.dbg[13] = b200_globaltimer();
 	const CutCtl *c = S.ctl;
@@ -399,12 +406,27 @@ __global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr)
 			}
 			__syncthreads();
 		}
+		// survivors of this tile pair are collected in shared memory and published with ONE global
+		// atomic per block (thousands of single-address atomics would serialise in L2)
 		const u32 b = tb * K4_T + j;
+		if (threadIdx.x == 0) nsv = 0;
+		__syncthreads();
 #pragma unroll
 		for (int k = 0; k < K4_T / 4; k++) {
 			const u32 a = ta * K4_T + i0 + 4 * k;
-			if (a < b && b < M && cnt[k] >= thr) k4_push_survivor(S, a, b);
+			if (a < b && b < M && cnt[k] >= thr) {
+				const u32 q = atomicAdd(&nsv, 1u);
+				if (q < K4_SV) { sva[q] = a; svb[q] = b; }
+				else k4_push_survivor(S, a, b);           // rare overflow of the block buffer
+			}
 		}
+		__syncthreads();
+		const u32 n = min(nsv, (u32)K4_SV);
+		if (threadIdx.x == 0 && n) gbase = atomicAdd(&S.ctl->n_surv, n);
+		__syncthreads();
+		for (u32 q = threadIdx.x; q < n; q += K_THREADS)
+			if (gbase + q < S.cap_pairs) { S.surv_a[gbase + q] = sva[q]; S.surv_b[gbase + q] = svb[q]; }
+		__syncthreads();
 	}
 }
 
@@ -412,9 +434,8 @@ __global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr)
 // inc(a) & inc(b) (edge_test, bslv_poly.c:487-505).  Lanes scan 32 candidate rows per step; only the
 // non-zero words of the mask are compared (a mask holds >= d-2 bits, rarely more than a few words).
 #define K4_NZ 8
-__device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bits, u32 s, u32 lane, u32 M, u32 wl, u32 mpad)
+__device__ __forceinline__ bool k4_contain_verdict(const DevState &S, const u64 *bits, u32 a, u32 b, u32 lane, u32 M, u32 wl, u32 mpad)
 {
-	const u32 a = S.surv_a[s], b = S.surv_b[s];
 	bool adjacent = true;
 	if (S.d != 1) {
 		// the non-zero words of the mask inc(a) & inc(b): the first K4_NZ in registers of every lane
@@ -465,28 +486,95 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *bi
 			if (__any_sync(0xffffffffu, any)) { adjacent = false; break; }
 		}
 	}
-	if (adjacent && lane == 0) k4_push_pair(S, a, b);
+	return adjacent;
 }
-#define K4_CONTAIN_SBITS 6016u      // 47 KB: the whole bit matrix of a medium cut (M = 2000, 3 words per row)
+// Containment by columns, one warp per surviving pair: lane l owns word l (+32, +64, ...) of the
+// candidate set, which is the AND of the columns (rows-on-facet bitmaps) of every facet in the mask
+// inc(a) & inc(b); the pair is adjacent iff nothing but a and b survives (edge_test, bslv_poly.c:487-505).
+// Work per pair: |mask| column words per lane instead of a scan over all M candidate rows.
+__device__ __forceinline__ bool k4_columns_verdict(const DevState &S, u32 a, u32 b, u32 lane, u32 M, u32 wl, u32 mpad)
+{
+	if (S.d == 1) return true;
+	const u64 *tb = k4_tbits(S, wl, mpad);
+	const u32 mw = mpad / 64;
+	bool other = false;
+	for (u32 x0 = 0; x0 < mw && !other; x0 += 32) {            // warp-uniform trip count
+		const u32 xw = x0 + lane;
+		u64 acc = 0;
+		if (xw < mw) acc = (xw + 1) * 64 <= M ? ~(u64)0 : (M > xw * 64 ? (((u64)1 << (M - xw * 64)) - 1) : 0);
+		for (u32 w = 0; w < wl; w++) {
+			u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];   // same value in every lane
+			while (m) {
+				const u32 col = w * 64 + (u32)__ffsll((long long)m) - 1;
+				m &= m - 1;
+				if (xw < mw) acc &= tb[(size_t)col * mw + xw];
+			}
+		}
+		if ((a >> 6) == xw) acc &= ~((u64)1 << (a & 63));
+		if ((b >> 6) == xw) acc &= ~((u64)1 << (b & 63));
+		other = __any_sync(0xffffffffu, acc != 0);
+	}
+	return !other;
+}
+__device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *, u32 s, u32 lane, u32 M, u32 wl, u32 mpad)
+{
+	const u32 a = S.surv_a[s], b = S.surv_b[s];
+	if (k4_columns_verdict(S, a, b, lane, M, wl, mpad) && lane == 0) k4_push_pair(S, a, b);
+}
+
+template <bool COLUMNS>
+__device__ __forceinline__ void contain_block_rounds(const DevState &S, u32 *pra, u32 *prb, u32 &npr, u32 &pbase)
+{
+	const CutCtl *c = S.ctl;
+	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad, ns = c->n_surv;
+	const u32 lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	// adjacent pairs of a block round are collected in shared memory; one global atomic per round
+	for (u32 s0 = blockIdx.x * wpb; s0 < ns; s0 += gridDim.x * wpb) {   // block-uniform trip count
+		const u32 s = s0 + (threadIdx.x >> 5);
+		bool adj = false;
+		u32 a = 0, b = 0;
+		if (s < ns) {
+			a = S.surv_a[s];
+			b = S.surv_b[s];
+			adj = COLUMNS ? k4_columns_verdict(S, a, b, lane, M, wl, mpad) : k4_contain_verdict(S, S.bits, a, b, lane, M, wl, mpad);
+		}
+		if (threadIdx.x == 0) npr = 0;
+		__syncthreads();
+		if (adj && lane == 0) {
+			const u32 q = atomicAdd(&npr, 1u);
+			pra[q] = a;
+			prb[q] = b;
+			atomicAdd(&S.deg[a], 1u);
+			atomicAdd(&S.deg[b], 1u);
+		}
+		__syncthreads();
+		if (threadIdx.x == 0 && npr) pbase = atomicAdd(&S.ctl->n_pairs, npr);
+		__syncthreads();
+		if (threadIdx.x < npr && pbase + threadIdx.x < S.cap_pairs) {
+			S.pair_a[pbase + threadIdx.x] = pra[threadIdx.x];
+			S.pair_b[pbase + threadIdx.x] = prb[threadIdx.x];
+		}
+		__syncthreads();
+	}
+}
 __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 {
-	__shared__ u64 sb[K4_CONTAIN_SBITS];
+	__shared__ u32 pra[K_THREADS / 32], prb[K_THREADS / 32], npr, pbase;
 	cudaGridDependencySynchronize();
 	if (blockIdx.x == 0 && threadIdx.x == 0) S.dbg[14] = b200_globaltimer();
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	if (c->n_surv > S.cap_pairs) return;             // overflow is flagged by k_adj_scan
-	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad, ns = c->n_surv;
-	const u32 lane = threadIdx.x & 31;
-	const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-	if (blockIdx.x * (blockDim.x >> 5) >= ns) return;   // no survivor for this block
-	const u64 *bits = S.bits;
-	if ((u64)wl * mpad <= K4_CONTAIN_SBITS) {        // every candidate row is read from shared memory
-		for (u32 x = threadIdx.x; x < wl * mpad; x += K_THREADS) sb[x] = S.bits[x];
-		__syncthreads();
-		bits = sb;
-	}
-	for (u32 s = warp; s < ns; s += nwarps) k4_contain_warp(S, bits, s, lane, M, wl, mpad);
+	contain_block_rounds<true>(S, pra, prb, npr, pbase);
+}
+// K6 keeps the row-scan form: its columns are the 10^5..10^6 live vertices
+__global__ void __launch_bounds__(K_THREADS) k6_contain(DevState S)
+{
+	__shared__ u32 pra[K_THREADS / 32], prb[K_THREADS / 32], npr, pbase;
+	const CutCtl *c = S.ctl;
+	if (c->status & ST_SKIP_B) return;
+	if (c->n_surv > S.cap_pairs) return;
+	contain_block_rounds<false>(S, pra, prb, npr, pbase);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_adj_scan(DevState S)
@@ -854,7 +942,6 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, int header_only)
 {
 	__shared__ u32 ws[33];
-	__shared__ u64 sbits[NC > 1 ? TAIL_SBITS : 1];
 	__shared__ u32 slist[B200_VIS_MAX];
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
 	cudaGridDependencySynchronize();      // K1 (and the exchange kernels) precede this launch
@@ -1009,11 +1096,14 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	TAIL_LOOP(j, M) k4_assign_columns(S, j);
 	TAIL_SYNC();
 	TP(6);
-	// every thread derives the matrix shape itself (no barrier between plan and build)
-	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 31) & ~31u;
-	const bool bits_ovf = (u64)wl * mpad > S.cap_bits;
+	// every thread derives the matrix shape itself (no barrier between plan and the stores below)
+	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 63) & ~63u;
+	const bool bits_ovf = k4_words(wl, mpad, c->n_local) > S.cap_bits;
 	if (ctid == 0) k4_plan(S);
 	if (!bits_ovf) {
+		u64 *tb = k4_tbits(S, wl, mpad);
+		for (u64 x = ctid; x < (u64)c->n_local * (mpad / 64); x += NC * TAIL_THREADS) tb[x] = 0;
+		TAIL_SYNC();
 		TAIL_LOOP(j, M) {
 			for (u32 w = 0; w < wl; w++) S.bits[(size_t)w * mpad + j] = 0;
 			const u32 r = c->nrows + j, f = P.facet;
@@ -1023,34 +1113,28 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 				if (fc == f) continue;
 				const u32 col = S.facet_local[fc];
 				S.bits[(size_t)(col >> 6) * mpad + j] |= (u64)1 << (col & 63);
+				atomicOr((unsigned long long *)&tb[(size_t)col * (mpad / 64) + (j >> 6)], (unsigned long long)1 << (j & 63));
 			}
 		}
 		TAIL_SYNC();
 		TP(7);
 		if (mode == 1) return;                            // k4_filter, k4_contain, k_tail2 follow
-		// the pair test is M^2 integer work: 8 SMs only pay off for small M, beyond that the
+		// the pair filter is M^2 integer work: 8 SMs only pay off for small M, beyond that the
 		// multi-block k4_filter / k4_contain (all 148 SMs) follow
-		const bool in_smem = NC > 1 && (u64)wl * mpad <= TAIL_SBITS;
 		if (M > (NC == 1 ? B200_K4_SMALL / 2 : B200_K4_SMALL)) {
 			if (rank == 0) tail_stage_header(S, ST_K4_PENDING, header_only);
 			return;
 		}
-		// ---- P7: pair test inside the cluster; each CTA stages the whole bit matrix in shared memory
-		const u64 *bits = S.bits;
-		if (in_smem) {
-			for (u32 x = threadIdx.x; x < wl * mpad; x += TAIL_THREADS) sbits[x] = S.bits[x];
-			__syncthreads();
-			bits = sbits;
-		}
+		// ---- P7: pair test inside the cluster
 		for (u32 p = ctid; p < M * M; p += NC * TAIL_THREADS) {
 			const u32 a = p / M, b = p % M;
-			if (a < b) k4_filter_pair_in(S, bits, wl, mpad, a, b, k4_threshold(S, true));
+			if (a < b) k4_filter_pair_in(S, S.bits, wl, mpad, a, b, k4_threshold(S, true));
 		}
 		TAIL_SYNC();
 		TP(8);
 		if (c->n_surv <= S.cap_pairs) {
 			const u32 ns = c->n_surv;
-			for (u32 s = ctid >> 5; s < ns; s += NC * TAIL_THREADS / 32) k4_contain_warp(S, bits, s, threadIdx.x & 31, M, wl, mpad);
+			for (u32 s = ctid >> 5; s < ns; s += NC * TAIL_THREADS / 32) k4_contain_warp(S, S.bits, s, threadIdx.x & 31, M, wl, mpad);
 		}
 		TAIL_SYNC();
 	} else {
@@ -1169,5 +1253,6 @@ __global__ void k6_begin(DevState S, u32 M, u32 wl, u32 mpad)
 	c->n_new = M;
 	c->wl = wl;
 	c->mpad = mpad;
+	c->n_local = 0;
 	c->n_surv = c->n_pairs = 0;
 }
