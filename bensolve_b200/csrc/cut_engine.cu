@@ -1024,24 +1024,19 @@ void CutEngine::cut(const CutParams &P, CutDelta &out)
 	const double t_run = now_us();
 	account(P, n_live_before, nrows_before);
 	if (hdr_.status & ST_REDUNDANT) { out.redundant = 1; return; }
-	// ---- unpack the delta record
+	// ---- the delta record is consumed in place (pinned staging buffer)
 	const u32 n_new = hdr_.n_new;
 	const StageLayout L = stage_layout(hdr_, d_);
 	out.trigger_slot = hdr_.min_strict_slot;
 	out.n_new = n_new;
 	out.first_new_slot = hdr_.slot_cnt - n_new;
-	out.coords.resize((size_t)n_new * d_);
-	out.ideal.resize(n_new);
-	out.parent_slot.resize(n_new);
-	if (n_new) {
-		memcpy(out.coords.data(), pinned_stage_ + L.coords, (size_t)n_new * d_ * sizeof(double));
-		memcpy(out.parent_slot.data(), pinned_stage_ + L.parent, (size_t)n_new * 4);
-		memcpy(out.ideal.data(), pinned_stage_ + L.ideal, n_new);
-	}
-	const u32 *ds = (const u32 *)(pinned_stage_ + L.dead_slots);
-	for (u32 i = 0; i < hdr_.n_vis; i++) if (ds[i] != B200_NONE) out.dead_slots.push_back(ds[i]);
-	const u32 *df = (const u32 *)(pinned_stage_ + L.dead_facets);
-	out.dead_facets.assign(df, df + hdr_.n_dead_facets);
+	out.coords = (const double *)(pinned_stage_ + L.coords);
+	out.parent_slot = (const u32 *)(pinned_stage_ + L.parent);
+	out.ideal = (const u8 *)(pinned_stage_ + L.ideal);
+	out.dead_slots = (const u32 *)(pinned_stage_ + L.dead_slots);
+	out.n_dead_entries = hdr_.n_vis;
+	out.dead_facets = (const u32 *)(pinned_stage_ + L.dead_facets);
+	out.n_dead_facets = hdr_.n_dead_facets;
 	maybe_compact();
 	stats_.host_us[3] += now_us() - t_run;
 	stats_.host_us[4] += now_us() - t_in;

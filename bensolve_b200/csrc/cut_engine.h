@@ -7,16 +7,19 @@
 
 #include "cut_types.h"
 
-struct CutDelta {             // what one cut changed, in host slot numbers (SURVEY 8(b) coherence rule)
+struct CutDelta {             // what one cut changed, in host slot numbers (SURVEY 8(b) coherence rule).
+	// The arrays point into the engine's pinned staging buffer and stay valid until its next cut.
 	int redundant = 0;        // 1 => nothing changed, poly__add_vrtx returns EXIT_FAILURE
 	u32 trigger_slot = 0;     // lowest strictly violated slot: the reference's args->idx (bslv_poly.c:121-131)
 	u32 first_new_slot = 0;
 	u32 n_new = 0;
-	std::vector<double> coords;     // AoS [n_new][d]
-	std::vector<u8> ideal;          // [n_new]
-	std::vector<u32> parent_slot;   // [n_new] slot copied from (ZERO copies) or B200_NONE (edge vertices)
-	std::vector<u32> dead_slots;
-	std::vector<u32> dead_facets;
+	const double *coords = nullptr;     // AoS [n_new][d]
+	const u8 *ideal = nullptr;          // [n_new]
+	const u32 *parent_slot = nullptr;   // [n_new] slot copied from (ZERO copies) or B200_NONE (edge vertices)
+	const u32 *dead_slots = nullptr;    // [n_dead_entries], entries equal to B200_NONE are to be skipped
+	u32 n_dead_entries = 0;
+	const u32 *dead_facets = nullptr;   // [n_dead_facets]
+	u32 n_dead_facets = 0;
 };
 
 struct MirrorDump {           // bulk state for rebuilding the host mirror after a device-resident batch

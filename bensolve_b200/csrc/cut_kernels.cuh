@@ -1035,6 +1035,9 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 			S.he_off[n_vis] = carry;
 			if (carry > B200_HE_CAP) c->status |= ST_NEED_BIG;
 		}
+		__syncthreads();
+		if (carry <= B200_HE_CAP)                          // owner of every half-edge (CTA 0 has the offsets at hand)
+			for (u32 i = threadIdx.x; i < n_vis; i += TAIL_THREADS) he_owner_fill(S, i);
 	}
 	TAIL_SYNC();
 	if (c->status & ST_NEED_BIG) {
@@ -1046,15 +1049,13 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	const u32 H = S.he_off[n_vis];
 	TP(2);
 	// ---- P3: evaluate every (visited vertex, neighbour) pair
-	TAIL_LOOP(i, n_vis) he_owner_fill(S, i);
-	TAIL_SYNC();
 	TAIL_LOOP(e, H) he_eval(S, e);
 	TAIL_SYNC();
 	TP(3);
-	// ---- P4: sizes, offsets, capacity plan (nothing mutated so far except ZERO+ projections)
-	TAIL_LOOP(i, n_vis) he_count(S, i);
-	TAIL_SYNC();
+	// ---- P4: sizes, offsets, capacity plan by CTA 0 (nothing mutated so far except ZERO+ projections)
 	if (rank == 0) {
+		for (u32 i = threadIdx.x; i < n_vis; i += TAIL_THREADS) he_count(S, i);
+		__syncthreads();
 		u32 carry[3] = {0, 0, 0};
 		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
 			u32 i = base + threadIdx.x;

@@ -215,7 +215,7 @@ static void apply_delta(poly_args *a, const CutDelta &dl)
 	if (P->cnt != dl.first_new_slot) die("poly__add_vrtx", "host mirror and device disagree on the slot count");
 	for (u32 r = 0; r < dl.n_new; r++) {
 		const size_t s = mirror_append(P);
-		memcpy(P->data + s * d, dl.coords.data() + (size_t)r * d, d * sizeof(double));
+		memcpy(P->data + s * d, dl.coords + (size_t)r * d, d * sizeof(double));
 		if (dl.ideal[r]) ST_BT(P->ideal, s);
 		const u32 par = dl.parent_slot[r];
 		if (par != B200_NONE && IS_ELEM(P->sltn, par)) {   // copy inherits sltn + pre-image (bslv_poly.c:583-587)
@@ -223,8 +223,9 @@ static void apply_delta(poly_args *a, const CutDelta &dl)
 			memcpy(P->data_primg + s * P->dim_primg, P->data_primg + (size_t)par * P->dim_primg, P->dim_primg * sizeof(double));
 		}
 	}
-	for (u32 s : dl.dead_slots) UNST_BT(P->used, s);
-	for (u32 f : dl.dead_facets) UNST_BT(D->used, f);
+	for (u32 i = 0; i < dl.n_dead_entries; i++)
+		if (dl.dead_slots[i] != B200_NONE) UNST_BT(P->used, dl.dead_slots[i]);
+	for (u32 i = 0; i < dl.n_dead_facets; i++) UNST_BT(D->used, dl.dead_facets[i]);
 }
 
 extern "C" int poly__add_vrtx(poly_args *args)
