@@ -106,9 +106,51 @@ B200_HD bool zp_activate(const DevState &S, const CutParams &P, u32 i)
 	return true;
 }
 
+// Short lists (simple vertices have exactly d entries) are fetched with independent loads and
+// compared in registers: a sorted merge over global memory is a chain of dependent L2 round trips.
+#define B200_SHORT 8
+B200_HD void load_short(const u32 *p, u32 n, u32 r[B200_SHORT])
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (u32 t = 0; t < B200_SHORT; t++) r[t] = t < n ? p[t] : B200_NONE;
+}
+// bit t of the result <=> a[t] also occurs in b   (both lists at most B200_SHORT long, entries distinct)
+B200_HD u32 common_mask_short(const u32 ra[B200_SHORT], u32 na, const u32 rb[B200_SHORT])
+{
+	u32 m = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (u32 t = 0; t < B200_SHORT; t++) {
+		bool hit = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 u = 0; u < B200_SHORT; u++) hit |= (rb[u] == ra[t]);
+		if (t < na && hit) m |= 1u << t;
+	}
+	return m;
+}
+B200_HD u32 popc32(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+	return (u32)__popc(x);
+#else
+	return (u32)__builtin_popcount(x);
+#endif
+}
+
 // |A n B| of two sorted lists
 B200_HD u32 isect_count(const u32 *a, u32 na, const u32 *b, u32 nb)
 {
+	if (na <= B200_SHORT && nb <= B200_SHORT) {
+		u32 ra[B200_SHORT], rb[B200_SHORT];
+		load_short(a, na, ra);
+		load_short(b, nb, rb);
+		return popc32(common_mask_short(ra, na, rb));
+	}
 	u32 i = 0, j = 0, n = 0;
 	while (i < na && j < nb) {
 		u32 x = a[i], y = b[j];
@@ -171,6 +213,16 @@ B200_HD void clr_bit_atomic(u32 *w, u32 i) { B200_ATOMIC_AND(&w[i >> 5], ~(1u <<
 B200_HD void rewire(const DevState &S, u32 k, u32 v, u32 nw)
 {
 	u32 off = S.adj_off[k], n = S.adj_len[k];
+	if (n <= B200_SHORT) {
+		u32 r[B200_SHORT];
+		load_short(S.adj_pool + off, n, r);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 q = 0; q < B200_SHORT; q++)
+			if (q < n && r[q] == v) { S.adj_pool[off + q] = nw; return; }
+		return;
+	}
 	for (u32 q = 0; q < n; q++)
 		if (S.adj_pool[off + q] == v) { S.adj_pool[off + q] = nw; return; }
 }
@@ -218,18 +270,33 @@ B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 
 	// incidence {f} u (inc(k) n inc(v)), sorted; f is the largest facet id so far
 	const u32 *iv = S.inc_pool + S.inc_off[v], *ik = S.inc_pool + S.inc_off[k];
 	const u32 niv = S.inc_len[v], nik = S.inc_len[k];
-	u32 a = 0, b = 0, w = ipos;
-	while (a < niv && b < nik) {
-		const u32 x = iv[a], y = ik[b];
-		if (x == y) {
-			S.inc_pool[w++] = x;
-			B200_ATOMIC_ADD(&S.facet_cnt[x], 1u);
+	u32 w = ipos;
+	if (niv <= B200_SHORT && nik <= B200_SHORT) {
+		u32 rv[B200_SHORT], rk[B200_SHORT];
+		load_short(iv, niv, rv);
+		load_short(ik, nik, rk);
+		const u32 m = common_mask_short(rv, niv, rk);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 t = 0; t < B200_SHORT; t++)
+			if ((m >> t) & 1u) {
+				S.inc_pool[w++] = rv[t];
+				B200_ATOMIC_ADD(&S.facet_cnt[rv[t]], 1u);
+			}
+	} else {
+		u32 a = 0, b = 0;
+		while (a < niv && b < nik) {
+			const u32 x = iv[a], y = ik[b];
+			if (x == y) {
+				S.inc_pool[w++] = x;
+				B200_ATOMIC_ADD(&S.facet_cnt[x], 1u);
+			}
+			a += (x <= y);
+			b += (y <= x);
 		}
-		a += (x <= y);
-		b += (y <= x);
 	}
-	S.inc_pool[w++] = f;
-	B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
+	S.inc_pool[w++] = f;                      // facet_cnt[f] is set once to n_new by the plan stage
 	S.inc_off[nw] = ipos;
 	S.inc_len[nw] = w - ipos;
 }
@@ -239,6 +306,13 @@ B200_HD void shared_facet_mask(const DevState &S, u32 v, u32 k, u64 mask[B200_MA
 {
 	const u32 *iv = S.inc_pool + S.inc_off[v], *ik = S.inc_pool + S.inc_off[k];
 	const u32 niv = S.inc_len[v], nik = S.inc_len[k];
+	if (niv <= B200_SHORT && nik <= B200_SHORT) {
+		u32 rv[B200_SHORT], rk[B200_SHORT];
+		load_short(iv, niv, rv);
+		load_short(ik, nik, rk);
+		mask[0] |= (u64)common_mask_short(rv, niv, rk);
+		return;
+	}
 	u32 a = 0, b = 0;
 	while (a < niv && a < B200_MAXINC && b < nik) {
 		const u32 x = iv[a], y = ik[b];
@@ -274,8 +348,7 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 			S.inc_pool[w++] = iv[a];
 			B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
 		}
-	S.inc_pool[w++] = f;
-	B200_ATOMIC_ADD(&S.facet_cnt[f], 1u);
+	S.inc_pool[w++] = f;                      // facet_cnt[f] is set once to n_new by the plan stage
 	S.inc_off[nw] = ipos;
 	S.inc_len[nw] = w - ipos;
 }
@@ -394,10 +467,8 @@ B200_HD void he_finish_vertex(const DevState &S, const CutParams &P, u32 i)
 	if (c == CLS_ZERO) {
 		emit_copy_row(S, P, v, S.base3[3 * (size_t)i + 0], S.ctl->inc_used + S.base3[3 * (size_t)i + 1], S.base3[3 * (size_t)i + 2],
 		              S.cnt3[3 * (size_t)i + 2], &S.zmask[(size_t)i * (B200_MAXINC / 64)]);
-		B200_ATOMIC_ADD(&S.ctl->n_zero, 1u);
-	} else
-		B200_ATOMIC_ADD(&S.ctl->n_minus, 1u);
-	retire_row(S, v, i);
+	}
+	retire_row(S, v, i);                      // n_minus / n_zero were counted by the plan stage
 }
 
 // redundant halfspace: nothing is cut, the non-PLUS rows K1 marked go back to PLUS

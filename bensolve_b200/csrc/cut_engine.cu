@@ -751,6 +751,7 @@ static void emu_scan3_plan(DevState &S)
 	for (u32 i = 0; i < c->n_vis; i++)
 		for (int k = 0; k < 3; k++) { S.base3[3 * (size_t)i + k] = carry[k]; carry[k] += S.cnt3[3 * (size_t)i + k]; }
 	c->n_new = carry[0]; c->inc_new = carry[1]; c->padj_new = carry[2];
+	S.facet_cnt[S.cur->facet] = carry[0];
 	if ((u64)c->nrows + carry[0] > S.cap_rows) c->status |= ST_OVF_ROWS;
 	if ((u64)c->inc_used + carry[1] > S.cap_inc) c->status |= ST_OVF_INC;
 	if (carry[2] > S.cap_padj) c->status |= ST_OVF_PADJ;
@@ -854,7 +855,12 @@ void CutEngine::launch_small(const CutParams &Pin, int mode, bool header_only)
 	if (H > B200_HE_CAP) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
 	for (u32 i = 0; i < c->n_vis; i++) he_owner_fill(S, i);
 	for (u32 e = 0; e < H; e++) he_eval(S, e);
-	for (u32 i = 0; i < c->n_vis; i++) he_count(S, i);
+	for (u32 i = 0; i < c->n_vis; i++) {
+		he_count(S, i);
+		const u8 cl = S.cls[S.vis[i]];
+		c->n_minus += (cl == CLS_MINUS);
+		c->n_zero += (cl == CLS_ZERO);
+	}
 	emu_scan3_plan(S);
 	if (c->status & (ST_OVF_A | ST_ERR_DEGENERATE)) { launch_part_c(header_only); return; }
 	for (u32 e = H; e-- > 0;) he_emit(S, P, e);            // any order is valid: run it backwards here

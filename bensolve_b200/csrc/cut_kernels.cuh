@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan3_plan(DevState S)
 		c->n_new = carry[0];
 		c->inc_new = carry[1];
 		c->padj_new = carry[2];
+		S.facet_cnt[S.cur->facet] = carry[0];          // every new row lies on the new facet
 		u32 st = 0;
 		if ((u64)c->nrows + carry[0] > S.cap_rows) st |= ST_OVF_ROWS;
 		if ((u64)c->inc_used + carry[1] > S.cap_inc) st |= ST_OVF_INC;
@@ -1054,7 +1055,19 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	TP(3);
 	// ---- P4: sizes, offsets, capacity plan by CTA 0 (nothing mutated so far except ZERO+ projections)
 	if (rank == 0) {
-		for (u32 i = threadIdx.x; i < n_vis; i += TAIL_THREADS) he_count(S, i);
+		u32 nm = 0, nz = 0;
+		for (u32 i = threadIdx.x; i < n_vis; i += TAIL_THREADS) {
+			he_count(S, i);
+			const u8 cl = S.cls[S.vis[i]];
+			nm += (cl == CLS_MINUS);
+			nz += (cl == CLS_ZERO);
+		}
+		nm = __reduce_add_sync(0xffffffffu, nm);
+		nz = __reduce_add_sync(0xffffffffu, nz);
+		if ((threadIdx.x & 31) == 0) {               // one atomic per warp instead of one per visited vertex
+			if (nm) atomicAdd(&c->n_minus, nm);
+			if (nz) atomicAdd(&c->n_zero, nz);
+		}
 		__syncthreads();
 		u32 carry[3] = {0, 0, 0};
 		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
@@ -1071,6 +1084,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 			c->n_new = carry[0];
 			c->inc_new = carry[1];
 			c->padj_new = carry[2];
+			S.facet_cnt[S.cur->facet] = carry[0];      // every new row lies on the new facet
 			u32 st = 0;
 			if ((u64)c->nrows + carry[0] > S.cap_rows) st |= ST_OVF_ROWS;
 			if ((u64)c->inc_used + carry[1] > S.cap_inc) st |= ST_OVF_INC;
