@@ -285,7 +285,11 @@ CutEngine::~CutEngine()
 	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
 	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
 	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits, S_.stage, S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits,
+#ifdef B200_EMULATE
+	                S_.stage,
+#endif
+	                S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 	drop_shadow();
 #ifndef B200_EMULATE
@@ -389,11 +393,17 @@ void CutEngine::ensure_stage(u64 need)
 {
 	if (need <= S_.cap_stage) return;
 	const u64 cap = std::max<u64>(need, S_.cap_stage * 2);
-	regrow(S_.stage, cap, 0);
 #ifndef B200_EMULATE
+	// mapped pinned host memory: the kernels write the delta record straight into it (no D2H copy)
+	if (stream_) CK(cudaStreamSynchronize(STREAM));
 	if (pinned_stage_) CK(cudaFreeHost(pinned_stage_));
-	CK(cudaMallocHost((void **)&pinned_stage_, cap));
+	CK(cudaHostAlloc((void **)&pinned_stage_, cap, cudaHostAllocMapped));
+	memset(pinned_stage_, 0, cap);
+	void *dp = nullptr;
+	CK(cudaHostGetDevicePointer(&dp, pinned_stage_, 0));
+	S_.stage = (unsigned char *)dp;
 #else
+	regrow(S_.stage, cap, 0);
 	free(pinned_stage_);
 	pinned_stage_ = (unsigned char *)calloc(1, cap);
 #endif
@@ -509,7 +519,7 @@ void CutEngine::launch_part_a(const CutParams &P)
 	const int gmap = num_sms_ * 4;
 	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
 	if (dev_vals_)
-		k_begin_dev<<<1, 32, 0, STREAM>>>(S_, dev_vals_, dev_ideal_, dev_index_, P.facet, P.batch_first);
+		k_begin_dev<<<1, 32, 0, STREAM>>>(S_, dev_vals_, dev_ideal_, dev_index_, P.facet, P.batch_first, P.seq);
 	else
 		k_begin<<<1, 32, 0, STREAM>>>(S_, P);
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
@@ -643,6 +653,8 @@ void CutEngine::launch_k4_and_tail2(bool header_only)
 void CutEngine::launch_part_c(bool header_only)
 {
 	k_pack_delta<<<header_only ? 1 : num_sms_ * 2, K_THREADS, 0, STREAM>>>(S_, header_only ? 1 : 0);
+	k_publish<<<1, 32, 0, STREAM>>>(S_, seq_);
+	stats_.kernel_launches++;
 	stats_.kernel_launches++;
 }
 
@@ -650,14 +662,20 @@ void CutEngine::launch_part_c(bool header_only)
 // record is longer than the speculative first chunk.
 void CutEngine::fetch_delta()
 {
-	const u64 first = header_only_ ? B200_STAGE_HDR : std::min<u64>(S_.cap_stage, 64 * 1024);
-	CK(cudaMemcpyAsync(pinned_stage_, S_.stage, first, cudaMemcpyDeviceToHost, STREAM));
-	CK(cudaStreamSynchronize(STREAM));
-	memcpy(&hdr_, pinned_stage_, sizeof(CutCtl));
-	if (!header_only_ && !(hdr_.status & (ST_OVF_A | ST_OVF_B | ST_OVF_STAGE | ST_NEED_BIG | ST_K4_PENDING)) && hdr_.stage_bytes > first) {
-		CK(cudaMemcpyAsync(pinned_stage_ + first, S_.stage + first, hdr_.stage_bytes - first, cudaMemcpyDeviceToHost, STREAM));
-		CK(cudaStreamSynchronize(STREAM));
+	volatile u32 *seqp = (volatile u32 *)(pinned_stage_ + B200_STAGE_SEQ);
+	for (u64 spins = 1; *seqp != seq_; spins++) {
+		if ((spins & 0x3fff) == 0) {          // every ~16k polls make sure the stream is still healthy
+			cudaError_t e = cudaStreamQuery(STREAM);
+			if (e != cudaSuccess && e != cudaErrorNotReady)
+				fail(std::string("CUDA error while waiting for the cut: ") + cudaGetErrorString(e));
+			if (e == cudaSuccess && *seqp != seq_) {
+				CK(cudaStreamSynchronize(STREAM));
+				if (*seqp != seq_) fail("bensolve_b200: the device finished a cut without publishing its record");
+			}
+		}
 	}
+	__sync_synchronize();
+	memcpy(&hdr_, pinned_stage_, sizeof(CutCtl));
 }
 #else // ---- host-side test double: same stage bodies, run serially
 static CutParams emu_params(const DevState &S, const CutParams &Pin, const double *dv, const unsigned char *di, u64 vi)
@@ -909,6 +927,16 @@ bool CutEngine::use_small_path() const
 #endif
 }
 
+void CutEngine::bump_seq()
+{
+	++seq_;
+#ifndef B200_EMULATE
+	k_set_seq<<<1, 32, 0, STREAM>>>(S_, seq_);
+#else
+	S_.cur->seq = seq_;
+#endif
+}
+
 void CutEngine::run_cut(const CutParams &P, bool header_only)
 {
 #ifndef B200_EMULATE
@@ -921,13 +949,15 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 #ifndef B200_EMULATE
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[2], STREAM));
 #endif
+	CutParams Pq = P;                        // P + the sequence number the device publishes when the record is staged
 	const bool force_big = (flags_ & 4) != 0;
 	bool small = use_small_path() && !force_big && !prefer_big_;
 	auto launch_all = [&]() {
+		Pq.seq = ++seq_;
 		if (small) {
-			launch_small(P, expect_m_ > (B200_K4_SMALL * 7) / 8 ? 1 : 0, header_only);
+			launch_small(Pq, expect_m_ > (B200_K4_SMALL * 7) / 8 ? 1 : 0, header_only);
 		} else {
-			launch_part_a(P);
+			launch_part_a(Pq);
 			launch_part_b(false);
 			launch_part_c(header_only);
 		}
@@ -948,6 +978,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 			prefer_big_ = true;
 			launch_all();
 		} else if (hdr_.status & ST_K4_PENDING) {   // tail stopped before the pair test
+			bump_seq();
 			launch_k4_and_tail2(header_only);
 		} else if (hdr_.status & ST_OVF_A) {
 			if (hdr_.status & ST_OVF_ROWS) ensure_rows(hdr_.nrows + hdr_.n_new + B200_TILE);
@@ -958,10 +989,12 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 			if (hdr_.status & ST_OVF_PAIRS) ensure_pairs(std::max(hdr_.n_pairs, hdr_.n_surv));
 			if (hdr_.status & ST_OVF_BITS) ensure_bits(k4_words(hdr_.wl, hdr_.mpad, hdr_.n_local));
 			if (hdr_.status & ST_OVF_ADJ) ensure_adj(hdr_.adj_used + hdr_.adj_new);
+			bump_seq();
 			launch_part_b(true);
 			launch_part_c(header_only);
 		} else {
 			ensure_stage(hdr_.stage_bytes);
+			bump_seq();
 			launch_part_c(header_only);
 		}
 		fetch_delta();

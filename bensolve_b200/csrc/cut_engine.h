@@ -102,12 +102,14 @@ private:
 	void launch_part_b(bool rerun);
 	void launch_part_c(bool header_only);
 	void fetch_delta();
+	void bump_seq();
 	void ensure_stage(u64 need);
 	void maybe_compact();
 
 	int d_;
 	unsigned flags_ = 0;
 	bool header_only_ = false;
+	u32 seq_ = 0;                  // sequence number of the record the host waits for
 	bool tiny_caps_ = false;
 	bool small_dirty_ = true;      // tile counters / K1 accumulators must be cleared before the small-cut path runs
 	bool prefer_big_ = false;      // the last cut did not fit the single-CTA tail

@@ -68,7 +68,7 @@ __global__ void k_begin(DevState S, CutParams P)
 
 // begin for the device-resident batch path: the halfspace is built on the device from the dual
 // point vals[i] with the default callback's meaning (cone_polar, bslv_poly.c:30-39)
-__global__ void k_begin_dev(DevState S, const double *vals, const unsigned char *ideal, u64 i, u32 facet, u32 batch_first)
+__global__ void k_begin_dev(DevState S, const double *vals, const unsigned char *ideal, u64 i, u32 facet, u32 batch_first, u32 seq)
 {
 	if (threadIdx.x || blockIdx.x) return;
 	CutParams P;
@@ -88,6 +88,8 @@ __global__ void k_begin_dev(DevState S, const double *vals, const unsigned char 
 	P.hh = hh;
 	P.facet = facet;
 	P.batch_first = batch_first;
+	P.seq = seq;
+	P.pad = 0;
 	*S.cur = P;
 	CutCtl *c = S.ctl;
 	c->status = 0;
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(K_THREADS) k_pack_delta(DevState S, int header
 		u32 v = ((const u32 *)c)[threadIdx.x];
 		if (threadIdx.x == offsetof(CutCtl, status) / 4 && !fits) v |= ST_OVF_STAGE;
 		if (threadIdx.x == offsetof(CutCtl, stage_bytes) / 4) v = (u32)L.total;
-		((u32 *)S.stage)[threadIdx.x] = v;
+		((volatile u32 *)S.stage)[threadIdx.x] = v;       // the sequence number follows in k_publish (next launch)
 	}
 	if (header_only || !fits || (c->status & (ST_SKIP_B))) return;
 	const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
@@ -857,17 +859,24 @@ template <int NC> __device__ __forceinline__ void tail_sync()
 #define TAIL_SYNC() tail_sync<NC>()
 #define TP(k) do { if (ctid == 0) S.dbg[k] = b200_globaltimer(); } while (0)
 
+// The staged record lives in mapped pinned host memory.  Every thread that wrote payload has fenced at
+// system scope (and a barrier lies in between); here the header words are written, fenced, and only
+// then the sequence number the host is spinning on.  Called by all threads of CTA 0; its first warp works.
 __device__ __forceinline__ void tail_stage_header(const DevState &S, u32 extra_status, bool header_only)
 {
-	// stages the control block as the head of the delta record (first threads of CTA 0)
 	CutCtl *c = S.ctl;
 	const StageLayout L = stage_layout(*c, S.d);
 	const bool fits = header_only || L.total <= S.cap_stage;
-	if (threadIdx.x < sizeof(CutCtl) / 4) {
-		u32 v = ((const u32 *)c)[threadIdx.x];
-		if (threadIdx.x == offsetof(CutCtl, status) / 4) v |= extra_status | (fits ? 0u : (u32)ST_OVF_STAGE);
-		if (threadIdx.x == offsetof(CutCtl, stage_bytes) / 4) v = (u32)L.total;
-		((u32 *)S.stage)[threadIdx.x] = v;
+	if (threadIdx.x < 32) {
+		if (threadIdx.x < sizeof(CutCtl) / 4) {
+			u32 v = ((const u32 *)c)[threadIdx.x];
+			if (threadIdx.x == offsetof(CutCtl, status) / 4) v |= extra_status | (fits ? 0u : (u32)ST_OVF_STAGE);
+			if (threadIdx.x == offsetof(CutCtl, stage_bytes) / 4) v = (u32)L.total;
+			((volatile u32 *)S.stage)[threadIdx.x] = v;
+		}
+		__threadfence_system();
+		__syncwarp();
+		if (threadIdx.x == 0) *(volatile u32 *)(S.stage + B200_STAGE_SEQ) = S.cur->seq;
 	}
 }
 __device__ __forceinline__ void tail_reset_for_next_cut(const DevState &S)
@@ -915,6 +924,7 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 				const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
 				const u32 first_row = c->nrows;             // not committed yet
 				for (u64 e = ctid; e < n; e += NC * TAIL_THREADS) pack_delta_item(S, L, e, first_row);
+				__threadfence_system();                 // the record goes to host memory: order it before the header / sequence number
 			}
 			TAIL_SYNC();
 			TAIL_LOOP(p, c->n_pairs) adj_pair_fill(S, p);
@@ -1270,4 +1280,19 @@ __global__ void k6_begin(DevState S, u32 M, u32 wl, u32 mpad)
 	c->mpad = mpad;
 	c->n_local = 0;
 	c->n_surv = c->n_pairs = 0;
+}
+
+// multi-kernel path: the record was written by a whole grid (k_pack_delta); the launch boundary orders
+// it before this single store of the sequence number the host spins on
+__global__ void k_publish(DevState S, u32 seq)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	__threadfence_system();
+	*(volatile u32 *)(S.stage + B200_STAGE_SEQ) = seq;
+}
+// re-launches inside one cut (pending K4, re-run after growth) publish under a fresh number
+__global__ void k_set_seq(DevState S, u32 seq)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	S.cur->seq = seq;
 }

@@ -57,6 +57,8 @@ struct CutParams {
 	double hh;      // sum h_j^2, left to right (bslv_poly.c:668-670)
 	u32 facet;      // id of the new facet = dual slot of this halfspace
 	u32 batch_first; // primal.cnt when the host mirror was last coherent (sltn inheritance roots, bslv_poly.c:583-587)
+	u32 seq;         // sequence number the device publishes in the staged header when the record is complete
+	u32 pad;
 };
 
 // Counters shared by the kernels of one cut; the host reads it back once per cut.
@@ -91,6 +93,8 @@ struct CutCtl {
 	u32 reserved0;
 };
 #define B200_STAGE_HDR 128u   // the packed delta starts with a copy of CutCtl, padded to this size
+#define B200_STAGE_SEQ 124u   // byte offset of the 'record complete' sequence number inside the header
+
 
 struct DevState {
 	int d;
@@ -123,7 +127,8 @@ struct DevState {
 	u8 *he_flag;         // [B200_HE_CAP]
 	u64 *zmask;          // [B200_VIS_MAX * B200_MAXINC/64] shared-facet masks of ZERO vertices
 	u32 *dead_facets;    // [cap_facets]
-	unsigned char *stage; // [cap_stage] packed per-cut delta: header | coords AoS | parent | ideal | dead slots | dead facets
+	unsigned char *stage; // [cap_stage] packed per-cut delta: header | coords AoS | parent | ideal | dead slots | dead facets.
+	                      // Device alias of MAPPED PINNED HOST memory: the kernels write the record straight to the host.
 	u64 cap_stage;
 	CutCtl *ctl;
 	CutParams *cur;
