@@ -620,20 +620,25 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 		small_dirty_ = false;
 		stats_.kernel_launches++;
 	}
-	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
-	launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_, true);
-	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 	// tiny cuts run the tail in one CTA (block barriers); larger ones in an 8-CTA cluster
 	static const u32 one_cta_max = getenv("B200_TAIL1_MAX_VIS") ? (u32)atoi(getenv("B200_TAIL1_MAX_VIS")) : 96u;
+	static const u32 fuse_max_rows = getenv("B200_FUSE_MAX_ROWS") ? (u32)atoi(getenv("B200_FUSE_MAX_ROWS")) : 16384u;
 	const bool tiny = expect_vis_ <= one_cta_max && (expect_m_ <= B200_K4_SMALL / 2 || mode == 1);
+	// a polytope of a few thousand rows is classified inside the single-CTA tail: one launch per cut
+	const bool fused = tiny && hdr_.nrows <= fuse_max_rows && !dev_vals_ && nranks_ == 1;
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
+	if (!fused) launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_, true);
+	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
+	const int mode_bits = mode | (fused ? TAIL_MODE_FUSED_K1 : 0);
+	const int ho = header_only ? 1 : 0;
 	if (tiny) {
-		launch_cluster(k_tail<1>, 1, STREAM, S_, mode, header_only ? 1 : 0);
+		launch_cluster(k_tail<1>, 1, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
 	} else if (g_tail_ctas == 4) {
-		launch_cluster(k_tail<4>, 4, STREAM, S_, mode, header_only ? 1 : 0);
+		launch_cluster(k_tail<4>, 4, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
 	} else if (g_tail_ctas == 16) {
-		launch_cluster(k_tail<16>, 16, STREAM, S_, mode, header_only ? 1 : 0);
+		launch_cluster(k_tail<16>, 16, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
 	} else {
-		launch_cluster(k_tail<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, mode, header_only ? 1 : 0);
+		launch_cluster(k_tail<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
 	}
 	stats_.kernel_launches += 2;
 	if (mode == 1) launch_k4_and_tail2(header_only);

@@ -950,14 +950,37 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 // mode 0: the whole rest of the cut; mode 1: stop after building K4's bit matrix (the multi-block
 // k4_filter / k4_contain and k_tail2 follow)
 #define TAIL_SBITS 2048u      // 16 KB of shared memory for K4's bit matrix inside the tail cluster
-template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode, int header_only)
+#define TAIL_MODE_STOP_AT_K4 1    // stop after building K4's matrices: k4_filter, k4_contain, k_tail2 follow
+#define TAIL_MODE_FUSED_K1 2      // small polytope: this (single) CTA classifies the rows itself, no K1 launch
+template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode_bits, int header_only, CutParams Parg, u32 nrows_host)
 {
+	const int mode = mode_bits & TAIL_MODE_STOP_AT_K4;
 	__shared__ u32 ws[33];
 	__shared__ u32 slist[B200_VIS_MAX];
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
 	cudaGridDependencySynchronize();      // K1 (and the exchange kernels) precede this launch
 	CutCtl *c = S.ctl;
 	TP(0);
+	if (NC == 1 && (mode_bits & TAIL_MODE_FUSED_K1)) {
+		// K1 inside the tail: a polytope of a few thousand rows (the Benson-loop regime) is classified
+		// by this CTA in a few hundred cycles; one launch per cut instead of two
+		if (threadIdx.x == 0) {
+			*S.cur = Parg;
+			S.facet_cnt[Parg.facet] = 0;
+			S.facet_alive[Parg.facet] = 1;
+		}
+		for (u32 r = threadIdx.x; r < nrows_host; r += TAIL_THREADS) {
+			bool strict, zp;
+			const u8 cl = classify_row(S, Parg, r, strict, zp);
+			if (cl == CLS_DEAD || cl == CLS_PLUS) continue;
+			S.cls[r] = cl;
+			const u32 pos = atomicAdd(&c->n_list, 1u);
+			if (pos < B200_VIS_MAX) S.nplist[pos] = r;
+			if (zp) atomicAdd(&c->n_zp, 1u);
+			if (strict) { atomicAdd(&c->n_strict, 1u); atomicMin(&c->min_strict_row, r); }
+		}
+		__syncthreads();
+	}
 	// ---- P0: reset per-cut outputs, decide, sort K1's unordered list into the ascending visited list
 	const u32 n_list = c->n_list;
 	if (ctid == 0) {
