@@ -404,9 +404,10 @@ B200_HD void he_owner_fill(const DevState &S, u32 i)
 {
 	for (u32 e = S.he_off[i]; e < S.he_off[i + 1]; e++) S.he_own[e] = i;
 }
-B200_HD void he_eval(const DevState &S, u32 e)
+// half-edge e of visited entry i (row v, first half-edge off_i); the caller knows the owner
+B200_HD void he_eval_at(const DevState &S, u32 e, u32 i, u32 v, u32 off_i)
 {
-	const u32 i = S.he_own[e], v = S.vis[i], k = S.adj_pool[S.adj_off[v] + (e - S.he_off[i])];
+	const u32 k = S.adj_pool[S.adj_off[v] + (e - off_i)];
 	const bool plus = S.cls[k] == CLS_PLUS;
 	S.he_k[e] = k;
 	S.he_flag[e] = plus ? 1 : 0;
@@ -422,18 +423,40 @@ B200_HD void he_eval(const DevState &S, u32 e)
 			if (mask[w]) B200_ATOMIC_OR64(&S.zmask[(size_t)i * (B200_MAXINC / 64) + w], mask[w]);
 	}
 }
+B200_HD void he_eval(const DevState &S, u32 e)
+{
+	const u32 i = S.he_own[e];
+	he_eval_at(S, e, i, S.vis[i], S.he_off[i]);
+}
 B200_HD void he_count(const DevState &S, u32 i)
 {
 	const u32 v = S.vis[i];
 	const u8 c = S.cls[v];
 	u32 n_out = 0, inc_sz = 0, nplus = 0;
 	if (is_visited_class(c)) {
-		for (u32 e = S.he_off[i]; e < S.he_off[i + 1]; e++) {       // also each half-edge's position among the PLUS ones
-			S.he_rank[e] = nplus;
-			S.he_incpre[e] = inc_sz;
-			nplus += S.he_flag[e];
-			inc_sz += S.he_inc[e];
-		}
+		const u32 e0 = S.he_off[i], e1 = S.he_off[i + 1];
+		if (e1 - e0 <= 12) {                                        // usual degree: all loads in flight before the first store
+			u32 fl[12], ic[12];
+#pragma unroll
+			for (u32 t = 0; t < 12; t++) {
+				fl[t] = e0 + t < e1 ? S.he_flag[e0 + t] : 0;
+				ic[t] = e0 + t < e1 ? S.he_inc[e0 + t] : 0;
+			}
+#pragma unroll
+			for (u32 t = 0; t < 12; t++)
+				if (e0 + t < e1) {
+					S.he_rank[e0 + t] = nplus;
+					S.he_incpre[e0 + t] = inc_sz;
+					nplus += fl[t];
+					inc_sz += ic[t];
+				}
+		} else
+			for (u32 e = e0; e < e1; e++) {       // also each half-edge's position among the PLUS ones
+				S.he_rank[e] = nplus;
+				S.he_incpre[e] = inc_sz;
+				nplus += S.he_flag[e];
+				inc_sz += S.he_inc[e];
+			}
 		if (c == CLS_ZERO) {
 			if (S.inc_len[v] > B200_MAXINC) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
 			n_out = 1;

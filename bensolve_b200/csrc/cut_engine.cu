@@ -649,9 +649,10 @@ void CutEngine::launch_k4_and_tail2(bool header_only)
 {
 	launch_dependent(k4_filter, num_sms_ * 4, K_THREADS, STREAM, S_, k4_threshold(S_, true));
 	launch_dependent(k4_contain, num_sms_ * 4, K_THREADS, STREAM, S_);
-	if (g_tail_ctas == 4) launch_cluster(k_tail2<4>, 4, STREAM, S_, header_only ? 1 : 0);
-	else if (g_tail_ctas == 16) launch_cluster(k_tail2<16>, 16, STREAM, S_, header_only ? 1 : 0);
-	else launch_cluster(k_tail2<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, header_only ? 1 : 0);
+	const int ho = header_only ? 1 : 0;
+	if (g_tail_ctas == 4) launch_cluster(k_tail2<4>, 4, STREAM, S_, ho);
+	else if (g_tail_ctas == 16) launch_cluster(k_tail2<16>, 16, STREAM, S_, ho);
+	else launch_cluster(k_tail2<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, ho);
 	stats_.kernel_launches += 3;
 }
 

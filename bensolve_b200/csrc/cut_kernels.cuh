@@ -889,7 +889,7 @@ __device__ __forceinline__ void tail_reset_for_next_cut(const DevState &S)
 }
 
 // phases after K4: adjacency build, commit, delta record (also the body of k_tail2)
-template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32 *ws, bool header_only)
+template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32 *ws, bool header_only, bool wrote_payload)
 {
 	CutCtl *c = S.ctl;
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
@@ -916,16 +916,8 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 		}
 		TAIL_SYNC();
 		if (!(c->status & ST_SKIP_B)) {
-			// adjacency offsets are known: place the PLUS neighbours and, independently, pack the
-			// delta record (the commit below does not change what it reads)
+			// adjacency offsets are known: place the PLUS neighbours
 			TAIL_LOOP(j, c->n_new) adj_place(S, j);
-			const StageLayout L = stage_layout(*c, S.d);
-			if (!header_only && L.total <= S.cap_stage) {
-				const u64 n = (u64)c->n_new * S.d + c->n_new + c->n_vis + c->n_dead_facets;
-				const u32 first_row = c->nrows;             // not committed yet
-				for (u64 e = ctid; e < n; e += NC * TAIL_THREADS) pack_delta_item(S, L, e, first_row);
-				__threadfence_system();                 // the record goes to host memory: order it before the header / sequence number
-			}
 			TAIL_SYNC();
 			TAIL_LOOP(p, c->n_pairs) adj_pair_fill(S, p);
 			TAIL_SYNC();
@@ -939,6 +931,10 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 			}
 		}
 	}
+	// single-launch cut: the record went to host memory from this grid, every writer orders its payload before
+	// the header / sequence number (late, so that the PCIe writes have drained by now); with k_tail2 as a
+	// separate launch the grid boundary has done that already
+	if (wrote_payload) __threadfence_system();
 	TAIL_SYNC();
 	if (rank == 0) {
 		tail_stage_header(S, 0, header_only);
@@ -957,6 +953,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	const int mode = mode_bits & TAIL_MODE_STOP_AT_K4;
 	__shared__ u32 ws[33];
 	__shared__ u32 slist[B200_VIS_MAX];
+	__shared__ u32 soff[B200_VIS_MAX + 1];
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
 	cudaGridDependencySynchronize();      // K1 (and the exchange kernels) precede this launch
 	CutCtl *c = S.ctl;
@@ -1004,6 +1001,8 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 		}
 	}
 	if (n_list <= B200_VIS_MAX) {
+		// on-plane vertices (rare): clear the shared-facet masks the half-edge evaluation ORs into
+		if (n_list > c->n_strict) TAIL_LOOP(x, n_list * (B200_MAXINC / 64)) S.zmask[x] = 0;
 		// every CTA stages the list in shared memory; an element's position in the sorted order is
 		// the number of smaller elements (rows are distinct)
 		for (u32 x = threadIdx.x; x < n_list; x += TAIL_THREADS) slist[x] = S.nplist[x];
@@ -1048,42 +1047,46 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 			TAIL_SYNC();
 		}
 	}
-	// ---- P2: half-edge offsets
-	TAIL_SYNC();                      // all CTAs are past the status check above before CTA 0 may set NEED_BIG
-	if (rank == 0) {
-		u32 carry = 0;
-		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
-			u32 i = base + threadIdx.x, v = 0, tot;
-			if (i < n_vis) {
-				const u32 r = S.vis[i];
-				const u8 cl = S.cls[r];
-				v = is_visited_class(cl) ? S.adj_len[r] : 0;
-				if (cl == CLS_ZERO)                        // shared-facet mask of an on-plane vertex: only the words its list needs
-					for (u32 w = 0; w < (S.inc_len[r] + 63) / 64 && w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
-			}
-			u32 e = block_excl_scan(v, ws, tot);
-			if (i < n_vis) S.he_off[i] = carry + e;
-			carry += tot;
+	// ---- P2: half-edge offsets.  Every CTA derives them itself into shared memory (the visited list is short),
+	// so no cluster barrier separates the scan from the evaluation; CTA 0 also stores them for the later phases
+	for (u32 x = threadIdx.x; x < n_vis; x += TAIL_THREADS) slist[x] = S.vis[x];      // read back by the same thread below
+	u32 H = 0;
+	for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
+		u32 i = base + threadIdx.x, v = 0, tot;
+		if (i < n_vis) {
+			const u32 r = slist[i];
+			v = is_visited_class(S.cls[r]) ? S.adj_len[r] : 0;
 		}
-		if (threadIdx.x == 0) {
-			S.he_off[n_vis] = carry;
-			if (carry > B200_HE_CAP) c->status |= ST_NEED_BIG;
+		u32 e = block_excl_scan(v, ws, tot);
+		if (i < n_vis) {
+			soff[i] = H + e;
+			if (rank == 0) S.he_off[i] = H + e;
 		}
-		__syncthreads();
-		if (carry <= B200_HE_CAP)                          // owner of every half-edge (CTA 0 has the offsets at hand)
-			for (u32 i = threadIdx.x; i < n_vis; i += TAIL_THREADS) he_owner_fill(S, i);
+		H += tot;
 	}
-	TAIL_SYNC();
-	if (c->status & ST_NEED_BIG) {
-		if (rank == 0) tail_stage_header(S, 0, header_only);
+	if (threadIdx.x == 0) {
+		soff[n_vis] = H;
+		if (rank == 0) S.he_off[n_vis] = H;
+	}
+	__syncthreads();
+	if (H > B200_HE_CAP) {                 // every CTA sees the same total; the status word itself is left alone (others may still read it)
+		if (rank == 0) tail_stage_header(S, ST_NEED_BIG, header_only);
 		TAIL_SYNC();
 		if (ctid == 0) tail_reset_for_next_cut(S);
 		return;
 	}
-	const u32 H = S.he_off[n_vis];
 	TP(2);
-	// ---- P3: evaluate every (visited vertex, neighbour) pair
-	TAIL_LOOP(e, H) he_eval(S, e);
+	// ---- P3: evaluate every (visited vertex, neighbour) pair; the owner of a half-edge is found by bisection
+	TAIL_LOOP(e, H) {
+		u32 lo = 0, hi = n_vis;            // soff[lo] <= e < soff[hi]
+		while (hi - lo > 1) {
+			const u32 mid = (lo + hi) >> 1;
+			if (soff[mid] <= e) lo = mid;
+			else hi = mid;
+		}
+		S.he_own[e] = lo;
+		he_eval_at(S, e, lo, slist[lo], soff[lo]);
+	}
 	TAIL_SYNC();
 	TP(3);
 	// ---- P4: sizes, offsets, capacity plan by CTA 0 (nothing mutated so far except ZERO+ projections)
@@ -1144,6 +1147,18 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	TAIL_LOOP(j, M) k4_assign_columns(S, j);
 	TAIL_SYNC();
 	TP(6);
+	// ---- delta record: everything it holds is final now (new rows, parents, retired slots, dead facets).  The
+	// stores go to mapped host memory and drain over PCIe while the pair test and the adjacency build run
+	bool wrote_payload = false;
+	if (!header_only) {
+		const StageLayout L = stage_layout(*c, S.d);
+		if (L.total <= S.cap_stage) {
+			const u64 n = (u64)M * S.d + M + n_vis + c->n_dead_facets;
+			const u32 first_row = c->nrows;             // not committed yet
+			for (u64 e = ctid; e < n; e += NC * TAIL_THREADS) pack_delta_item(S, L, e, first_row);
+			wrote_payload = ctid < n;
+		}
+	}
 	// every thread derives the matrix shape itself (no barrier between plan and the stores below)
 	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 63) & ~63u;
 	const bool bits_ovf = k4_words(wl, mpad, c->n_local) > S.cap_bits;
@@ -1191,7 +1206,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	}
 	TP(9);
 	// ---- P8: adjacency, commit, delta record
-	tail_adjacency_and_pack<NC>(S, ws, header_only);
+	tail_adjacency_and_pack<NC>(S, ws, header_only, wrote_payload);
 	TP(10);
 }
 
@@ -1201,7 +1216,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail2(Dev
 	const u32 ctid = tail_rank<NC>() * TAIL_THREADS + threadIdx.x;
 	cudaGridDependencySynchronize();
 	TP(11);
-	tail_adjacency_and_pack<NC>(S, ws, header_only);
+	tail_adjacency_and_pack<NC>(S, ws, header_only, false);
 	TP(12);
 }
 
