@@ -227,6 +227,35 @@ B200_HD void rewire(const DevState &S, u32 k, u32 v, u32 nw)
 		if (S.adj_pool[off + q] == v) { S.adj_pool[off + q] = nw; return; }
 }
 
+// K4 column relabelling (see k4_assign_columns below): the first toucher of a facet in a cut allocates the
+// facet's column of the cut's bit matrix; epoch = new facet id + 1 tags the cut.
+B200_HD void k4_assign_one(const DevState &S, u32 fc, u32 epoch)
+{
+	if (B200_ATOMIC_EXCH(&S.facet_epoch[fc], epoch) != epoch) S.facet_local[fc] = B200_ATOMIC_ADD(&S.ctl->n_local, 1u);
+}
+// same for the masked entries of a short list: the exchanges are independent and go out together, the fresh
+// columns are taken with one counter update
+B200_HD void k4_assign_short(const DevState &S, const u32 fc[B200_SHORT], u32 mask, u32 epoch)
+{
+	u32 old[B200_SHORT];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (u32 t = 0; t < B200_SHORT; t++) old[t] = ((mask >> t) & 1u) ? B200_ATOMIC_EXCH(&S.facet_epoch[fc[t]], epoch) : epoch;
+	u32 fresh = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (u32 t = 0; t < B200_SHORT; t++) fresh |= (old[t] != epoch ? 1u : 0u) << t;
+	if (!fresh) return;
+	u32 col = B200_ATOMIC_ADD(&S.ctl->n_local, popc32(fresh));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (u32 t = 0; t < B200_SHORT; t++)
+		if ((fresh >> t) & 1u) S.facet_local[fc[t]] = col++;
+}
+
 // ---- K3b pieces, shared by the vertex-serial form (emit_outputs) and the half-edge-parallel form
 
 // new vertex on the edge (v MINUS, k PLUS), SURVEY A.3 / bslv_poly.c:597-627 + incidence :634-665.
@@ -236,46 +265,77 @@ B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 
 	const CutCtl *ctl = S.ctl;
 	const size_t cap = S.cap_rows;
 	const int d = S.d;
-	const u32 nw = ctl->nrows + j, f = P.facet;
+	const u32 f = P.facet;
+	// The body is a chain of dependent memory round trips if written naively, so the loads are grouped in
+	// waves and issued before the first store (stores end the compiler's freedom to hoist loads).
+	// ---- wave 1: everything addressed by v and k alone
+	const u32 nw = ctl->nrows + j, slot = ctl->slot_cnt + j;
 	const bool v_ideal = bit_test(S.ideal, v), k_ideal = bit_test(S.ideal, k);
-	const u32 rb = k_ideal ? v : k;           // base
-	const u32 rd = k_ideal ? k : v;           // direction source
+	const u32 aoff = S.adj_off[k], an = S.adj_len[k];
+	const u32 iov = S.inc_off[v], iok = S.inc_off[k], niv = S.inc_len[v], nik = S.inc_len[k];
 	const bool both = k_ideal && v_ideal, none = !k_ideal && !v_ideal;
 	double base[B200_MAXD], dir[B200_MAXD];
-	for (int t = 0; t < d; t++) {
-		base[t] = S.coord[t * cap + rb];
-		double dv = S.coord[t * cap + rd];
-		if (both) dv = B200_SUB(dv, S.coord[t * cap + v]);
-		else if (none) dv = B200_SUB(dv, S.coord[t * cap + k]);
-		dir[t] = dv;
+	for (int t0 = 0; t0 < d; t0 += 8) {            // 16 independent coordinate loads per round
+		double cv[8], ck[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int u = 0; u < 8; u++) {
+			cv[u] = t0 + u < d ? S.coord[(t0 + u) * cap + v] : 0.0;
+			ck[u] = t0 + u < d ? S.coord[(t0 + u) * cap + k] : 0.0;
+		}
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int u = 0; u < 8; u++)
+			if (t0 + u < d) {
+				base[t0 + u] = k_ideal ? cv[u] : ck[u];          // base point
+				double dv = k_ideal ? ck[u] : cv[u];              // direction source
+				if (both) dv = B200_SUB(dv, cv[u]);
+				else if (none) dv = B200_SUB(dv, ck[u]);
+				dir[t0 + u] = dv;
+			}
 	}
+	// ---- wave 2: the short lists (k's neighbours, both incidence lists)
+	const bool short_adj = an <= B200_SHORT, short_inc = niv <= B200_SHORT && nik <= B200_SHORT;
+	u32 ra[B200_SHORT], rv[B200_SHORT], rk[B200_SHORT];
+	load_short(S.adj_pool + aoff, short_adj ? an : 0, ra);
+	load_short(S.inc_pool + iov, short_inc ? niv : 0, rv);
+	load_short(S.inc_pool + iok, short_inc ? nik : 0, rk);
+	// ---- arithmetic: the reference's operation order (bslv_poly.c:597-627)
 	double hb = B200_MUL(P.h[0], base[0]), hd = B200_MUL(P.h[0], dir[0]);
 	for (int t = 1; t < d; t++) {
 		hb = B200_ADD(hb, B200_MUL(P.h[t], base[t]));
 		hd = B200_ADD(hd, B200_MUL(P.h[t], dir[t]));
 	}
 	const double mu = B200_DIV(B200_SUB(both ? 0.0 : P.alpha, hb), hd);
+	// ---- stores
 	for (int t = 0; t < d; t++) S.coord[t * cap + nw] = B200_ADD(base[t], B200_MUL(mu, dir[t]));
 	if (both) set_bit_atomic(S.ideal, nw);
 	set_bit_atomic(S.live, nw);
 	S.cls[nw] = CLS_PLUS;                     // invariant: every live row reads PLUS between cuts
-	S.row_slot[nw] = ctl->slot_cnt + j;
+	S.row_slot[nw] = slot;
 	S.new_parent[j] = B200_NONE;
 	S.root[nw] = B200_NONE;
 	S.deg[j] = 0;
 	S.new_padj_off[j] = pslot;
 	S.new_padj_len[j] = 1;
 	S.padj[pslot] = k;
-	rewire(S, k, v, nw);
-	// incidence {f} u (inc(k) n inc(v)), sorted; f is the largest facet id so far
-	const u32 *iv = S.inc_pool + S.inc_off[v], *ik = S.inc_pool + S.inc_off[k];
-	const u32 niv = S.inc_len[v], nik = S.inc_len[k];
+	// neighbour k of the dying row v now neighbours nw (bslv_poly.c:628-632)
+	if (short_adj) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 q = 0; q < B200_SHORT; q++)
+			if (q < an && ra[q] == v) { S.adj_pool[aoff + q] = nw; break; }
+	} else
+		rewire(S, k, v, nw);
+	// incidence {f} u (inc(k) n inc(v)), sorted; f is the largest facet id so far.  Each facet the new row
+	// lies on also gets its column of this cut's K4 bit matrix here (first toucher allocates it).
 	u32 w = ipos;
-	if (niv <= B200_SHORT && nik <= B200_SHORT) {
-		u32 rv[B200_SHORT], rk[B200_SHORT];
-		load_short(iv, niv, rv);
-		load_short(ik, nik, rk);
+	if (short_inc) {
 		const u32 m = common_mask_short(rv, niv, rk);
+		k4_assign_short(S, rv, m, f + 1);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -285,12 +345,14 @@ B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 
 				B200_ATOMIC_ADD(&S.facet_cnt[rv[t]], 1u);
 			}
 	} else {
+		const u32 *iv = S.inc_pool + iov, *ik = S.inc_pool + iok;
 		u32 a = 0, b = 0;
 		while (a < niv && b < nik) {
 			const u32 x = iv[a], y = ik[b];
 			if (x == y) {
 				S.inc_pool[w++] = x;
 				B200_ATOMIC_ADD(&S.facet_cnt[x], 1u);
+				k4_assign_one(S, x, f + 1);
 			}
 			a += (x <= y);
 			b += (y <= x);
@@ -347,6 +409,7 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 		if ((mask[a >> 6] >> (a & 63)) & 1) {
 			S.inc_pool[w++] = iv[a];
 			B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
+			k4_assign_one(S, iv[a], f + 1);
 		}
 	S.inc_pool[w++] = f;                      // facet_cnt[f] is set once to n_new by the plan stage
 	S.inc_off[nw] = ipos;
@@ -356,10 +419,21 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 // retire visited row v (bslv_poly.c:568, 679-688, 697-705): its facets lose one vertex
 B200_HD void retire_row(const DevState &S, u32 v, u32 i)
 {
-	const u32 *iv = S.inc_pool + S.inc_off[v];
+	const u32 off = S.inc_off[v], n = S.inc_len[v], slot = S.row_slot[v];
+	if (n <= B200_SHORT) {
+		u32 r[B200_SHORT];
+		load_short(S.inc_pool + off, n, r);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 a = 0; a < B200_SHORT; a++)
+			if (a < n) B200_ATOMIC_SUB(&S.facet_cnt[r[a]], 1u);
+	} else {
+		const u32 *iv = S.inc_pool + off;
+		for (u32 a = 0; a < n; a++) B200_ATOMIC_SUB(&S.facet_cnt[iv[a]], 1u);
+	}
 	clr_bit_atomic(S.live, v);
-	for (u32 a = 0, n = S.inc_len[v]; a < n; a++) B200_ATOMIC_SUB(&S.facet_cnt[iv[a]], 1u);
-	S.dead_slots[i] = S.row_slot[v];
+	S.dead_slots[i] = slot;
 }
 
 // K3b + K5 for visited entry i, vertex-serial form (multi-kernel path and host test double)
@@ -407,21 +481,80 @@ B200_HD void he_owner_fill(const DevState &S, u32 i)
 // half-edge e of visited entry i (row v, first half-edge off_i); the caller knows the owner
 B200_HD void he_eval_at(const DevState &S, u32 e, u32 i, u32 v, u32 off_i)
 {
-	const u32 k = S.adj_pool[S.adj_off[v] + (e - off_i)];
-	const bool plus = S.cls[k] == CLS_PLUS;
+	// loads addressed by v alone go out together with the adjacency lookup, those addressed by k follow in one wave
+	const u32 aoff = S.adj_off[v];
+	const u8 cv = S.cls[v];
+	const u32 iov = S.inc_off[v], niv = S.inc_len[v];
+	const u32 k = S.adj_pool[aoff + (e - off_i)];
+	const u8 ck = S.cls[k];
+	const u32 iok = S.inc_off[k], nik = S.inc_len[k];
+	const bool plus = ck == CLS_PLUS;
+	u32 inc = 0;
+	if (plus) {
+		if (cv == CLS_MINUS) {
+			inc = 1 + isect_count(S.inc_pool + iov, niv, S.inc_pool + iok, nik);
+		} else {
+			u64 mask[B200_MAXINC / 64] = {0};
+			shared_facet_mask(S, v, k, mask);
+			const int nw = (int)((niv + 63) / 64) < B200_MAXINC / 64 ? (int)((niv + 63) / 64) : B200_MAXINC / 64;
+			for (int w = 0; w < nw; w++)
+				if (mask[w]) B200_ATOMIC_OR64(&S.zmask[(size_t)i * (B200_MAXINC / 64) + w], mask[w]);
+		}
+	}
 	S.he_k[e] = k;
 	S.he_flag[e] = plus ? 1 : 0;
-	S.he_inc[e] = 0;
-	if (!plus) return;
-	if (S.cls[v] == CLS_MINUS) {
-		S.he_inc[e] = 1 + isect_count(S.inc_pool + S.inc_off[v], S.inc_len[v], S.inc_pool + S.inc_off[k], S.inc_len[k]);
-	} else {
-		u64 mask[B200_MAXINC / 64] = {0};
-		shared_facet_mask(S, v, k, mask);
-		const int nw = (int)((S.inc_len[v] + 63) / 64) < B200_MAXINC / 64 ? (int)((S.inc_len[v] + 63) / 64) : B200_MAXINC / 64;
-		for (int w = 0; w < nw; w++)
-			if (mask[w]) B200_ATOMIC_OR64(&S.zmask[(size_t)i * (B200_MAXINC / 64) + w], mask[w]);
-	}
+	S.he_inc[e] = inc;
+}
+// sizes of what visited entry i (row v, class c, half-edges [e0, e1)) produces: out[0] new rows, out[1]
+// incidence entries, out[2] PLUS neighbours; also each half-edge's position among the PLUS ones.
+// Returns false when an on-plane vertex lies on more facets than the mask holds.
+B200_HD bool he_count_core(const DevState &S, u32 i, u32 v, u8 c, u32 e0, u32 e1, u32 out[3])
+{
+	u32 n_out = 0, inc_sz = 0, nplus = 0;
+	bool ok = true;
+	// a row that is not cut has no half-edges (e0 == e1), so the loop needs no class test and its loads do not
+	// wait for the class
+	if (e1 - e0 <= 12) {                                        // usual degree: all loads in flight before the first store
+		u32 fl[12], ic[12];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 t = 0; t < 12; t++) {
+			fl[t] = e0 + t < e1 ? S.he_flag[e0 + t] : 0;
+			ic[t] = e0 + t < e1 ? S.he_inc[e0 + t] : 0;
+		}
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 t = 0; t < 12; t++)
+			if (e0 + t < e1) {
+				S.he_rank[e0 + t] = nplus;
+				S.he_incpre[e0 + t] = inc_sz;
+				nplus += fl[t];
+				inc_sz += ic[t];
+			}
+	} else
+		for (u32 e = e0; e < e1; e++) {
+			S.he_rank[e] = nplus;
+			S.he_incpre[e] = inc_sz;
+			nplus += S.he_flag[e];
+			inc_sz += S.he_inc[e];
+		}
+	if (is_visited_class(c)) {
+		if (c == CLS_ZERO) {
+			if (S.inc_len[v] > B200_MAXINC) ok = false;
+			n_out = 1;
+			inc_sz = 1;
+			const int nw = (int)((S.inc_len[v] + 63) / 64) < B200_MAXINC / 64 ? (int)((S.inc_len[v] + 63) / 64) : B200_MAXINC / 64;
+			for (int w = 0; w < nw; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
+		} else
+			n_out = nplus;
+	} else
+		inc_sz = nplus = 0;
+	out[0] = n_out;
+	out[1] = inc_sz;
+	out[2] = nplus;
+	return ok;
 }
 B200_HD void he_eval(const DevState &S, u32 e)
 {
@@ -431,44 +564,11 @@ B200_HD void he_eval(const DevState &S, u32 e)
 B200_HD void he_count(const DevState &S, u32 i)
 {
 	const u32 v = S.vis[i];
-	const u8 c = S.cls[v];
-	u32 n_out = 0, inc_sz = 0, nplus = 0;
-	if (is_visited_class(c)) {
-		const u32 e0 = S.he_off[i], e1 = S.he_off[i + 1];
-		if (e1 - e0 <= 12) {                                        // usual degree: all loads in flight before the first store
-			u32 fl[12], ic[12];
-#pragma unroll
-			for (u32 t = 0; t < 12; t++) {
-				fl[t] = e0 + t < e1 ? S.he_flag[e0 + t] : 0;
-				ic[t] = e0 + t < e1 ? S.he_inc[e0 + t] : 0;
-			}
-#pragma unroll
-			for (u32 t = 0; t < 12; t++)
-				if (e0 + t < e1) {
-					S.he_rank[e0 + t] = nplus;
-					S.he_incpre[e0 + t] = inc_sz;
-					nplus += fl[t];
-					inc_sz += ic[t];
-				}
-		} else
-			for (u32 e = e0; e < e1; e++) {       // also each half-edge's position among the PLUS ones
-				S.he_rank[e] = nplus;
-				S.he_incpre[e] = inc_sz;
-				nplus += S.he_flag[e];
-				inc_sz += S.he_inc[e];
-			}
-		if (c == CLS_ZERO) {
-			if (S.inc_len[v] > B200_MAXINC) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
-			n_out = 1;
-			inc_sz = 1;
-			const int nw = (int)((S.inc_len[v] + 63) / 64) < B200_MAXINC / 64 ? (int)((S.inc_len[v] + 63) / 64) : B200_MAXINC / 64;
-			for (int w = 0; w < nw; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
-		} else
-			n_out = nplus;
-	}
-	S.cnt3[3 * (size_t)i + 0] = n_out;
-	S.cnt3[3 * (size_t)i + 1] = inc_sz;
-	S.cnt3[3 * (size_t)i + 2] = nplus;
+	u32 out[3];
+	if (!he_count_core(S, i, v, S.cls[v], S.he_off[i], S.he_off[i + 1], out)) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
+	S.cnt3[3 * (size_t)i + 0] = out[0];
+	S.cnt3[3 * (size_t)i + 1] = out[1];
+	S.cnt3[3 * (size_t)i + 2] = out[2];
 }
 B200_HD void he_emit(const DevState &S, const CutParams &P, u32 e)
 {
@@ -501,10 +601,26 @@ B200_HD void reset_class(const DevState &S, u32 i) { S.cls[S.vis[i]] = CLS_PLUS;
 // variant, bslv_poly.c:686-687/:705, leaves order-dependent ghosts -- SURVEY section 0)
 B200_HD void collect_dead_facets(const DevState &S, u32 i)
 {
-	u32 v = S.vis[i];
-	if (S.dead_slots[i] == B200_NONE) { S.cls[v] = CLS_PLUS; return; }   // a ZERO+ row nobody reached stays as it is
-	const u32 *iv = S.inc_pool + S.inc_off[v];
-	for (u32 a = 0, n = S.inc_len[v]; a < n; a++) {
+	const u32 v = S.vis[i];
+	const u32 ds = S.dead_slots[i], off = S.inc_off[v], n = S.inc_len[v];
+	if (ds == B200_NONE) { S.cls[v] = CLS_PLUS; return; }   // a ZERO+ row nobody reached stays as it is
+	if (n <= B200_SHORT) {
+		u32 r[B200_SHORT], cnt[B200_SHORT];
+		load_short(S.inc_pool + off, n, r);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 a = 0; a < B200_SHORT; a++) cnt[a] = a < n ? S.facet_cnt[r[a]] : 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 a = 0; a < B200_SHORT; a++)
+			if (cnt[a] == 0 && B200_ATOMIC_EXCH(&S.facet_alive[r[a]], 0u) == 1u)
+				S.dead_facets[B200_ATOMIC_ADD(&S.ctl->n_dead_facets, 1u)] = r[a];
+		return;
+	}
+	const u32 *iv = S.inc_pool + off;
+	for (u32 a = 0; a < n; a++) {
 		u32 fc = iv[a];
 		if (S.facet_cnt[fc] == 0 && B200_ATOMIC_EXCH(&S.facet_alive[fc], 0u) == 1u)
 			S.dead_facets[B200_ATOMIC_ADD(&S.ctl->n_dead_facets, 1u)] = fc;
@@ -518,12 +634,26 @@ B200_HD void collect_dead_facets(const DevState &S, u32 i)
 // column relabelling: first toucher of a facet in this cut allocates its column
 B200_HD void k4_assign_columns(const DevState &S, u32 j)
 {
+	// (emit_edge_vertex / emit_copy_row have done this for the rows they created: every exchange below then
+	// finds the tag in place; the stage remains for paths that build rows differently)
 	const u32 r = S.ctl->nrows + j, f = S.cur->facet, epoch = f + 1;
-	const u32 *l = S.inc_pool + S.inc_off[r];
-	for (u32 q = 0, n = S.inc_len[r]; q < n; q++) {
+	const u32 off = S.inc_off[r], n = S.inc_len[r];
+	if (n <= B200_SHORT) {
+		u32 l[B200_SHORT];
+		load_short(S.inc_pool + off, n, l);
+		u32 m = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 q = 0; q < B200_SHORT; q++) m |= (q < n && l[q] != f ? 1u : 0u) << q;
+		k4_assign_short(S, l, m, epoch);
+		return;
+	}
+	const u32 *l = S.inc_pool + off;
+	for (u32 q = 0; q < n; q++) {
 		const u32 fc = l[q];
 		if (fc == f) continue;
-		if (B200_ATOMIC_EXCH(&S.facet_epoch[fc], epoch) != epoch) S.facet_local[fc] = B200_ATOMIC_ADD(&S.ctl->n_local, 1u);
+		k4_assign_one(S, fc, epoch);
 	}
 }
 // K4 keeps two packed forms of the incidence of the M new rows over the L facets they touch:
@@ -540,19 +670,54 @@ B200_HD void k4_plan(const DevState &S)
 	c->mpad = (c->n_new + 63) & ~63u;
 	if (k4_words(c->wl, c->mpad, c->n_local) > S.cap_bits) c->status |= ST_OVF_BITS;
 }
-B200_HD void k4_build_row(const DevState &S, u32 j)
+B200_HD void k4_build_row_at(const DevState &S, u32 j, u32 nrows, u32 f, u32 wl, u32 mpad)
 {
-	const CutCtl *c = S.ctl;
-	const u32 r = c->nrows + j, f = S.cur->facet, wl = c->wl, mpad = c->mpad;
+	const u32 r = nrows + j;
+	const u32 off = S.inc_off[r], n = S.inc_len[r];
+	u64 *tb = k4_tbits(S, wl, mpad);
+	if (n <= B200_SHORT && wl <= 4) {
+		// short row, narrow matrix (the usual case): list and column numbers by independent loads, the row's
+		// words assembled in registers and stored once
+		u32 l[B200_SHORT], col[B200_SHORT];
+		load_short(S.inc_pool + off, n, l);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 q = 0; q < B200_SHORT; q++) col[q] = (q < n && l[q] != f) ? S.facet_local[l[q]] : B200_NONE;
+		u64 acc[4] = {0, 0, 0, 0};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 q = 0; q < B200_SHORT; q++)
+			if (col[q] != B200_NONE) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+				for (u32 w = 0; w < 4; w++)
+					if ((col[q] >> 6) == w) acc[w] |= (u64)1 << (col[q] & 63);
+				B200_ATOMIC_OR64(&tb[(size_t)col[q] * (mpad / 64) + (j >> 6)], (u64)1 << (j & 63));   // zeroed by k4_zero_cols
+			}
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 w = 0; w < 4; w++)
+			if (w < wl) S.bits[(size_t)w * mpad + j] = acc[w];
+		return;
+	}
 	for (u32 w = 0; w < wl; w++) S.bits[(size_t)w * mpad + j] = 0;
-	const u32 *l = S.inc_pool + S.inc_off[r];
-	for (u32 q = 0, n = S.inc_len[r]; q < n; q++) {
+	const u32 *l = S.inc_pool + off;
+	for (u32 q = 0; q < n; q++) {
 		const u32 fc = l[q];
 		if (fc == f) continue;
 		const u32 col = S.facet_local[fc];
 		S.bits[(size_t)(col >> 6) * mpad + j] |= (u64)1 << (col & 63);
-		B200_ATOMIC_OR64(&k4_tbits(S, wl, mpad)[(size_t)col * (mpad / 64) + (j >> 6)], (u64)1 << (j & 63));   // zeroed by k4_zero_cols
+		B200_ATOMIC_OR64(&tb[(size_t)col * (mpad / 64) + (j >> 6)], (u64)1 << (j & 63));   // zeroed by k4_zero_cols
 	}
+}
+B200_HD void k4_build_row(const DevState &S, u32 j)
+{
+	const CutCtl *c = S.ctl;
+	k4_build_row_at(S, j, c->nrows, S.cur->facet, c->wl, c->mpad);
 }
 // the column matrix is filled with atomics, so it is cleared first (one barrier / launch earlier)
 B200_HD void k4_zero_cols(const DevState &S, u64 x)

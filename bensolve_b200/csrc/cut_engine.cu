@@ -276,6 +276,9 @@ CutEngine::~CutEngine()
 		fprintf(stderr, "[b200] tail phase ns:");
 		for (int k = 0; k < 16; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, " (per cut, %llu cuts)\n", (unsigned long long)stats_.cuts);
+		fprintf(stderr, "[b200] sub-phases (thread 0 of CTA 0):");
+		for (int k = 0; k < 8; k++) fprintf(stderr, " s%d=%.1fus", k, stats_.sub_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
+		fprintf(stderr, "\n");
 		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions);
 	}
 #ifndef B200_EMULATE
@@ -476,8 +479,9 @@ void CutEngine::upload_initial(u32 n, const double *coords_aos, const u8 *ideal,
 #ifndef B200_EMULATE
 template <int D, int IT> static void launch_classify_lists_it(const DevState &S, const CutParams &P, const double *dv, const unsigned char *di, u64 vi, u32 nrows, u32 tlo, u32 thi, int grid, cudaStream_t st)
 {
-	if (dv) k_classify_lists<D, true, IT><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi, nrows, tlo, thi);
-	else k_classify_lists<D, false, IT><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0, nrows, tlo, thi);
+	const u32 nr = nrows;
+	if (dv) k_classify_lists<D, true, IT><<<grid, K_THREADS, 0, st>>>(S, P, dv, di, vi, nr, tlo, thi);
+	else k_classify_lists<D, false, IT><<<grid, K_THREADS, 0, st>>>(S, P, nullptr, nullptr, 0, nr, tlo, thi);
 }
 // grid: one block per group of IT*512 rows, capped at the number of co-resident blocks (persistent
 // grid-stride loop beyond that), so the last wave is never a partial one
@@ -1019,8 +1023,11 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[2], (cudaEvent_t)ev_[3]));
 		stats_.cut_ms += ms;
 		{
-			u64 tp[16] = {0};
+			u64 tp[24] = {0};
 			d2h(tp, S_.dbg, sizeof tp);
+			if (tp[16] > tp[3] && tp[4] >= tp[16]) { stats_.sub_ns[0] += tp[16] - tp[3]; stats_.sub_ns[1] += tp[4] - tp[16]; }
+			if (tp[17] >= tp[4] && tp[18] >= tp[17] && tp[5] >= tp[18]) { stats_.sub_ns[2] += tp[17] - tp[4]; stats_.sub_ns[3] += tp[18] - tp[17]; stats_.sub_ns[4] += tp[5] - tp[18]; }
+			if (tp[19] >= tp[5] && tp[6] >= tp[19]) { stats_.sub_ns[5] += tp[19] - tp[5]; stats_.sub_ns[6] += tp[6] - tp[19]; }
 			for (int k = 0; k < 12; k++) if (tp[k] >= tp[0] && tp[k + 1] > tp[k] && k != 10) stats_.phase_ns[k] += tp[k + 1] - tp[k];
 			if (tp[11] >= tp[0] && tp[7] >= tp[0] && tp[11] > tp[7] && tp[9] < tp[0]) {
 				stats_.phase_ns[12] += tp[11] - tp[7];   // k4_filter + k4_contain + launch gaps

@@ -1089,62 +1089,75 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	}
 	TAIL_SYNC();
 	TP(3);
-	// ---- P4: sizes, offsets, capacity plan by CTA 0 (nothing mutated so far except ZERO+ projections)
-	if (rank == 0) {
-		u32 nm = 0, nz = 0;
-		for (u32 i = threadIdx.x; i < n_vis; i += TAIL_THREADS) {
-			he_count(S, i);
-			const u8 cl = S.cls[S.vis[i]];
-			nm += (cl == CLS_MINUS);
-			nz += (cl == CLS_ZERO);
-		}
-		nm = __reduce_add_sync(0xffffffffu, nm);
-		nz = __reduce_add_sync(0xffffffffu, nz);
-		if ((threadIdx.x & 31) == 0) {               // one atomic per warp instead of one per visited vertex
-			if (nm) atomicAdd(&c->n_minus, nm);
-			if (nz) atomicAdd(&c->n_zero, nz);
-		}
-		__syncthreads();
-		u32 carry[3] = {0, 0, 0};
+	// ---- P4: sizes, offsets, capacity plan.  Every CTA derives them itself (same inputs, same values; the counts
+	// go from registers straight into the scans), so no cluster barrier separates the plan from the emission;
+	// CTA 0 alone updates the control block
+	{
+		u32 nm = 0, nz = 0, carry[3] = {0, 0, 0};
+		bool bad = false;
 		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
-			u32 i = base + threadIdx.x;
+			const u32 i = base + threadIdx.x;
+			u32 cnt[3] = {0, 0, 0};
+			if (i < n_vis) {
+				const u32 v = slist[i];
+				const u8 cl = S.cls[v];
+				bad |= !he_count_core(S, i, v, cl, soff[i], soff[i + 1], cnt);
+				nm += (cl == CLS_MINUS);
+				nz += (cl == CLS_ZERO);
+			}
 #pragma unroll
 			for (int k = 0; k < 3; k++) {
-				u32 v = i < n_vis ? S.cnt3[3 * (size_t)i + k] : 0, tot;
-				u32 e = block_excl_scan(v, ws, tot);
-				if (i < n_vis) S.base3[3 * (size_t)i + k] = carry[k] + e;
+				u32 tot;
+				const u32 e = block_excl_scan(cnt[k], ws, tot);
+				if (i < n_vis) {
+					S.cnt3[3 * (size_t)i + k] = cnt[k];
+					S.base3[3 * (size_t)i + k] = carry[k] + e;
+				}
 				carry[k] += tot;
 			}
 		}
-		if (threadIdx.x == 0) {
-			c->n_new = carry[0];
-			c->inc_new = carry[1];
-			c->padj_new = carry[2];
-			S.facet_cnt[S.cur->facet] = carry[0];      // every new row lies on the new facet
-			u32 st = 0;
-			if ((u64)c->nrows + carry[0] > S.cap_rows) st |= ST_OVF_ROWS;
-			if ((u64)c->inc_used + carry[1] > S.cap_inc) st |= ST_OVF_INC;
-			if (carry[2] > S.cap_padj) st |= ST_OVF_PADJ;
-			c->status |= st;
+		TP(16);
+		u32 st = 0;
+		if ((u64)c->nrows + carry[0] > S.cap_rows) st |= ST_OVF_ROWS;
+		if ((u64)c->inc_used + carry[1] > S.cap_inc) st |= ST_OVF_INC;
+		if (carry[2] > S.cap_padj) st |= ST_OVF_PADJ;
+		if (rank == 0) {
+			nm = __reduce_add_sync(0xffffffffu, nm);
+			nz = __reduce_add_sync(0xffffffffu, nz);
+			if ((threadIdx.x & 31) == 0) {               // one atomic per warp instead of one per visited vertex
+				if (nm) atomicAdd(&c->n_minus, nm);
+				if (nz) atomicAdd(&c->n_zero, nz);
+			}
+			if (bad) atomicOr(&c->status, (u32)ST_ERR_DEGENERATE);
+			if (threadIdx.x == 0) {
+				c->n_new = carry[0];
+				c->inc_new = carry[1];
+				c->padj_new = carry[2];
+				S.facet_cnt[S.cur->facet] = carry[0];      // every new row lies on the new facet
+				if (st) atomicOr(&c->status, st);
+			}
 		}
-	}
-	TAIL_SYNC();
-	if (c->status & ST_SKIP_A) {
-		if (rank == 0) tail_stage_header(S, 0, header_only);
-		TAIL_SYNC();
-		if (ctid == 0) tail_reset_for_next_cut(S);
-		return;
+		// block-wide (and, the inputs being the same, cluster-wide) agreement on whether the cut can proceed;
+		// the barrier also orders this CTA's base3 / he_rank stores before its own reads below
+		if (__syncthreads_or(st != 0 || bad)) {
+			if (rank == 0) tail_stage_header(S, 0, header_only);
+			TAIL_SYNC();
+			if (ctid == 0) tail_reset_for_next_cut(S);
+			return;
+		}
 	}
 	TP(4);
 	// ---- P5: new rows + rewiring (per half-edge) and copies + retirement (per vertex): independent
 	TAIL_LOOP(e, H) he_emit(S, P, e);
+	TP(17);
 	TAIL_LOOP(i, n_vis) he_finish_vertex(S, P, i);
+	TP(18);
 	TAIL_SYNC();
 	TP(5);
 	// ---- P6: dead facets (needs the final facet counts) and K4's column relabelling: independent
 	const u32 M = c->n_new;
-	TAIL_LOOP(i, n_vis) collect_dead_facets(S, i);
-	TAIL_LOOP(j, M) k4_assign_columns(S, j);
+	TAIL_LOOP(i, n_vis) collect_dead_facets(S, i);      // (K4's columns were assigned as the rows were emitted)
+	TP(19);
 	TAIL_SYNC();
 	TP(6);
 	// ---- delta record: everything it holds is final now (new rows, parents, retired slots, dead facets).  The
@@ -1167,17 +1180,9 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 		u64 *tb = k4_tbits(S, wl, mpad);
 		for (u64 x = ctid; x < (u64)c->n_local * (mpad / 64); x += NC * TAIL_THREADS) tb[x] = 0;
 		TAIL_SYNC();
-		TAIL_LOOP(j, M) {
-			for (u32 w = 0; w < wl; w++) S.bits[(size_t)w * mpad + j] = 0;
-			const u32 r = c->nrows + j, f = P.facet;
-			const u32 *l = S.inc_pool + S.inc_off[r];
-			for (u32 q = 0, n = S.inc_len[r]; q < n; q++) {
-				const u32 fc = l[q];
-				if (fc == f) continue;
-				const u32 col = S.facet_local[fc];
-				S.bits[(size_t)(col >> 6) * mpad + j] |= (u64)1 << (col & 63);
-				atomicOr((unsigned long long *)&tb[(size_t)col * (mpad / 64) + (j >> 6)], (unsigned long long)1 << (j & 63));
-			}
+		{
+			const u32 nrows = c->nrows, f = P.facet;
+			TAIL_LOOP(j, M) k4_build_row_at(S, j, nrows, f, wl, mpad);
 		}
 		TAIL_SYNC();
 		TP(7);
