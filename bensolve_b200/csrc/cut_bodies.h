@@ -260,19 +260,19 @@ B200_HD void k4_assign_short(const DevState &S, const u32 fc[B200_SHORT], u32 ma
 
 // new vertex on the edge (v MINUS, k PLUS), SURVEY A.3 / bslv_poly.c:597-627 + incidence :634-665.
 // j = index among this cut's new rows, ipos = where its incidence list goes, pslot = its padj slot.
-B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 k, u32 j, u32 ipos, u32 pslot)
+// The two halves below are independent of each other (geometry + adjacency / incidence + facet counts), so the
+// tail kernels give them to different warps; the bodies are chains of dependent memory round trips if written
+// naively, so in each the loads are grouped in waves and issued before the first store (stores end the compiler's
+// freedom to hoist loads).
+B200_HD void emit_edge_geom(const DevState &S, const CutParams &P, u32 v, u32 k, u32 j, u32 pslot)
 {
 	const CutCtl *ctl = S.ctl;
 	const size_t cap = S.cap_rows;
 	const int d = S.d;
-	const u32 f = P.facet;
-	// The body is a chain of dependent memory round trips if written naively, so the loads are grouped in
-	// waves and issued before the first store (stores end the compiler's freedom to hoist loads).
 	// ---- wave 1: everything addressed by v and k alone
 	const u32 nw = ctl->nrows + j, slot = ctl->slot_cnt + j;
 	const bool v_ideal = bit_test(S.ideal, v), k_ideal = bit_test(S.ideal, k);
 	const u32 aoff = S.adj_off[k], an = S.adj_len[k];
-	const u32 iov = S.inc_off[v], iok = S.inc_off[k], niv = S.inc_len[v], nik = S.inc_len[k];
 	const bool both = k_ideal && v_ideal, none = !k_ideal && !v_ideal;
 	double base[B200_MAXD], dir[B200_MAXD];
 	for (int t0 = 0; t0 < d; t0 += 8) {            // 16 independent coordinate loads per round
@@ -296,12 +296,10 @@ B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 
 				dir[t0 + u] = dv;
 			}
 	}
-	// ---- wave 2: the short lists (k's neighbours, both incidence lists)
-	const bool short_adj = an <= B200_SHORT, short_inc = niv <= B200_SHORT && nik <= B200_SHORT;
-	u32 ra[B200_SHORT], rv[B200_SHORT], rk[B200_SHORT];
+	// ---- wave 2: k's neighbours
+	const bool short_adj = an <= B200_SHORT;
+	u32 ra[B200_SHORT];
 	load_short(S.adj_pool + aoff, short_adj ? an : 0, ra);
-	load_short(S.inc_pool + iov, short_inc ? niv : 0, rv);
-	load_short(S.inc_pool + iok, short_inc ? nik : 0, rk);
 	// ---- arithmetic: the reference's operation order (bslv_poly.c:597-627)
 	double hb = B200_MUL(P.h[0], base[0]), hd = B200_MUL(P.h[0], dir[0]);
 	for (int t = 1; t < d; t++) {
@@ -330,8 +328,17 @@ B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 
 			if (q < an && ra[q] == v) { S.adj_pool[aoff + q] = nw; break; }
 	} else
 		rewire(S, k, v, nw);
-	// incidence {f} u (inc(k) n inc(v)), sorted; f is the largest facet id so far.  Each facet the new row
-	// lies on also gets its column of this cut's K4 bit matrix here (first toucher allocates it).
+}
+// incidence {f} u (inc(k) n inc(v)), sorted; f is the largest facet id so far.  Each facet the new row lies on
+// also gets its column of this cut's K4 bit matrix here (first toucher allocates it).
+B200_HD void emit_edge_inc(const DevState &S, const CutParams &P, u32 v, u32 k, u32 j, u32 ipos)
+{
+	const u32 f = P.facet, nw = S.ctl->nrows + j;
+	const u32 iov = S.inc_off[v], iok = S.inc_off[k], niv = S.inc_len[v], nik = S.inc_len[k];
+	const bool short_inc = niv <= B200_SHORT && nik <= B200_SHORT;
+	u32 rv[B200_SHORT], rk[B200_SHORT];
+	load_short(S.inc_pool + iov, short_inc ? niv : 0, rv);
+	load_short(S.inc_pool + iok, short_inc ? nik : 0, rk);
 	u32 w = ipos;
 	if (short_inc) {
 		const u32 m = common_mask_short(rv, niv, rk);
@@ -361,6 +368,11 @@ B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 
 	S.inc_pool[w++] = f;                      // facet_cnt[f] is set once to n_new by the plan stage
 	S.inc_off[nw] = ipos;
 	S.inc_len[nw] = w - ipos;
+}
+B200_HD void emit_edge_vertex(const DevState &S, const CutParams &P, u32 v, u32 k, u32 j, u32 ipos, u32 pslot)
+{
+	emit_edge_geom(S, P, v, k, j, pslot);
+	emit_edge_inc(S, P, v, k, j, ipos);
 }
 
 // which elements of inc(v) also lie in inc(k): bit a of mask <=> iv[a] in inc(k)   (bslv_poly.c:634-652)
@@ -570,18 +582,22 @@ B200_HD void he_count(const DevState &S, u32 i)
 	S.cnt3[3 * (size_t)i + 1] = out[1];
 	S.cnt3[3 * (size_t)i + 2] = out[2];
 }
-B200_HD void he_emit(const DevState &S, const CutParams &P, u32 e)
+// part 0: geometry, bookkeeping and rewiring of the new row; part 1: its incidence list; 2: both
+B200_HD void he_emit_part(const DevState &S, const CutParams &P, u32 e, int part)
 {
-	if (!S.he_flag[e]) return;
-	const u32 i = S.he_own[e], k = S.he_k[e], rank = S.he_rank[e], incpre = S.he_incpre[e], v = S.vis[i];
+	const u32 flag = S.he_flag[e], i = S.he_own[e], k = S.he_k[e], rank = S.he_rank[e], incpre = S.he_incpre[e];
+	if (!flag) return;
+	const u32 v = S.vis[i];
 	const u32 jrow = S.base3[3 * (size_t)i + 0], ibase = S.ctl->inc_used + S.base3[3 * (size_t)i + 1], ppos = S.base3[3 * (size_t)i + 2];
-	if (S.cls[v] == CLS_MINUS)
-		emit_edge_vertex(S, P, v, k, jrow + rank, ibase + incpre, ppos + rank);
-	else {
+	if (S.cls[v] == CLS_MINUS) {
+		if (part != 1) emit_edge_geom(S, P, v, k, jrow + rank, ppos + rank);
+		if (part != 0) emit_edge_inc(S, P, v, k, jrow + rank, ibase + incpre);
+	} else if (part != 1) {
 		S.padj[ppos + rank] = k;
 		rewire(S, k, v, S.ctl->nrows + jrow);
 	}
 }
+B200_HD void he_emit(const DevState &S, const CutParams &P, u32 e) { he_emit_part(S, P, e, 2); }
 B200_HD void he_finish_vertex(const DevState &S, const CutParams &P, u32 i)
 {
 	const u32 v = S.vis[i];

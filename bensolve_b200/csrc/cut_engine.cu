@@ -48,7 +48,7 @@ static inline double now_us() { return std::chrono::duration<double, std::micro>
 
 static int g_device = -1;
 static int g_pdl = 1;            // programmatic dependent launch between the kernels of one cut (env B200_PDL=0 disables)
-static int g_tail_ctas = 8;      // cluster size of the tail kernels (env B200_TAIL_CTAS = 4, 8 or 16)
+static int g_tail_ctas = 16;     // cluster size of the tail kernels (env B200_TAIL_CTAS = 4, 8 or 16; 16 falls back to 8 if the device cannot host it)
 static int g_k1_grid = 0;        // K1 grid policy (env B200_K1_GRID): 0 balanced rounds, 1 one block per group, 2 capped at residency
 static int g_k1_it = 1;     // tile iterations whose loads a K1 thread keeps in flight (env B200_K1_IT = 1, 2 or 4)
 int b200_num_devices()
@@ -222,8 +222,23 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	if (const char *e = getenv("B200_TAIL_CTAS")) g_tail_ctas = atoi(e);
 	if (const char *e = getenv("B200_PDL")) g_pdl = atoi(e);
 	if (g_tail_ctas == 16) {
-		CK(cudaFuncSetAttribute(k_tail<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-		CK(cudaFuncSetAttribute(k_tail2<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+		// 16 CTAs per cluster is the non-portable maximum: opt in, and fall back to the portable 8 when no GPC of
+		// this device can host 16 CTAs of 1024 threads
+		bool ok = cudaFuncSetAttribute(k_tail<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+		          cudaFuncSetAttribute(k_tail2<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+		if (ok) {
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3(16);
+			cfg.blockDim = dim3(TAIL_THREADS);
+			cudaLaunchAttribute at[1];
+			at[0].id = cudaLaunchAttributeClusterDimension;
+			at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+			cfg.attrs = at; cfg.numAttrs = 1;
+			int n1 = 0, n2 = 0;
+			ok = cudaOccupancyMaxActiveClusters(&n1, k_tail<16>, &cfg) == cudaSuccess && n1 > 0 &&
+			     cudaOccupancyMaxActiveClusters(&n2, k_tail2<16>, &cfg) == cudaSuccess && n2 > 0;
+		}
+		if (!ok) { (void)cudaGetLastError(); g_tail_ctas = 8; }
 	}
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, g_device));
@@ -639,15 +654,19 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 		launch_cluster(k_tail<1>, 1, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
 	} else if (g_tail_ctas == 4) {
 		launch_cluster(k_tail<4>, 4, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
-	} else if (g_tail_ctas == 16) {
+	} else if (g_tail_ctas == 16 && wide_cluster()) {
 		launch_cluster(k_tail<16>, 16, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
 	} else {
 		launch_cluster(k_tail<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, mode_bits, ho, P, hdr_.nrows);
 	}
-	stats_.kernel_launches += 2;
+	stats_.kernel_launches += fused ? 1 : 2;
 	if (mode == 1) launch_k4_and_tail2(header_only);
 	CK(cudaGetLastError());
 }
+
+// The 16-CTA cluster pays (more warps, fewer lanes each) once a cut has a few thousand half-edges or several hundred
+// new rows; below that the portable 8-CTA cluster has the cheaper barriers.
+bool CutEngine::wide_cluster() const { return expect_vis_ > 256 || expect_m_ > 512; }
 
 void CutEngine::launch_k4_and_tail2(bool header_only)
 {
@@ -655,7 +674,7 @@ void CutEngine::launch_k4_and_tail2(bool header_only)
 	launch_dependent(k4_contain, num_sms_ * 4, K_THREADS, STREAM, S_);
 	const int ho = header_only ? 1 : 0;
 	if (g_tail_ctas == 4) launch_cluster(k_tail2<4>, 4, STREAM, S_, ho);
-	else if (g_tail_ctas == 16) launch_cluster(k_tail2<16>, 16, STREAM, S_, ho);
+	else if (g_tail_ctas == 16 && wide_cluster()) launch_cluster(k_tail2<16>, 16, STREAM, S_, ho);
 	else launch_cluster(k_tail2<TAIL_CTAS>, TAIL_CTAS, STREAM, S_, ho);
 	stats_.kernel_launches += 3;
 }

@@ -46,6 +46,32 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *warp_sums /* >= 33 */
 	return r;
 }
 
+// three scans in one pass (same barriers as one)
+__device__ __forceinline__ void block_excl_scan3(const u32 v[3], u32 *warp_sums /* >= 99 */, u32 r[3], u32 total[3])
+{
+	const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	u32 incl[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		incl[k] = warp_incl_scan(v[k]);
+		if (lane == 31) warp_sums[33 * k + wid] = incl[k];
+	}
+	__syncthreads();
+	if (wid < 3) {
+		u32 s = lane < nw ? warp_sums[33 * wid + lane] : 0;
+		u32 si = warp_incl_scan(s);
+		warp_sums[33 * wid + lane] = si - s;
+		if (lane == 31) warp_sums[33 * wid + 32] = si;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		r[k] = incl[k] - v[k] + warp_sums[33 * k + wid];
+		total[k] = warp_sums[33 * k + 32];
+	}
+	__syncthreads();
+}
+
 // ------------------------------------------------------------------ stage 0: begin
 __global__ void k_begin(DevState S, CutParams P)
 {
@@ -857,6 +883,15 @@ template <int NC> __device__ __forceinline__ void tail_sync()
 }
 #define TAIL_LOOP(i, n) for (u32 i = ctid; i < (u32)(n); i += NC * TAIL_THREADS)
 #define TAIL_SYNC() tail_sync<NC>()
+// Items whose work is gathers (row -> lists -> neighbours) are spread over ALL warps of the cluster, a few lanes
+// per warp: measured on B200 a warp-level memory instruction costs ~4 cycles per distinct sector it touches, per
+// warp, so a chain of gathers finishes 32/c times sooner in a warp with c active lanes -- and the other warps
+// would sit at the barrier anyway.  Item w*c + l goes to lane l < c of warp w (consecutive items stay together).
+#define TAIL_SPREAD(i, n)                                                                                                  \
+	for (u32 _b = 0, _n = (u32)(n); _b < _n; _b += NC * TAIL_THREADS)                                                      \
+		for (u32 _m = min(_n - _b, (u32)(NC * TAIL_THREADS)), _c = (_m + NC * (TAIL_THREADS / 32) - 1) / (NC * (TAIL_THREADS / 32)), \
+		         _l = threadIdx.x & 31, i = _b + (rank * (TAIL_THREADS / 32) + (threadIdx.x >> 5)) * _c + _l, _once = 1;     \
+		     _once && _l < _c && i < _n; _once = 0)
 #define TP(k) do { if (ctid == 0) S.dbg[k] = b200_globaltimer(); } while (0)
 
 // The staged record lives in mapped pinned host memory.  Every thread that wrote payload has fenced at
@@ -917,11 +952,11 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 		TAIL_SYNC();
 		if (!(c->status & ST_SKIP_B)) {
 			// adjacency offsets are known: place the PLUS neighbours
-			TAIL_LOOP(j, c->n_new) adj_place(S, j);
+			TAIL_SPREAD(j, c->n_new) adj_place(S, j);
 			TAIL_SYNC();
-			TAIL_LOOP(p, c->n_pairs) adj_pair_fill(S, p);
+			TAIL_SPREAD(p, c->n_pairs) adj_pair_fill(S, p);
 			TAIL_SYNC();
-			TAIL_LOOP(j, c->n_new) adj_sort(S, j);
+			TAIL_SPREAD(j, c->n_new) adj_sort(S, j);
 			if (ctid == 0) {
 				c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
 				c->nrows += c->n_new;
@@ -951,7 +986,7 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode_bits, int header_only, CutParams Parg, u32 nrows_host)
 {
 	const int mode = mode_bits & TAIL_MODE_STOP_AT_K4;
-	__shared__ u32 ws[33];
+	__shared__ u32 ws[99];
 	__shared__ u32 slist[B200_VIS_MAX];
 	__shared__ u32 soff[B200_VIS_MAX + 1];
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
@@ -1024,7 +1059,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	}
 	TAIL_SYNC();
 	if (c->status & (ST_REDUNDANT | ST_NEED_BIG)) {
-		if (!(c->status & ST_NEED_BIG)) TAIL_LOOP(i, c->n_vis) reset_class(S, i);
+		if (!(c->status & ST_NEED_BIG)) TAIL_SPREAD(i, c->n_vis) reset_class(S, i);
 		if (rank == 0) tail_stage_header(S, 0, header_only);
 		TAIL_SYNC();
 		if (ctid == 0) tail_reset_for_next_cut(S);
@@ -1037,7 +1072,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	if (c->n_zp) {
 		for (;;) {
 			bool any = false;
-			TAIL_LOOP(i, n_vis) any |= zp_activate(S, P, i);
+			TAIL_SPREAD(i, n_vis) any |= zp_activate(S, P, i);
 			if (any) atomicOr(&c->scratch_flag, 1u);
 			TAIL_SYNC();
 			const u32 f = c->scratch_flag;
@@ -1077,7 +1112,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	}
 	TP(2);
 	// ---- P3: evaluate every (visited vertex, neighbour) pair; the owner of a half-edge is found by bisection
-	TAIL_LOOP(e, H) {
+	TAIL_SPREAD(e, H) {
 		u32 lo = 0, hi = n_vis;            // soff[lo] <= e < soff[hi]
 		while (hi - lo > 1) {
 			const u32 mid = (lo + hi) >> 1;
@@ -1089,56 +1124,63 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	}
 	TAIL_SYNC();
 	TP(3);
-	// ---- P4: sizes, offsets, capacity plan.  Every CTA derives them itself (same inputs, same values; the counts
-	// go from registers straight into the scans), so no cluster barrier separates the plan from the emission;
-	// CTA 0 alone updates the control block
+	// ---- P4a: sizes per visited vertex, spread over the whole cluster (the strided list accesses are LSU work)
 	{
-		u32 nm = 0, nz = 0, carry[3] = {0, 0, 0};
+		u32 nm = 0, nz = 0;
 		bool bad = false;
+		TAIL_SPREAD(i, n_vis) {
+			const u32 v = slist[i];
+			const u8 cl = S.cls[v];
+			u32 cnt[3];
+			bad |= !he_count_core(S, i, v, cl, soff[i], soff[i + 1], cnt);
+			S.cnt3[3 * (size_t)i + 0] = cnt[0];
+			S.cnt3[3 * (size_t)i + 1] = cnt[1];
+			S.cnt3[3 * (size_t)i + 2] = cnt[2];
+			nm += (cl == CLS_MINUS);
+			nz += (cl == CLS_ZERO);
+		}
+		nm = __reduce_add_sync(0xffffffffu, nm);
+		nz = __reduce_add_sync(0xffffffffu, nz);
+		if ((threadIdx.x & 31) == 0) {               // one atomic per warp instead of one per visited vertex
+			if (nm) atomicAdd(&c->n_minus, nm);
+			if (nz) atomicAdd(&c->n_zero, nz);
+		}
+		if (bad) atomicOr(&c->status, (u32)ST_ERR_DEGENERATE);
+	}
+	TAIL_SYNC();
+	TP(16);
+	// ---- P4b: offsets and capacity plan.  Every CTA scans the (contiguous) counts itself, so no further cluster
+	// barrier separates the plan from the emission; CTA 0 alone updates the control block
+	{
+		u32 carry[3] = {0, 0, 0};
+		const bool bad = (c->status & ST_ERR_DEGENERATE) != 0;      // (only the OVF bits can change under this read)
 		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
 			const u32 i = base + threadIdx.x;
-			u32 cnt[3] = {0, 0, 0};
+			u32 v3[3] = {0, 0, 0}, e3[3], tot3[3];
 			if (i < n_vis) {
-				const u32 v = slist[i];
-				const u8 cl = S.cls[v];
-				bad |= !he_count_core(S, i, v, cl, soff[i], soff[i + 1], cnt);
-				nm += (cl == CLS_MINUS);
-				nz += (cl == CLS_ZERO);
+#pragma unroll
+				for (int k = 0; k < 3; k++) v3[k] = S.cnt3[3 * (size_t)i + k];
 			}
+			block_excl_scan3(v3, ws, e3, tot3);
 #pragma unroll
 			for (int k = 0; k < 3; k++) {
-				u32 tot;
-				const u32 e = block_excl_scan(cnt[k], ws, tot);
-				if (i < n_vis) {
-					S.cnt3[3 * (size_t)i + k] = cnt[k];
-					S.base3[3 * (size_t)i + k] = carry[k] + e;
-				}
-				carry[k] += tot;
+				if (i < n_vis) S.base3[3 * (size_t)i + k] = carry[k] + e3[k];
+				carry[k] += tot3[k];
 			}
 		}
-		TP(16);
 		u32 st = 0;
 		if ((u64)c->nrows + carry[0] > S.cap_rows) st |= ST_OVF_ROWS;
 		if ((u64)c->inc_used + carry[1] > S.cap_inc) st |= ST_OVF_INC;
 		if (carry[2] > S.cap_padj) st |= ST_OVF_PADJ;
-		if (rank == 0) {
-			nm = __reduce_add_sync(0xffffffffu, nm);
-			nz = __reduce_add_sync(0xffffffffu, nz);
-			if ((threadIdx.x & 31) == 0) {               // one atomic per warp instead of one per visited vertex
-				if (nm) atomicAdd(&c->n_minus, nm);
-				if (nz) atomicAdd(&c->n_zero, nz);
-			}
-			if (bad) atomicOr(&c->status, (u32)ST_ERR_DEGENERATE);
-			if (threadIdx.x == 0) {
-				c->n_new = carry[0];
-				c->inc_new = carry[1];
-				c->padj_new = carry[2];
-				S.facet_cnt[S.cur->facet] = carry[0];      // every new row lies on the new facet
-				if (st) atomicOr(&c->status, st);
-			}
+		if (ctid == 0) {
+			c->n_new = carry[0];
+			c->inc_new = carry[1];
+			c->padj_new = carry[2];
+			S.facet_cnt[S.cur->facet] = carry[0];      // every new row lies on the new facet
+			if (st) atomicOr(&c->status, st);
 		}
 		// block-wide (and, the inputs being the same, cluster-wide) agreement on whether the cut can proceed;
-		// the barrier also orders this CTA's base3 / he_rank stores before its own reads below
+		// the barrier also orders this CTA's base3 stores before its own reads below
 		if (__syncthreads_or(st != 0 || bad)) {
 			if (rank == 0) tail_stage_header(S, 0, header_only);
 			TAIL_SYNC();
@@ -1148,15 +1190,18 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	}
 	TP(4);
 	// ---- P5: new rows + rewiring (per half-edge) and copies + retirement (per vertex): independent
-	TAIL_LOOP(e, H) he_emit(S, P, e);
+	TAIL_SPREAD(x, 2 * H) {                            // geometry and incidence of a new row go to different warps
+		const int part = x >= H;
+		he_emit_part(S, P, part ? x - H : x, part);
+	}
 	TP(17);
-	TAIL_LOOP(i, n_vis) he_finish_vertex(S, P, i);
+	TAIL_SPREAD(i, n_vis) he_finish_vertex(S, P, i);
 	TP(18);
 	TAIL_SYNC();
 	TP(5);
 	// ---- P6: dead facets (needs the final facet counts) and K4's column relabelling: independent
 	const u32 M = c->n_new;
-	TAIL_LOOP(i, n_vis) collect_dead_facets(S, i);      // (K4's columns were assigned as the rows were emitted)
+	TAIL_SPREAD(i, n_vis) collect_dead_facets(S, i);      // (K4's columns were assigned as the rows were emitted)
 	TP(19);
 	TAIL_SYNC();
 	TP(6);
@@ -1182,7 +1227,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 		TAIL_SYNC();
 		{
 			const u32 nrows = c->nrows, f = P.facet;
-			TAIL_LOOP(j, M) k4_build_row_at(S, j, nrows, f, wl, mpad);
+			TAIL_SPREAD(j, M) k4_build_row_at(S, j, nrows, f, wl, mpad);
 		}
 		TAIL_SYNC();
 		TP(7);
