@@ -316,6 +316,7 @@ B200_HD void emit_edge_geom(const DevState &S, const CutParams &P, u32 v, u32 k,
 	S.new_parent[j] = B200_NONE;
 	S.root[nw] = B200_NONE;
 	S.deg[j] = 0;
+	S.adj_fill[j] = 0;
 	S.new_padj_off[j] = pslot;
 	S.new_padj_len[j] = 1;
 	S.padj[pslot] = k;
@@ -412,6 +413,7 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 	S.new_parent[j] = S.row_slot[v];
 	S.root[nw] = S.row_slot[v] < P.batch_first ? S.row_slot[v] : S.root[v];
 	S.deg[j] = 0;
+	S.adj_fill[j] = 0;
 	S.new_padj_off[j] = pslot;
 	S.new_padj_len[j] = nplus;
 	const u32 *iv = S.inc_pool + S.inc_off[v];
@@ -833,40 +835,53 @@ B200_HD void adj_place(const DevState &S, u32 j)
 {
 	const u32 nw = S.ctl->nrows + j;
 	const u32 off = S.ctl->adj_used + S.adj_base[j];
-	const u32 np = S.new_padj_len[j];
+	const u32 np = S.new_padj_len[j], po = S.new_padj_off[j];
 	S.adj_off[nw] = off;
 	S.adj_len[nw] = np + S.deg[j];
-	for (u32 q = 0; q < np; q++) S.adj_pool[off + q] = S.padj[S.new_padj_off[j] + q];
-	S.adj_fill[j] = np;
+	for (u32 q = 0; q < np; q++) S.adj_pool[off + q] = S.padj[po + q];
 }
+// adj_fill[j] counts the new-facet neighbours placed so far (zeroed when row j is emitted); the slot behind the
+// PLUS neighbours is derived from the scan, so this stage does not wait for adj_place
 B200_HD void adj_pair_fill(const DevState &S, u32 p)
 {
-	const u32 nrows = S.ctl->nrows, a = S.pair_a[p], b = S.pair_b[p];
-	S.adj_pool[S.adj_off[nrows + a] + B200_ATOMIC_ADD(&S.adj_fill[a], 1u)] = nrows + b;
-	S.adj_pool[S.adj_off[nrows + b] + B200_ATOMIC_ADD(&S.adj_fill[b], 1u)] = nrows + a;
+	const u32 nrows = S.ctl->nrows, used = S.ctl->adj_used, a = S.pair_a[p], b = S.pair_b[p];
+	const u32 oa = used + S.adj_base[a] + S.new_padj_len[a], ob = used + S.adj_base[b] + S.new_padj_len[b];
+	const u32 pa = B200_ATOMIC_ADD(&S.adj_fill[a], 1u), pb = B200_ATOMIC_ADD(&S.adj_fill[b], 1u);
+	S.adj_pool[oa + pa] = nrows + b;
+	S.adj_pool[ob + pb] = nrows + a;
+}
+// rank-sort of up to N entries in registers (entries are distinct): one load and one store each
+template <int N> B200_HD void adj_sort_regs(u32 *l, u32 m)
+{
+	u32 buf[N];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (u32 x = 0; x < N; x++) buf[x] = x < m ? l[x] : B200_NONE;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (u32 x = 0; x < N; x++) {
+		if (x >= m) break;
+		u32 rk = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (u32 y = 0; y < N; y++) rk += (buf[y] < buf[x]);
+		l[rk] = buf[x];
+	}
 }
 B200_HD void adj_sort(const DevState &S, u32 j)
 {
 	const u32 nw = S.ctl->nrows + j;
-	u32 *l = S.adj_pool + S.adj_off[nw];
-	const u32 lo = S.new_padj_len[j], n = S.adj_len[nw], m = n - lo;
-	if (m <= 24) {      // the usual case: rank-sort in registers (entries are distinct), one load and one store each
-		u32 buf[24];
-#pragma unroll
-		for (u32 x = 0; x < 24; x++) buf[x] = x < m ? l[lo + x] : B200_NONE;
-#pragma unroll
-		for (u32 x = 0; x < 24; x++) {
-			if (x >= m) break;
-			u32 rk = 0;
-#pragma unroll
-			for (u32 y = 0; y < 24; y++) rk += (buf[y] < buf[x]);
-			l[lo + rk] = buf[x];
-		}
-		return;
-	}
-	for (u32 x = lo + 1; x < n; x++) {
+	const u32 lo = S.new_padj_len[j], n = S.adj_len[nw];
+	u32 *l = S.adj_pool + S.adj_off[nw] + lo;
+	const u32 m = n - lo;
+	if (m <= 8) { adj_sort_regs<8>(l, m); return; }       // simple vertices: d-1 new-facet neighbours
+	if (m <= 24) { adj_sort_regs<24>(l, m); return; }
+	for (u32 x = 1; x < m; x++) {
 		u32 key = l[x], y = x;
-		while (y > lo && l[y - 1] > key) { l[y] = l[y - 1]; y--; }
+		while (y > 0 && l[y - 1] > key) { l[y] = l[y - 1]; y--; }
 		l[y] = key;
 	}
 }

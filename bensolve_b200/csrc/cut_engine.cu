@@ -292,7 +292,7 @@ CutEngine::~CutEngine()
 		for (int k = 0; k < 16; k++) fprintf(stderr, " p%d=%.1fus", k, stats_.phase_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, " (per cut, %llu cuts)\n", (unsigned long long)stats_.cuts);
 		fprintf(stderr, "[b200] sub-phases (thread 0 of CTA 0):");
-		for (int k = 0; k < 8; k++) fprintf(stderr, " s%d=%.1fus", k, stats_.sub_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
+		for (int k = 0; k < 14; k++) fprintf(stderr, " s%d=%.1fus", k, stats_.sub_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, "\n");
 		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions);
 	}
@@ -1042,10 +1042,14 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 		CK(cudaEventElapsedTime(&ms, (cudaEvent_t)ev_[2], (cudaEvent_t)ev_[3]));
 		stats_.cut_ms += ms;
 		{
-			u64 tp[24] = {0};
+			u64 tp[28] = {0};
 			d2h(tp, S_.dbg, sizeof tp);
 			if (tp[16] > tp[3] && tp[4] >= tp[16]) { stats_.sub_ns[0] += tp[16] - tp[3]; stats_.sub_ns[1] += tp[4] - tp[16]; }
 			if (tp[17] >= tp[4] && tp[18] >= tp[17] && tp[5] >= tp[18]) { stats_.sub_ns[2] += tp[17] - tp[4]; stats_.sub_ns[3] += tp[18] - tp[17]; stats_.sub_ns[4] += tp[5] - tp[18]; }
+			if (tp[11] >= tp[0] && tp[20] >= tp[11] && tp[21] >= tp[20] && tp[22] >= tp[21] && tp[23] >= tp[22] && tp[24] >= tp[23] && tp[25] >= tp[24] && tp[12] >= tp[25]) {
+				stats_.sub_ns[7] += tp[20] - tp[11]; stats_.sub_ns[8] += tp[21] - tp[20]; stats_.sub_ns[9] += tp[22] - tp[21]; stats_.sub_ns[10] += tp[23] - tp[22];
+				stats_.sub_ns[11] += tp[24] - tp[23]; stats_.sub_ns[12] += tp[25] - tp[24]; stats_.sub_ns[13] += tp[12] - tp[25];
+			}
 			if (tp[19] >= tp[5] && tp[6] >= tp[19]) { stats_.sub_ns[5] += tp[19] - tp[5]; stats_.sub_ns[6] += tp[6] - tp[19]; }
 			for (int k = 0; k < 12; k++) if (tp[k] >= tp[0] && tp[k + 1] > tp[k] && k != 10) stats_.phase_ns[k] += tp[k + 1] - tp[k];
 			if (tp[11] >= tp[0] && tp[7] >= tp[0] && tp[11] > tp[7] && tp[9] < tp[0]) {

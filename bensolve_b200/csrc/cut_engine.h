@@ -39,7 +39,7 @@ struct EngineStats {
 	u64 pair_tests = 0, new_adjacent_pairs = 0, algorithmic_bytes = 0, kernel_launches = 0, compactions = 0;
 	double classify_ms = 0, cut_ms = 0;
 	u64 phase_ns[16] = {0};
-	u64 sub_ns[8] = {0};
+	u64 sub_ns[16] = {0};
 	double host_us[8] = {0};
 	u64 redo_loops = 0;
 };

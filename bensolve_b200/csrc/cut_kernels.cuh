@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(K_THREADS) k_pairs_reset(DevState S)
 		S.ctl->n_surv = 0;
 		S.ctl->status &= ~(u32)ST_OVF_B;
 	}
-	B200_GRID_STRIDE(j, S.ctl->n_new) S.deg[j] = 0;
+	B200_GRID_STRIDE(j, S.ctl->n_new) { S.deg[j] = 0; S.adj_fill[j] = 0; }
 }
 
 __global__ void __launch_bounds__(K_THREADS) k4_assign(DevState S)
@@ -930,6 +930,7 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
 	const u32 st_in = c->status;      // every CTA reads the status before CTA 0 may change it below
 	TAIL_SYNC();
+	TP(20);
 	if (!(st_in & ST_SKIP_B)) {
 		if (rank == 0) {
 			if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) {
@@ -950,12 +951,14 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 			}
 		}
 		TAIL_SYNC();
+		TP(21);
 		if (!(c->status & ST_SKIP_B)) {
 			// adjacency offsets are known: place the PLUS neighbours
 			TAIL_SPREAD(j, c->n_new) adj_place(S, j);
+			TP(22);
+			TAIL_SPREAD(p, c->n_pairs) adj_pair_fill(S, p);   // independent of the placement: offsets are derived, not read back
 			TAIL_SYNC();
-			TAIL_SPREAD(p, c->n_pairs) adj_pair_fill(S, p);
-			TAIL_SYNC();
+			TP(23);
 			TAIL_SPREAD(j, c->n_new) adj_sort(S, j);
 			if (ctid == 0) {
 				c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
@@ -969,8 +972,10 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 	// single-launch cut: the record went to host memory from this grid, every writer orders its payload before
 	// the header / sequence number (late, so that the PCIe writes have drained by now); with k_tail2 as a
 	// separate launch the grid boundary has done that already
+	TP(24);
 	if (wrote_payload) __threadfence_system();
 	TAIL_SYNC();
+	TP(25);
 	if (rank == 0) {
 		tail_stage_header(S, 0, header_only);
 		__syncthreads();
