@@ -8,7 +8,9 @@ one cut per remaining halfspace, ending with a coherent host mirror.
 
     value : cuts/s with the halfspaces already resident in HBM (b200_poly_add_batch_device)
     e2e   : cuts/s through the reference-facing call, one poly__add_vrtx per halfspace with HOST
-            buffers; every call returns with primal.data/used/ideal/cnt current on the host
+            buffers; every call returns with primal.data/used/ideal/cnt current on the host.  The loop
+            around poly__add_vrtx is the C caller's (b200_poly_add_each = what bslv_algs.c writes),
+            not a Python loop
     roofline : K1 (classify), the dominant kernel, timed alone with CUDA events on its own stream
                with an L2 flush before each launch, against MEASURED_PEAKS.json hbm_gbs
     cpu_baseline : the unmodified reference engine (oracle/_ref) on a bounded prefix of the trace
@@ -219,8 +221,7 @@ def run_b200(a, trace):
         barrier()
         t0 = time.perf_counter()
         e = fresh_engine()
-        for i in range(d, n):
-            e.add(trace.vals[i], 0)
+        e.add_each(trace.vals[d:])        # the C caller's loop: one poly__add_vrtx per halfspace, host buffers
         barrier()
         dt = time.perf_counter() - t0
         st = e.stats()
@@ -282,7 +283,7 @@ def run_b200(a, trace):
             "live_vertices": int(n_live), "slots": int(per_step["slots"]), "facets": int(per_step["facets"]),
             "l2": "step: coordinates (%.0f MB) stay L2-resident across cuts, inherent to the workload; roofline: L2 flushed (read sweep over 256 MB) before every timed K1 launch" % (n_live * 8 * d / 1e6),
             "multi_gpu": (f"{world} ranks: state replicated, K1 (classify) sharded by row range, visited lists merged by one NCCL all-gather per cut, rest of the cut replicated" if world > 1 else "single"),
-            "timed_region": "poly__initialise .. last cut returned with a coherent host mirror; poly__kill between steps is untimed; device and host storage pre-sized with b200_poly_reserve from the warm-up's counts",
+            "timed_region": "poly__initialise .. last cut returned with a coherent host mirror; poly__kill between steps is untimed; device and host storage pre-sized with b200_poly_reserve from the warm-up's counts; the host mirror's coordinate block and the pinned download staging are recycled from the previous (killed) polytope of the process",
         },
         "vertex_evals_per_s": evals_v / t_value,
         "e2e": {"value": cuts_e / t_e2e, "unit": "cuts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step,

@@ -233,6 +233,17 @@ class PolyEngine:
         self.args.ideal = int(ideal)
         return self.lib.poly__add_vrtx(self._args_ref)
 
+    def add_each(self, vals, ideal=None):
+        """b200_poly_add_each: the C caller's loop, one poly__add_vrtx per row of `vals` (host memory)."""
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        n = len(vals)
+        rcs = (C.c_int * n)()
+        idl = None if ideal is None else np.ascontiguousarray(ideal, dtype=np.uint8)
+        self.lib.b200_poly_add_each.restype = C.c_long
+        self.lib.b200_poly_add_each.argtypes = [C.POINTER(PolyArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+        self.lib.b200_poly_add_each(self._args_ref, vals.ctypes.data, None if idl is None else idl.ctypes.data, n, rcs)
+        return list(rcs)
+
     def add_batch(self, vals, ideal=None):
         """b200_poly_add_batch: host arrays in, one device-resident pass, mirror coherent at return."""
         vals = np.ascontiguousarray(vals, dtype=np.float64)

@@ -318,6 +318,7 @@ CutEngine::~CutEngine()
 #else
 	free(pinned_hdr_);
 	free(pinned_stage_);
+	free(pinned_bulk_);
 #endif
 }
 
@@ -1150,24 +1151,60 @@ void CutEngine::reserve(u64 rows, u64 inc_entries, u64 adj_entries)
 
 void CutEngine::download_mirror(MirrorDump &o, u32 n_facets)
 {
+	const u32 n = hdr_.nrows;
+	const size_t nw = (n + 31) / 32;
+	ensure_facets(n_facets);
+	// one pinned buffer, one stream-ordered copy per array: pageable vectors cost more in page faults and
+	// zero-fill than the transfer itself at 10^6 rows
+	size_t off = 0;
+	auto take = [&](size_t bytes) { const size_t o0 = off; off += (bytes + 255) & ~(size_t)255; return o0; };
+	const size_t o_slot = take((size_t)n * 4), o_root = take((size_t)n * 4), o_live = take(nw * 4), o_ideal = take(nw * 4),
+	             o_facet = take((size_t)n_facets * 4), o_coord = take((size_t)n * d_ * sizeof(double));
+#ifndef B200_EMULATE
+	// pinned staging shared by the engines of this host thread (grow-only): pinning ~100 MB per engine would cost
+	// more than the faster copy saves, a pageable destination runs at ~2 GB/s once its page faults are counted
+	static thread_local unsigned char *t_bulk = nullptr;
+	static thread_local size_t t_bulk_cap = 0;
+	CK(cudaSetDevice(g_device));
+	if (off > t_bulk_cap) {
+		const size_t cap = std::max(off, t_bulk_cap * 2);
+		if (t_bulk) CK(cudaFreeHost(t_bulk));
+		t_bulk = nullptr; t_bulk_cap = 0;
+		CK(cudaMallocHost((void **)&t_bulk, cap));
+		t_bulk_cap = cap;
+	}
+	pinned_bulk_ = t_bulk;
+#else
+	if (off > pinned_bulk_cap_) {
+		free(pinned_bulk_);
+		pinned_bulk_ = (unsigned char *)malloc(off);
+		pinned_bulk_cap_ = off;
+	}
+#endif
+	unsigned char *b = pinned_bulk_;
 #ifndef B200_EMULATE
 	CK(cudaSetDevice(g_device));
+	auto get = [&](size_t o0, const void *src, size_t bytes) { if (bytes) CK(cudaMemcpyAsync(b + o0, src, bytes, cudaMemcpyDeviceToHost, STREAM)); };
+#else
+	auto get = [&](size_t o0, const void *src, size_t bytes) { if (bytes) memcpy(b + o0, src, bytes); };
+#endif
+	get(o_slot, S_.row_slot, (size_t)n * 4);
+	get(o_root, S_.root, (size_t)n * 4);
+	get(o_live, S_.live, nw * 4);
+	get(o_ideal, S_.ideal, nw * 4);
+	get(o_facet, S_.facet_alive, (size_t)n_facets * 4);
+	for (int j = 0; j < d_; j++) get(o_coord + (size_t)j * n * sizeof(double), S_.coord + (size_t)j * S_.cap_rows, (size_t)n * sizeof(double));
+#ifndef B200_EMULATE
 	CK(cudaStreamSynchronize(STREAM));
 #endif
-	const u32 n = hdr_.nrows;
 	o.nrows = n;
 	o.slot_cnt = hdr_.slot_cnt;
-	o.row_slot.resize(n); o.root.resize(n);
-	o.live_words.resize((n + 31) / 32); o.ideal_words.resize((n + 31) / 32);
-	o.coords_soa.resize((size_t)n * d_);
-	o.facet_alive.resize(n_facets);
-	d2h(o.row_slot.data(), S_.row_slot, (size_t)n * 4);
-	d2h(o.root.data(), S_.root, (size_t)n * 4);
-	d2h(o.live_words.data(), S_.live, o.live_words.size() * 4);
-	d2h(o.ideal_words.data(), S_.ideal, o.ideal_words.size() * 4);
-	for (int j = 0; j < d_; j++) d2h(o.coords_soa.data() + (size_t)j * n, S_.coord + (size_t)j * S_.cap_rows, (size_t)n * sizeof(double));
-	ensure_facets(n_facets);
-	d2h(o.facet_alive.data(), S_.facet_alive, (size_t)n_facets * 4);
+	o.row_slot = (const u32 *)(b + o_slot);
+	o.root = (const u32 *)(b + o_root);
+	o.live_words = (const u32 *)(b + o_live);
+	o.ideal_words = (const u32 *)(b + o_ideal);
+	o.facet_alive = (const u32 *)(b + o_facet);
+	o.coords_soa = (const double *)(b + o_coord);
 }
 
 // K6: adjacency among the live facets (dual polytope), by the same AND+POPC filter and containment

@@ -23,9 +23,9 @@ struct CutDelta {             // what one cut changed, in host slot numbers (SUR
 };
 
 struct MirrorDump {           // bulk state for rebuilding the host mirror after a device-resident batch
-	u32 nrows = 0, slot_cnt = 0;
-	std::vector<u32> row_slot, live_words, ideal_words, root, facet_alive;
-	std::vector<double> coords_soa;   // [d][nrows]
+	u32 nrows = 0, slot_cnt = 0;  // (views into the engine's pinned bulk buffer, valid until the next engine call)
+	const u32 *row_slot = nullptr, *live_words = nullptr, *ideal_words = nullptr, *root = nullptr, *facet_alive = nullptr;
+	const double *coords_soa = nullptr;   // [d][nrows]
 };
 
 struct HostStructure {        // snapshot for lazy materialisation of the host poly_lists
@@ -122,6 +122,8 @@ private:
 	CutCtl hdr_{};            // host copy of the control block as of the last sync
 	CutCtl *pinned_hdr_ = nullptr;
 	unsigned char *pinned_stage_ = nullptr;
+	unsigned char *pinned_bulk_ = nullptr;   // staging for bulk downloads (mirror rebuild), grown geometrically
+	size_t pinned_bulk_cap_ = 0;
 	void *stream_ = nullptr;
 	void *ev_[4] = {nullptr, nullptr, nullptr, nullptr};
 	int num_sms_ = 148;

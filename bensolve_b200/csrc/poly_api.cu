@@ -16,6 +16,9 @@
 
 #include <algorithm>
 #include <stdexcept>
+#include <chrono>
+#include <thread>
+#include <mutex>
 #include <vector>
 
 #include "../../include/bensolve_b200.h"
@@ -56,6 +59,54 @@ static Handle *handle_of(const polytope *p)
 // ------------------------------------------------------------------ host mirror storage
 static void list_reset(poly_list *l) { l->cnt = 0; l->blcks = 0; l->data = NULL; }
 
+// The coordinate array of a 10^6-vertex polytope is a few hundred MB.  Fresh memory of that size costs more in page
+// faults and kernel zero-fill than the cuts that fill it, so blocks released by poly__kill are kept (a few, bounded;
+// B200_HOST_CACHE_MB, default 1024, 0 = off) and handed to the next polytope of this process.  They are ordinary
+// malloc blocks.
+namespace {
+struct BigCache {
+	std::mutex mu;
+	struct E { void *p; size_t bytes; };
+	std::vector<E> held;
+	size_t held_bytes = 0;
+} g_big;
+const size_t BIG_MIN = (size_t)1 << 20;
+size_t big_limit()
+{
+	static const size_t lim = [] { const char *e = getenv("B200_HOST_CACHE_MB"); return (size_t)(e ? atol(e) : 1024) << 20; }();
+	return lim;
+}
+void *big_alloc(size_t bytes)       // a block of at least `bytes`
+{
+	if (bytes >= BIG_MIN) {
+		std::lock_guard<std::mutex> lk(g_big.mu);
+		size_t best = (size_t)-1;
+		for (size_t i = 0; i < g_big.held.size(); i++)
+			if (g_big.held[i].bytes >= bytes && g_big.held[i].bytes <= 4 * bytes && (best == (size_t)-1 || g_big.held[i].bytes < g_big.held[best].bytes)) best = i;
+		if (best != (size_t)-1) {
+			BigCache::E e = g_big.held[best];
+			g_big.held.erase(g_big.held.begin() + best);
+			g_big.held_bytes -= e.bytes;
+			return e.p;
+		}
+	}
+	return malloc(bytes);
+}
+void big_free(void *p, size_t bytes)
+{
+	if (!p) return;
+	if (bytes >= BIG_MIN && big_limit()) {
+		std::lock_guard<std::mutex> lk(g_big.mu);
+		if (g_big.held.size() < 4 && g_big.held_bytes + bytes <= big_limit()) {
+			g_big.held.push_back({p, bytes});
+			g_big.held_bytes += bytes;
+			return;
+		}
+	}
+	free(p);
+}
+}   // namespace
+
 static void mirror_alloc(polytope *p)
 {
 	const size_t cap = SLOTS_PER_BLOCK;
@@ -77,7 +128,15 @@ static void mirror_reserve(polytope *p, size_t slots)
 	size_t nb = p->blcks;
 	while (nb * SLOTS_PER_BLOCK <= slots) nb *= 2;
 	const size_t ncap = nb * SLOTS_PER_BLOCK;
-	p->data = (double *)realloc(p->data, ncap * std::max<size_t>(p->dim, 1) * sizeof(double));
+	const size_t row = std::max<size_t>(p->dim, 1) * sizeof(double), old_bytes = cap * row, new_bytes = ncap * row;
+	if (new_bytes >= BIG_MIN) {           // large: possibly a recycled block (see big_alloc)
+		double *nd = (double *)big_alloc(new_bytes);
+		if (!nd) die("mirror_reserve", "out of host memory");
+		memcpy(nd, p->data, p->cnt * row);
+		big_free(p->data, old_bytes);
+		p->data = nd;
+	} else
+		p->data = (double *)realloc(p->data, new_bytes);
 	p->data_primg = (double *)realloc(p->data_primg, ncap * std::max<size_t>(p->dim_primg, 1) * sizeof(double));
 	p->used = (vrtx_strg *)realloc(p->used, nb * sizeof(vrtx_strg));
 	p->ideal = (vrtx_strg *)realloc(p->ideal, nb * sizeof(vrtx_strg));
@@ -108,7 +167,8 @@ static size_t mirror_append(polytope *p)      // add_vrtx, bslv_poly.c:416-447
 
 static void mirror_free(polytope *p)
 {
-	free(p->data); free(p->data_primg); free(p->adjacence); free(p->incidence);
+	big_free(p->data, p->blcks * SLOTS_PER_BLOCK * std::max<size_t>(p->dim, 1) * sizeof(double));
+	free(p->data_primg); free(p->adjacence); free(p->incidence);
 	free(p->used); free(p->ideal); free(p->sltn);
 }
 
@@ -213,9 +273,18 @@ static void apply_delta(poly_args *a, const CutDelta &dl)
 	const size_t d = a->dim;
 	mirror_reserve(P, P->cnt + dl.n_new);
 	if (P->cnt != dl.first_new_slot) die("poly__add_vrtx", "host mirror and device disagree on the slot count");
+	// the new slots are contiguous: one block copy of the coordinates, one range of `used` bits
+	const size_t s0 = P->cnt, s1 = s0 + dl.n_new;
+	if (dl.n_new) memcpy(P->data + s0 * d, dl.coords, (size_t)dl.n_new * d * sizeof(double));
+	for (size_t s = s0; s < s1;) {
+		const size_t w = s / BTCNT, lo = s % BTCNT, hi = std::min<size_t>(BTCNT, lo + (s1 - s));
+		const btstrg mask = (hi == BTCNT ? ~(btstrg)0 : (((btstrg)1 << hi) - 1)) & ~(((btstrg)1 << lo) - 1);
+		P->used[w] |= mask;
+		s += hi - lo;
+	}
+	P->cnt = s1;
 	for (u32 r = 0; r < dl.n_new; r++) {
-		const size_t s = mirror_append(P);
-		memcpy(P->data + s * d, dl.coords + (size_t)r * d, d * sizeof(double));
+		const size_t s = s0 + r;
 		if (dl.ideal[r]) ST_BT(P->ideal, s);
 		const u32 par = dl.parent_slot[r];
 		if (par != B200_NONE && IS_ELEM(P->sltn, par)) {   // copy inherits sltn + pre-image (bslv_poly.c:583-587)
@@ -755,23 +824,58 @@ static void rebuild_mirror(poly_args *a, Handle *h, size_t first_slot)
 	polytope *P = &a->primal, *D = &a->dual;
 	const size_t d = a->dim;
 	MirrorDump m;
+	const auto tm0 = std::chrono::steady_clock::now();
 	h->engine->download_mirror(m, (u32)D->cnt);
+	const auto tm1 = std::chrono::steady_clock::now();
 	mirror_reserve(P, m.slot_cnt);
 	for (size_t s = P->cnt; s < m.slot_cnt; s++) { UNST_BT(P->used, s); UNST_BT(P->ideal, s); UNST_BT(P->sltn, s); }
 	P->cnt = m.slot_cnt;
 	for (size_t w = 0; w < (P->cnt + BTCNT - 1) / BTCNT; w++) P->used[w] = 0;
-	for (u32 r = 0; r < m.nrows; r++) {
-		if (!((m.live_words[r >> 5] >> (r & 31)) & 1u)) continue;
-		const size_t s = m.row_slot[r];
-		ST_BT(P->used, s);
-		if (s < first_slot) continue;
-		for (size_t j = 0; j < d; j++) P->data[s * d + j] = m.coords_soa[j * m.nrows + r];
-		if ((m.ideal_words[r >> 5] >> (r & 31)) & 1u) ST_BT(P->ideal, s);
-		const u32 root = m.root[r];
-		if (root != B200_NONE && IS_ELEM(P->sltn, root)) {
-			ST_BT(P->sltn, s);
-			memcpy(P->data_primg + s * P->dim_primg, P->data_primg + (size_t)root * P->dim_primg, P->dim_primg * sizeof(double));
+	// Rows are in creation order, so their slots ascend: the row range is cut where the slot crosses a multiple of
+	// 64 and each worker owns whole words of the bitsets.  The scatter of 10^6 rows into the slot-indexed mirror is
+	// a chain of cache misses for one thread.
+	const u32 n = m.nrows;
+	auto work = [&](u32 lo, u32 hi) {
+		for (u32 r = lo; r < hi; r++) {
+			if (!((m.live_words[r >> 5] >> (r & 31)) & 1u)) continue;
+			const size_t s = m.row_slot[r];
+			ST_BT(P->used, s);
+			if (s < first_slot) continue;
+			for (size_t j = 0; j < d; j++) P->data[s * d + j] = m.coords_soa[j * (size_t)n + r];
+			if ((m.ideal_words[r >> 5] >> (r & 31)) & 1u) ST_BT(P->ideal, s);
 		}
+	};
+	unsigned nt = std::thread::hardware_concurrency();
+	nt = nt ? std::min(nt, 16u) : 1u;
+	if (n < 65536) nt = 1;
+	std::vector<u32> cutp(nt + 1, n);
+	cutp[0] = 0;
+	for (unsigned t = 1; t < nt; t++) {
+		u32 r = (u32)((u64)n * t / nt);
+		r = std::max(r, cutp[t - 1]);
+		// advance to the first row whose slot starts a new 64-slot word relative to its predecessor
+		while (r < n && r > 0 && (m.row_slot[r] / BTCNT) == (m.row_slot[r - 1] / BTCNT)) r++;
+		cutp[t] = r;
+	}
+	if (nt == 1) work(0, n);
+	else {
+		std::vector<std::thread> th;
+		for (unsigned t = 0; t < nt; t++)
+			if (cutp[t] < cutp[t + 1]) th.emplace_back(work, cutp[t], cutp[t + 1]);
+		for (auto &x : th) x.join();
+	}
+	const auto tm2 = std::chrono::steady_clock::now();
+	if (getenv("B200_PHASES"))
+		fprintf(stderr, "[b200] mirror rebuild: download %.1f ms, scatter %.1f ms (%u threads, %u rows)\n", std::chrono::duration<double, std::milli>(tm1 - tm0).count(),
+		        std::chrono::duration<double, std::milli>(tm2 - tm1).count(), nt, n);
+	// pre-image inheritance through the device-side root journal (rows copied from an on-plane vertex): rare, serial
+	for (u32 r = 0; r < n; r++) {
+		const u32 root = m.root[r];
+		if (root == B200_NONE || !((m.live_words[r >> 5] >> (r & 31)) & 1u)) continue;
+		const size_t s = m.row_slot[r];
+		if (s < first_slot || !IS_ELEM(P->sltn, root)) continue;
+		ST_BT(P->sltn, s);
+		memcpy(P->data_primg + s * P->dim_primg, P->data_primg + (size_t)root * P->dim_primg, P->dim_primg * sizeof(double));
 	}
 	for (size_t f = 0; f < D->cnt; f++) {
 		if (m.facet_alive[f]) ST_BT(D->used, f);
@@ -797,12 +901,14 @@ extern "C" long b200_poly_add_batch_device(poly_args *a, const double *d_vals, c
 		h->host_may_have_edited = false;
 	}
 	long cuts = 0;
+	const auto t0 = std::chrono::steady_clock::now();
 	for (size_t i = 0; i < n; i++) {
 		const size_t f = mirror_append(D);
 		const int rc = h->engine->cut_from_device(d_vals, d_ideal, i, (u32)f, (u32)first_slot);
 		if (rc_out) rc_out[i] = rc;
 		cuts += (rc == 0);
 	}
+	const auto t1 = std::chrono::steady_clock::now();
 	// dual rows: the points themselves (host copy of the device inputs) and their ideal flags
 	std::vector<double> hv(n * d);
 	std::vector<unsigned char> hi(n, 0);
@@ -814,8 +920,25 @@ extern "C" long b200_poly_add_batch_device(poly_args *a, const double *d_vals, c
 	}
 	rebuild_mirror(a, h, first_slot);
 	a->idx = a->primal.cnt;
+	if (getenv("B200_PHASES"))
+		fprintf(stderr, "[b200] batch of %zu: cuts %.1f ms, mirror rebuild %.1f ms\n", n, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
 	return cuts;
 	GUARD_END("b200_poly_add_batch_device")
+}
+
+// the loop a C caller (bslv_algs.c) writes: one poly__add_vrtx per halfspace, mirror coherent after each
+extern "C" long b200_poly_add_each(poly_args *a, const double *vals, const unsigned char *ideal, size_t n, int *rc_out)
+{
+	long cuts = 0;
+	for (size_t i = 0; i < n; i++) {
+		for (size_t j = 0; j < a->dim; j++) a->val[j] = vals[i * a->dim + j];
+		a->ideal = ideal ? ideal[i] : 0;
+		const int rc = poly__add_vrtx(a);
+		if (rc_out) rc_out[i] = rc;
+		cuts += (rc == EXIT_SUCCESS);
+	}
+	return cuts;
 }
 
 extern "C" long b200_poly_add_batch(poly_args *a, const double *vals, const unsigned char *ideal, size_t n, int *rc_out)
@@ -824,17 +947,7 @@ extern "C" long b200_poly_add_batch(poly_args *a, const double *vals, const unsi
 	Handle *h = handle_of(&a->primal);
 	const bool device_path = a->init_data.intlsd && h->engine && !a->dim_primg_dl &&
 	                         (void (*)(double *, int, double *))a->dualV2primalH == default_dual_to_halfspace;
-	if (!device_path) {                      // generic callback / not yet initialised: one call per halfspace
-		long cuts = 0;
-		for (size_t i = 0; i < n; i++) {
-			for (size_t j = 0; j < a->dim; j++) a->val[j] = vals[i * a->dim + j];
-			a->ideal = ideal ? ideal[i] : 0;
-			const int rc = poly__add_vrtx(a);
-			if (rc_out) rc_out[i] = rc;
-			cuts += (rc == EXIT_SUCCESS);
-		}
-		return cuts;
-	}
+	if (!device_path) return b200_poly_add_each(a, vals, ideal, n, rc_out);   // generic callback / not yet initialised
 	double *dv = (double *)h->engine->device_alloc(n * a->dim * sizeof(double));
 	unsigned char *di = ideal ? (unsigned char *)h->engine->device_alloc(n) : nullptr;
 	h->engine->device_upload(dv, vals, n * a->dim * sizeof(double));

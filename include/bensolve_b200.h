@@ -113,6 +113,11 @@ int b200_poly_materialise(poly_args *);
  * or -1 on error. */
 long b200_poly_add_batch(poly_args *, const double *vals, const unsigned char *ideal, size_t n, int *rc_out);
 
+/* The loop a C caller writes around poly__add_vrtx (as bslv_algs.c does): for each i copy vals[i] into args->val,
+ * set args->ideal, call poly__add_vrtx; the host mirror is coherent after every call.  Works with any callback.
+ * Returns the number of non-redundant cuts. */
+long b200_poly_add_each(poly_args *, const double *vals, const unsigned char *ideal, size_t n, int *rc_out);
+
 /* Same with the dual points already resident in HBM (device pointer, row-major [n][dim]). */
 long b200_poly_add_batch_device(poly_args *, const double *d_vals, const unsigned char *d_ideal, size_t n, int *rc_out);
 

@@ -180,6 +180,20 @@ def test_gpu_batch_entry_point(product_lib, checker, tr, chunk):
     capi.compare_states(sa, sb, exact_coords=True)
 
 
+def test_gpu_add_each_is_the_per_call_loop(product_lib, checker):
+    """b200_poly_add_each (the C caller's loop around poly__add_vrtx) against one ctypes call per halfspace."""
+    tr = P.tangent_polytope(4, 90, 11)
+    a, b = capi.PolyEngine(checker, tr.dim), capi.PolyEngine(product_lib, tr.dim)
+    ra = P.replay(a, tr)
+    for i in range(tr.n_init):
+        b.add(tr.vals[i], int(tr.ideal[i]))
+    assert b.init_approx() == 0
+    rb = b.add_each(tr.vals[tr.n_init:], tr.ideal[tr.n_init:])
+    assert ra == rb
+    capi.compare_states(a.state(), b.state(), exact_coords=True)
+    a.kill(); b.kill()
+
+
 def test_gpu_reserve_then_run(product_lib, oracle_lib):
     tr = P.tangent_polytope(5, 120, 5)
     a, b = capi.PolyEngine(oracle_lib, 5), capi.PolyEngine(product_lib, 5)
