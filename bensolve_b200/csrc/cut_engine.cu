@@ -250,6 +250,7 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	S_.ctl = (CutCtl *)dalloc(sizeof(CutCtl));
 	S_.cur = (CutParams *)dalloc(sizeof(CutParams));
 	S_.dbg = (u64 *)dalloc(32 * sizeof(u64));
+	gc_totals_ = (u32 *)dalloc(4 * sizeof(u32));
 	nranks_ = g_comm.nranks;
 	rank_ = g_comm.rank;
 	S_.xchg_send = (u32 *)dalloc((size_t)B200_XCHG_WORDS * 4);
@@ -309,6 +310,7 @@ CutEngine::~CutEngine()
 #endif
 	                S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
+	dfree(gc_totals_);
 	drop_shadow();
 #ifndef B200_EMULATE
 	for (int i = 0; i < 4; i++) if (ev_[i]) cudaEventDestroy((cudaEvent_t)ev_[i]);
@@ -1323,7 +1325,7 @@ void CutEngine::compact()
 	if (nrows == n_live) return;
 	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE, ltiles = std::max<u32>(1, (n_live + B200_TILE - 1) / B200_TILE);
 	u32 *remap = S_.vis, *old_of = S_.dead_slots, *new_inc_off = S_.adj_base, *new_adj_off = S_.adj_fill;
-	u32 *totals = (u32 *)dalloc(4 * sizeof(u32));
+	u32 *totals = gc_totals_;                 // persistent: an allocation per compaction is a device-wide sync (and a peer mapping under NCCL)
 	// 1. remap = exclusive scan of the live bits
 	LiveBitOf lb{S_.live};
 	k_gscan_reduce<<<ntiles, K_THREADS, 0, STREAM>>>(lb, nrows, S_.tile_cnt);
@@ -1370,7 +1372,6 @@ void CutEngine::compact()
 	if (hdr_.nrows != n_live) fail("bensolve_b200: compaction lost rows");
 	void *old[11] = {S_.coord, S_.row_slot, S_.root, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len, S_.inc_pool, S_.adj_pool};
 	for (int k = 0; k < 11; k++) shadow_[k] = old[k];      // the previous arrays become the next shadow set
-	dfree(totals);
 	S_.coord = T.coord; S_.row_slot = T.row_slot; S_.root = T.root; S_.live = T.live; S_.ideal = T.ideal;
 	S_.inc_off = T.inc_off; S_.inc_len = T.inc_len; S_.adj_off = T.adj_off; S_.adj_len = T.adj_len;
 	S_.inc_pool = T.inc_pool; S_.adj_pool = T.adj_pool;

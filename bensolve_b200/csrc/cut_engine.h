@@ -122,6 +122,7 @@ private:
 	CutCtl hdr_{};            // host copy of the control block as of the last sync
 	CutCtl *pinned_hdr_ = nullptr;
 	unsigned char *pinned_stage_ = nullptr;
+	u32 *gc_totals_ = nullptr;               // device scratch of compact()
 	unsigned char *pinned_bulk_ = nullptr;   // staging for bulk downloads (mirror rebuild), grown geometrically
 	size_t pinned_bulk_cap_ = 0;
 	void *stream_ = nullptr;
