@@ -565,7 +565,7 @@ void CutEngine::launch_part_b(bool rerun)
 	k4_plan_kernel<<<1, 32, 0, STREAM>>>(S_);
 	k4_zero<<<gmap, K_THREADS, 0, STREAM>>>(S_);
 	k4_build<<<gmap, K_THREADS, 0, STREAM>>>(S_);
-	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, true));
+	k4_filter<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, true), 0);
 	k4_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
 	k_adj_scan<<<1, SCAN_THREADS, 0, STREAM>>>(S_);
 	k_adj_place<<<gmap, K_THREADS, 0, STREAM>>>(S_);
@@ -673,7 +673,10 @@ bool CutEngine::wide_cluster() const { return expect_vis_ > 256 || expect_m_ > 5
 
 void CutEngine::launch_k4_and_tail2(bool header_only)
 {
-	launch_dependent(k4_filter, num_sms_ * 4, K_THREADS, STREAM, S_, k4_threshold(S_, true));
+	// per-call path: one extra block publishes the early header (the payload k_tail wrote is complete), so that the
+	// host applies the record while the pair test and the adjacency build run
+	const int early = (!header_only && on_early_ && !early_done_) ? 1 : 0;
+	launch_dependent(k4_filter, num_sms_ * 4 + early, K_THREADS, STREAM, S_, k4_threshold(S_, true), early);
 	launch_dependent(k4_contain, num_sms_ * 4, K_THREADS, STREAM, S_);
 	const int ho = header_only ? 1 : 0;
 	if (g_tail_ctas == 4) launch_cluster(k_tail2<4>, 4, STREAM, S_, ho);
@@ -695,7 +698,32 @@ void CutEngine::launch_part_c(bool header_only)
 void CutEngine::fetch_delta()
 {
 	volatile u32 *seqp = (volatile u32 *)(pinned_stage_ + B200_STAGE_SEQ);
+	volatile u32 *earlyp = (volatile u32 *)(pinned_stage_ + B200_STAGE_EARLY + B200_STAGE_SEQ);
 	for (u64 spins = 1; *seqp != seq_; spins++) {
+		if (on_early_ && !early_done_ && !header_only_ && *earlyp == seq_) {
+			// the payload is complete and final (new rows, parents, retired slots, dead facets): hand it to the
+			// caller now; what is still running on the device only builds adjacency
+			__sync_synchronize();
+			CutCtl eh;
+			memcpy(&eh, pinned_stage_ + B200_STAGE_EARLY, sizeof(CutCtl));
+			const StageLayout L = stage_layout(eh, d_);
+			if (!(eh.status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE | ST_NEED_BIG)) && L.total <= S_.cap_stage) {
+				CutDelta e;
+				e.trigger_slot = eh.min_strict_slot;
+				e.n_new = eh.n_new;
+				e.first_new_slot = eh.slot_cnt;              // not committed yet on the device
+				e.coords = (const double *)(pinned_stage_ + L.coords);
+				e.parent_slot = (const u32 *)(pinned_stage_ + L.parent);
+				e.ideal = (const u8 *)(pinned_stage_ + L.ideal);
+				e.dead_slots = (const u32 *)(pinned_stage_ + L.dead_slots);
+				e.n_dead_entries = eh.n_vis;
+				e.dead_facets = (const u32 *)(pinned_stage_ + L.dead_facets);
+				e.n_dead_facets = eh.n_dead_facets;
+				early_done_ = true;
+				early_n_new_ = eh.n_new;
+				(*on_early_)(e);
+			}
+		}
 		if ((spins & 0x3fff) == 0) {          // every ~16k polls make sure the stream is still healthy
 			cudaError_t e = cudaStreamQuery(STREAM);
 			if (e != cudaSuccess && e != cudaErrorNotReady)
@@ -1093,12 +1121,23 @@ void CutEngine::account(const CutParams &P, u32 n_live_before, u32 nrows_before)
 	stats_.algorithmic_bytes += N * (8 * d_ + 1) + N + 4 * (nm + nz) + E * (24 * d_ + 24 * W) + nz * (16 * d_ + 16 * W) + 8 * M * W + 8 * A;
 }
 
-void CutEngine::cut(const CutParams &P, CutDelta &out)
+void CutEngine::cut(const CutParams &P, CutDelta &out, const std::function<void(const CutDelta &)> *on_early)
 {
 	const double t_in = now_us();
 	out = CutDelta();
 	const u32 n_live_before = hdr_.n_live, nrows_before = hdr_.nrows;
-	run_cut(P, false);
+	on_early_ = (on_early && *on_early) ? on_early : nullptr;
+	early_done_ = false;
+	try {
+		run_cut(P, false);
+	} catch (...) {
+		on_early_ = nullptr;
+		throw;
+	}
+	on_early_ = nullptr;
+	out.applied_early = early_done_;
+	if (early_done_ && ((hdr_.status & ST_REDUNDANT) || hdr_.n_new != early_n_new_))
+		fail("bensolve_b200: the early delta record disagrees with the final header");
 	const double t_run = now_us();
 	account(P, n_live_before, nrows_before);
 	if (hdr_.status & ST_REDUNDANT) { out.redundant = 1; return; }
@@ -1231,7 +1270,7 @@ void CutEngine::dual_adjacency(const std::vector<u32> &facet_rank, u32 M, std::v
 		CK(cudaMemsetAsync(S_.deg, 0, (size_t)M * 4, STREAM));
 		k6_begin<<<1, 32, 0, STREAM>>>(S_, M, wl, mpad);
 		k6_build<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, mpad);
-		k4_filter<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, false));
+		k4_filter<<<num_sms_ * 8, K_THREADS, 0, STREAM>>>(S_, k4_threshold(S_, false), 0);
 		k6_contain<<<num_sms_ * 4, K_THREADS, 0, STREAM>>>(S_);
 		stats_.kernel_launches += 4;
 		CK(cudaGetLastError());

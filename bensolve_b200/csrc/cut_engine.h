@@ -3,6 +3,7 @@
 #include <stddef.h>
 
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "cut_types.h"
@@ -20,6 +21,7 @@ struct CutDelta {             // what one cut changed, in host slot numbers (SUR
 	u32 n_dead_entries = 0;
 	const u32 *dead_facets = nullptr;   // [n_dead_facets]
 	u32 n_dead_facets = 0;
+	bool applied_early = false;         // the on_early callback of cut() has already received this record
 };
 
 struct MirrorDump {           // bulk state for rebuilding the host mirror after a device-resident batch
@@ -57,7 +59,9 @@ public:
 	                    const std::vector<std::vector<u32>> &inc, const std::vector<std::vector<u32>> &adj,
 	                    u32 n_facets, const std::vector<u32> &facet_counts);
 	// One halfspace; fills `out`.  Throws std::runtime_error on CUDA errors.
-	void cut(const CutParams &P, CutDelta &out);
+	// on_early (optional) is called from inside cut() with the complete delta as soon as the device has written it,
+	// while the adjacency build of the same cut still runs; out.applied_early tells the caller it has been called
+	void cut(const CutParams &P, CutDelta &out, const std::function<void(const CutDelta &)> *on_early = nullptr);
 	// Device-resident batch path: halfspace i of `d_vals` (device memory, [n][d], default callback
 	// meaning), no delta transfer; only the 128-byte header comes back.  Returns 1 if redundant.
 	int cut_from_device(const double *d_vals, const unsigned char *d_ideal, u64 i, u32 facet, u32 batch_first);
@@ -122,6 +126,9 @@ private:
 	CutCtl hdr_{};            // host copy of the control block as of the last sync
 	CutCtl *pinned_hdr_ = nullptr;
 	unsigned char *pinned_stage_ = nullptr;
+	const std::function<void(const CutDelta &)> *on_early_ = nullptr;
+	bool early_done_ = false;
+	u32 early_n_new_ = 0;
 	u32 *gc_totals_ = nullptr;               // device scratch of compact()
 	unsigned char *pinned_bulk_ = nullptr;   // staging for bulk downloads (mirror rebuild), grown geometrically
 	size_t pinned_bulk_cap_ = 0;

@@ -402,18 +402,32 @@ __global__ void __launch_bounds__(K_THREADS) k4_build(DevState S)
 #define K4_T 64
 #define K4_WCH 16
 #define K4_SV 512
-__global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr)
+// `early` != 0: the grid was launched with one extra block that does no pair work.  The producer grid (k_tail) has
+// written the delta record's payload to mapped host memory and has completed, so that block publishes a copy of
+// the control block plus the sequence number in the EARLY header: the host applies the record to its mirror while
+// the pair test and the adjacency build are still running.
+__global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr, int early)
 {
 	__shared__ u64 sa[K4_WCH][K4_T], sb[K4_WCH][K4_T];
 	__shared__ u32 sva[K4_SV], svb[K4_SV], nsv, gbase;
 	cudaGridDependencySynchronize();      // programmatic dependent launch: wait for the producer grid here
 	if (blockIdx.x == 0 && threadIdx.x == 0) S.dbg[13] = b200_globaltimer();
 	const CutCtl *c = S.ctl;
+	if (early && blockIdx.x == gridDim.x - 1) {
+		if (threadIdx.x < 32 && !(c->status & ST_SKIP_B)) {
+			if (threadIdx.x < sizeof(CutCtl) / 4) ((volatile u32 *)(S.stage + B200_STAGE_EARLY))[threadIdx.x] = ((const u32 *)c)[threadIdx.x];
+			__threadfence_system();
+			__syncwarp();
+			if (threadIdx.x == 0) *(volatile u32 *)(S.stage + B200_STAGE_EARLY + B200_STAGE_SEQ) = S.cur->seq;
+		}
+		return;
+	}
 	if (c->status & ST_SKIP_B) return;
 	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad;
 	const u32 nt = (M + K4_T - 1) / K4_T;
 	const u32 j = threadIdx.x & (K4_T - 1), i0 = threadIdx.x >> 6;
-	for (u32 tp = blockIdx.x; tp < nt * nt; tp += gridDim.x) {
+	const u32 nwork = gridDim.x - (early ? 1u : 0u);
+	for (u32 tp = blockIdx.x; tp < nt * nt; tp += nwork) {
 		const u32 ta = tp / nt, tb = tp % nt;
 		if (tb < ta) continue;                       // block-uniform
 		u32 cnt[K4_T / 4];

@@ -92,7 +92,8 @@ struct CutCtl {
 	u32 n_list;         // non-PLUS rows K1 appended to `nplist` (unordered; > B200_VIS_MAX = overflow)
 	u32 reserved0;
 };
-#define B200_STAGE_HDR 128u   // the packed delta starts with a copy of CutCtl, padded to this size
+#define B200_STAGE_HDR 256u   // the packed delta starts with two copies of CutCtl, 128 bytes each: the final header (status of the whole cut)
+#define B200_STAGE_EARLY 128u // and an early one, published when the payload behind it is complete but the adjacency build still runs
 #define B200_STAGE_SEQ 124u   // byte offset of the 'record complete' sequence number inside the header
 
 

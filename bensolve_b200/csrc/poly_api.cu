@@ -321,15 +321,26 @@ extern "C" int poly__add_vrtx(poly_args *args)
 	make_params(hp, d, (u32)f, P);
 	P.batch_first = (u32)args->primal.cnt;
 	CutDelta dl;
-	h->engine->cut(P, dl);
+	static const bool prof = getenv("B200_PHASES") != nullptr;
+	static double t_apply_us = 0, t_total_us = 0; static u64 n_calls = 0;
+	const auto tq0 = std::chrono::steady_clock::now();
+	const std::function<void(const CutDelta &)> early = [&](const CutDelta &e) { apply_delta(args, e); };
+	h->engine->cut(P, dl, &early);
+	const auto tq1 = std::chrono::steady_clock::now();
 	if (dl.redundant) {                                                  // (:132-136)
 		args->idx = args->primal.cnt;
 		UNST_BT(D->used, f);
 		return EXIT_FAILURE;
 	}
 	args->idx = dl.trigger_slot;
-	apply_delta(args, dl);
+	if (!dl.applied_early) apply_delta(args, dl);
 	h->lists_current = false;
+	if (prof) {
+		const auto tq2 = std::chrono::steady_clock::now();
+		t_apply_us += std::chrono::duration<double, std::micro>(tq2 - tq1).count();
+		t_total_us += std::chrono::duration<double, std::micro>(tq2 - tq0).count();
+		if (++n_calls % 2000 == 0) fprintf(stderr, "[b200] poly__add_vrtx: apply_delta %.1f us, cut+apply %.1f us (mean of %llu calls)\n", t_apply_us / n_calls, t_total_us / n_calls, (unsigned long long)n_calls);
+	}
 	return EXIT_SUCCESS;
 	GUARD_END("poly__add_vrtx")
 }
