@@ -295,7 +295,7 @@ CutEngine::~CutEngine()
 		fprintf(stderr, "[b200] sub-phases (thread 0 of CTA 0):");
 		for (int k = 0; k < 14; k++) fprintf(stderr, " s%d=%.1fus", k, stats_.sub_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, "\n");
-		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions);
+		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu (host ms in compaction %.1f, of which shadow allocation %.1f)\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions, stats_.host_us[5] / 1e3, stats_.host_us[6] / 1e3);
 	}
 #ifndef B200_EMULATE
 	cudaSetDevice(g_device);
@@ -1362,6 +1362,8 @@ void CutEngine::compact()
 	CK(cudaSetDevice(g_device));
 	const u32 nrows = hdr_.nrows, n_live = hdr_.n_live;
 	if (nrows == n_live) return;
+	const double t_gc0 = now_us();
+	double t_alloc = 0;
 	const u32 ntiles = (nrows + B200_TILE - 1) / B200_TILE, ltiles = std::max<u32>(1, (n_live + B200_TILE - 1) / B200_TILE);
 	u32 *remap = S_.vis, *old_of = S_.dead_slots, *new_inc_off = S_.adj_base, *new_adj_off = S_.adj_fill;
 	u32 *totals = gc_totals_;                 // persistent: an allocation per compaction is a device-wide sync (and a peer mapping under NCCL)
@@ -1382,6 +1384,7 @@ void CutEngine::compact()
 	// 3. gather into the shadow set of persistent arrays (allocated once per capacity), then swap
 	const u32 cap = S_.cap_rows;
 	if (!shadow_valid_ || shadow_rows_ != cap || shadow_inc_ != S_.cap_inc || shadow_adj_ != S_.cap_adj) {
+		const double ta0 = now_us();
 		drop_shadow();
 		shadow_[0] = dalloc((size_t)cap * d_ * sizeof(double));
 		for (int k = 1; k <= 2; k++) shadow_[k] = dalloc((size_t)cap * 4);          // row_slot, root
@@ -1391,6 +1394,7 @@ void CutEngine::compact()
 		shadow_[10] = dalloc((size_t)S_.cap_adj * 4);
 		shadow_rows_ = cap; shadow_inc_ = S_.cap_inc; shadow_adj_ = S_.cap_adj;
 		shadow_valid_ = true;
+		t_alloc = now_us() - ta0;
 	} else {                                   // only the bitsets rely on zero fill beyond the live rows
 		CK(cudaMemsetAsync(shadow_[3], 0, (size_t)cap / 8, STREAM));
 		CK(cudaMemsetAsync(shadow_[4], 0, (size_t)cap / 8, STREAM));
@@ -1416,7 +1420,8 @@ void CutEngine::compact()
 	S_.inc_pool = T.inc_pool; S_.adj_pool = T.adj_pool;
 	stats_.compactions++;
 	stats_.kernel_launches += 12;
-
+	stats_.host_us[5] += now_us() - t_gc0;
+	stats_.host_us[6] += t_alloc;
 }
 #else
 void CutEngine::compact()
