@@ -1218,16 +1218,26 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 	TP(18);
 	TAIL_SYNC();
 	TP(5);
-	// ---- P6: dead facets (needs the final facet counts) and K4's column relabelling: independent
+	// ---- P6: dead facets (needs the final facet counts) ‖ K4's matrix shape and the clearing of its column matrix
+	// (the columns were assigned as the rows were emitted, so their number is final since the barrier above)
 	const u32 M = c->n_new;
-	TAIL_SPREAD(i, n_vis) collect_dead_facets(S, i);      // (K4's columns were assigned as the rows were emitted)
+	// every thread derives the matrix shape itself (no barrier between plan and the stores below)
+	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 63) & ~63u;
+	const bool bits_ovf = k4_words(wl, mpad, c->n_local) > S.cap_bits;
+	if (ctid == 0) k4_plan(S);
+	if (!bits_ovf) {
+		u64 *tb = k4_tbits(S, wl, mpad);
+		for (u64 x = ctid; x < (u64)c->n_local * (mpad / 64); x += NC * TAIL_THREADS) tb[x] = 0;
+	}
+	TAIL_SPREAD(i, n_vis) collect_dead_facets(S, i);
 	TP(19);
 	TAIL_SYNC();
 	TP(6);
-	// ---- delta record: everything it holds is final now (new rows, parents, retired slots, dead facets).  The
-	// stores go to mapped host memory and drain over PCIe while the pair test and the adjacency build run
+	// ---- P7: delta record ‖ K4 bit matrices.  Everything the record holds is final now (new rows, parents, retired
+	// slots, dead facets); the stores go to mapped host memory and drain over PCIe while the pair test and the
+	// adjacency build run
 	bool wrote_payload = false;
-	if (!header_only) {
+	if (!header_only && !bits_ovf) {          // (on a bit-matrix overflow the host grows and re-runs; the record is packed then)
 		const StageLayout L = stage_layout(*c, S.d);
 		if (L.total <= S.cap_stage) {
 			const u64 n = (u64)M * S.d + M + n_vis + c->n_dead_facets;
@@ -1236,14 +1246,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 			wrote_payload = ctid < n;
 		}
 	}
-	// every thread derives the matrix shape itself (no barrier between plan and the stores below)
-	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 63) & ~63u;
-	const bool bits_ovf = k4_words(wl, mpad, c->n_local) > S.cap_bits;
-	if (ctid == 0) k4_plan(S);
 	if (!bits_ovf) {
-		u64 *tb = k4_tbits(S, wl, mpad);
-		for (u64 x = ctid; x < (u64)c->n_local * (mpad / 64); x += NC * TAIL_THREADS) tb[x] = 0;
-		TAIL_SYNC();
 		{
 			const u32 nrows = c->nrows, f = P.facet;
 			TAIL_SPREAD(j, M) k4_build_row_at(S, j, nrows, f, wl, mpad);
