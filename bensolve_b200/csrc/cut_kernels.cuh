@@ -942,13 +942,17 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 {
 	CutCtl *c = S.ctl;
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
-	const u32 st_in = c->status;      // every CTA reads the status before CTA 0 may change it below
-	TAIL_SYNC();
+	// Nothing in here writes the status word or the persistent counters before the last barrier (capacity
+	// overflows found by CTA 0 travel in scratch_flag, the commit waits), so no barrier is needed on entry and
+	// the bodies may read nrows / adj_used while other warps are still working.
+	const u32 st_in = c->status;
+	const u32 OVF_P = 8u, OVF_A = 16u;
 	TP(20);
-	if (!(st_in & ST_SKIP_B)) {
+	bool go = !(st_in & ST_SKIP_B);
+	if (go) {
 		if (rank == 0) {
 			if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) {
-				if (threadIdx.x == 0) c->status |= ST_OVF_PAIRS;
+				if (threadIdx.x == 0) atomicOr(&c->scratch_flag, OVF_P);
 			} else {
 				const u32 n = c->n_new;
 				u32 carry = 0;
@@ -960,13 +964,14 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 				}
 				if (threadIdx.x == 0) {
 					c->adj_new = carry;
-					if ((u64)c->adj_used + carry > S.cap_adj) c->status |= ST_OVF_ADJ;
+					if ((u64)c->adj_used + carry > S.cap_adj) atomicOr(&c->scratch_flag, OVF_A);
 				}
 			}
 		}
 		TAIL_SYNC();
 		TP(21);
-		if (!(c->status & ST_SKIP_B)) {
+		go = !(c->scratch_flag & (OVF_P | OVF_A));
+		if (go) {
 			// adjacency offsets are known: place the PLUS neighbours
 			TAIL_SPREAD(j, c->n_new) adj_place(S, j);
 			TP(22);
@@ -974,13 +979,6 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 			TAIL_SYNC();
 			TP(23);
 			TAIL_SPREAD(j, c->n_new) adj_sort(S, j);
-			if (ctid == 0) {
-				c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
-				c->nrows += c->n_new;
-				c->slot_cnt += c->n_new;
-				c->inc_used += c->inc_new;
-				c->adj_used += c->adj_new;
-			}
 		}
 	}
 	// single-launch cut: the record went to host memory from this grid, every writer orders its payload before
@@ -991,6 +989,19 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 	TAIL_SYNC();
 	TP(25);
 	if (rank == 0) {
+		if (threadIdx.x == 0) {
+			const u32 fl = c->scratch_flag;
+			if (fl & OVF_P) c->status |= ST_OVF_PAIRS;
+			if (fl & OVF_A) c->status |= ST_OVF_ADJ;
+			if (go) {                                  // commit: every reader of these counters is past the barrier
+				c->n_live = c->n_live + c->n_new - (c->n_minus + c->n_zero);
+				c->nrows += c->n_new;
+				c->slot_cnt += c->n_new;
+				c->inc_used += c->inc_new;
+				c->adj_used += c->adj_new;
+			}
+		}
+		__syncthreads();
 		tail_stage_header(S, 0, header_only);
 		__syncthreads();
 		if (threadIdx.x == 0) tail_reset_for_next_cut(S);
