@@ -1188,6 +1188,29 @@ void CutEngine::reserve(u64 rows, u64 inc_entries, u64 adj_entries)
 	ensure_rows((u32)rows);
 	ensure_inc((u32)inc_entries);
 	ensure_adj((u32)adj_entries);
+	ensure_shadow();        // the compaction's second set of arrays belongs to "no allocation after reserve" too
+}
+
+// the shadow set of persistent arrays the compaction gathers into (allocated once per capacity); true if (re)allocated
+bool CutEngine::ensure_shadow()
+{
+#ifndef B200_EMULATE
+	const u32 cap = S_.cap_rows;
+	if (shadow_valid_ && shadow_rows_ == cap && shadow_inc_ == S_.cap_inc && shadow_adj_ == S_.cap_adj) return false;
+	CK(cudaSetDevice(g_device));
+	drop_shadow();
+	shadow_[0] = dalloc((size_t)cap * d_ * sizeof(double));
+	for (int k = 1; k <= 2; k++) shadow_[k] = dalloc((size_t)cap * 4);          // row_slot, root
+	for (int k = 3; k <= 4; k++) shadow_[k] = dalloc((size_t)cap / 8);           // live, ideal
+	for (int k = 5; k <= 8; k++) shadow_[k] = dalloc((size_t)cap * 4);          // inc_off, inc_len, adj_off, adj_len
+	shadow_[9] = dalloc((size_t)S_.cap_inc * 4);
+	shadow_[10] = dalloc((size_t)S_.cap_adj * 4);
+	shadow_rows_ = cap; shadow_inc_ = S_.cap_inc; shadow_adj_ = S_.cap_adj;
+	shadow_valid_ = true;
+	return true;
+#else
+	return false;
+#endif
 }
 
 void CutEngine::download_mirror(MirrorDump &o, u32 n_facets)
@@ -1383,21 +1406,13 @@ void CutEngine::compact()
 	k_gscan_apply<<<ltiles, K_THREADS, 0, STREAM>>>(la, n_live, S_.tile_base, new_adj_off);
 	// 3. gather into the shadow set of persistent arrays (allocated once per capacity), then swap
 	const u32 cap = S_.cap_rows;
-	if (!shadow_valid_ || shadow_rows_ != cap || shadow_inc_ != S_.cap_inc || shadow_adj_ != S_.cap_adj) {
+	{
 		const double ta0 = now_us();
-		drop_shadow();
-		shadow_[0] = dalloc((size_t)cap * d_ * sizeof(double));
-		for (int k = 1; k <= 2; k++) shadow_[k] = dalloc((size_t)cap * 4);          // row_slot, root
-		for (int k = 3; k <= 4; k++) shadow_[k] = dalloc((size_t)cap / 8);           // live, ideal
-		for (int k = 5; k <= 8; k++) shadow_[k] = dalloc((size_t)cap * 4);          // inc_off, inc_len, adj_off, adj_len
-		shadow_[9] = dalloc((size_t)S_.cap_inc * 4);
-		shadow_[10] = dalloc((size_t)S_.cap_adj * 4);
-		shadow_rows_ = cap; shadow_inc_ = S_.cap_inc; shadow_adj_ = S_.cap_adj;
-		shadow_valid_ = true;
-		t_alloc = now_us() - ta0;
-	} else {                                   // only the bitsets rely on zero fill beyond the live rows
-		CK(cudaMemsetAsync(shadow_[3], 0, (size_t)cap / 8, STREAM));
-		CK(cudaMemsetAsync(shadow_[4], 0, (size_t)cap / 8, STREAM));
+		if (!ensure_shadow()) {                // only the bitsets rely on zero fill beyond the live rows
+			CK(cudaMemsetAsync(shadow_[3], 0, (size_t)cap / 8, STREAM));
+			CK(cudaMemsetAsync(shadow_[4], 0, (size_t)cap / 8, STREAM));
+		} else
+			t_alloc = now_us() - ta0;
 	}
 	GcTarget T;
 	T.coord = (double *)shadow_[0];

@@ -103,6 +103,7 @@ private:
 	void launch_k4_and_tail2(bool header_only);
 	bool use_small_path() const;
 	bool wide_cluster() const;
+	bool ensure_shadow();
 	void run_cut(const CutParams &P, bool header_only);
 	void account(const CutParams &P, u32 n_live_before, u32 nrows_before);
 	void launch_part_b(bool rerun);
