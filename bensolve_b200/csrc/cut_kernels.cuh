@@ -1010,7 +1010,6 @@ template <int NC> __device__ void tail_adjacency_and_pack(const DevState &S, u32
 
 // mode 0: the whole rest of the cut; mode 1: stop after building K4's bit matrix (the multi-block
 // k4_filter / k4_contain and k_tail2 follow)
-#define TAIL_SBITS 2048u      // 16 KB of shared memory for K4's bit matrix inside the tail cluster
 #define TAIL_MODE_STOP_AT_K4 1    // stop after building K4's matrices: k4_filter, k4_contain, k_tail2 follow
 #define TAIL_MODE_FUSED_K1 2      // small polytope: this (single) CTA classifies the rows itself, no K1 launch
 template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevState S, int mode_bits, int header_only, CutParams Parg, u32 nrows_host)

@@ -258,6 +258,40 @@ def test_host_logic_capacity_negotiation(oracle_lib, emul_lib, tiny_caps, tr, fl
     run_pair(oracle_lib, emul_lib, tr, exact=True, flags_b=flags)
 
 
+def test_host_logic_recycled_coordinate_block(oracle_lib, emul_lib):
+    """The host mirror's coordinate block of a killed polytope is handed to the next one (poly_api.cu big_alloc /
+    big_free): a polytope built in recycled, non-zero memory must come out identical."""
+    tr = P.lattice_polytope(4, 40, seed=5)
+    states = []
+    for rep in range(3):
+        b = capi.PolyEngine(emul_lib, tr.dim)
+        assert b.reserve(120000, 1 << 20, 1 << 20) == 0      # > 1 MB of coordinates: the recycling path
+        rb = P.replay(b, tr)
+        states.append((rb, b.state()))
+        b.kill()
+    a = capi.PolyEngine(oracle_lib, tr.dim)
+    ra = P.replay(a, tr)
+    sa = a.state()
+    a.kill()
+    for rb, sb in states:
+        assert ra == rb
+        capi.compare_states(sa, sb, exact_coords=True)
+
+
+def test_host_logic_add_each_matches_per_call(oracle_lib, emul_lib):
+    """b200_poly_add_each is the loop around poly__add_vrtx a C caller writes."""
+    tr = P.mixed_polyhedron(4, 40, seed=3)
+    a, b = capi.PolyEngine(oracle_lib, tr.dim), capi.PolyEngine(emul_lib, tr.dim)
+    ra = P.replay(a, tr)
+    for i in range(tr.n_init):
+        b.add(tr.vals[i], int(tr.ideal[i]))
+    assert b.init_approx() == 0
+    rb = b.add_each(tr.vals[tr.n_init:], tr.ideal[tr.n_init:])
+    assert ra == rb
+    capi.compare_states(a.state(), b.state(), exact_coords=True)
+    a.kill(); b.kill()
+
+
 def test_product_fails_loudly_without_gpu(tmp_path):
     """No CPU fallback for the cut: on a machine without a CUDA device the first call that needs the
     device (poly__intl_apprx) prints a message and aborts; nothing is computed on the host."""
