@@ -893,7 +893,7 @@ struct StageLayout { u64 coords, parent, dead_slots, dead_facets, ideal, total; 
 B200_HD StageLayout stage_layout(const CutCtl &c, int d)
 {
 	StageLayout L;
-	const bool cutting = !(c.status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE));
+	const bool cutting = !(c.status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE | ST_NEED_BIG));
 	const u64 n_new = cutting ? c.n_new : 0, n_vis = cutting ? c.n_vis : 0, n_dead = cutting ? c.n_dead_facets : 0;
 	L.coords = B200_STAGE_HDR;
 	L.parent = L.coords + 8 * n_new * (u64)d;

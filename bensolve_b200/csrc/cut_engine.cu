@@ -264,6 +264,8 @@ CutEngine::CutEngine(int dim) : d_(dim)
 	S_.he_incpre = (u32 *)dalloc(B200_HE_CAP * sizeof(u32));
 	S_.he_flag = (u8 *)dalloc(B200_HE_CAP);
 	S_.zmask = (u64 *)dalloc((size_t)B200_VIS_MAX * (B200_MAXINC / 64) * sizeof(u64));
+	S_.cap_he = B200_HE_CAP;
+	if (const char *e = getenv("B200_HE_CAP")) S_.cap_he = std::min<u32>(B200_HE_CAP, (u32)std::max(1, atoi(e)));   // test hook
 	tiny_caps_ = getenv("B200_TINY_CAPS") != nullptr;
 	if (tiny_caps_) {                        // test hook: start so small that every capacity negotiation path runs
 		ensure_rows(B200_TILE);
@@ -335,6 +337,8 @@ void CutEngine::drop_shadow()
 void CutEngine::ensure_rows(u32 need)
 {
 	if (need <= S_.cap_rows) return;
+	// the multi-GPU exchange packs (row | class << 30) into one word (k_xchg_pack / k_xchg_merge)
+	if (nranks_ > 1 && need > (1u << 30)) fail("bensolve_b200: more than 2^30 rows are not supported with several ranks");
 	drop_shadow();
 	const u32 old = S_.cap_rows, keep = hdr_.nrows;
 	const u32 cap = round_up(std::max<u64>(need, (u64)old * 2), B200_TILE);
@@ -645,7 +649,8 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 	// tiny cuts run the tail in one CTA (block barriers); larger ones in an 8-CTA cluster
 	static const u32 one_cta_max = getenv("B200_TAIL1_MAX_VIS") ? (u32)atoi(getenv("B200_TAIL1_MAX_VIS")) : 96u;
 	static const u32 fuse_max_rows = getenv("B200_FUSE_MAX_ROWS") ? (u32)atoi(getenv("B200_FUSE_MAX_ROWS")) : 16384u;
-	const bool tiny = expect_vis_ <= one_cta_max && (expect_m_ <= B200_K4_SMALL / 2 || mode == 1);
+	const bool force_wide = (flags_ & 16) != 0;     // test hook: every cut through the widest cluster + the grid-wide pair test
+	const bool tiny = !force_wide && expect_vis_ <= one_cta_max && (expect_m_ <= B200_K4_SMALL / 2 || mode == 1);
 	// a polytope of a few thousand rows is classified inside the single-CTA tail: one launch per cut
 	const bool fused = tiny && hdr_.nrows <= fuse_max_rows && !dev_vals_ && nranks_ == 1;
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
@@ -669,7 +674,7 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 
 // The 16-CTA cluster pays (more warps, fewer lanes each) once a cut has a few thousand half-edges or several hundred
 // new rows; below that the portable 8-CTA cluster has the cheaper barriers.
-bool CutEngine::wide_cluster() const { return expect_vis_ > 256 || expect_m_ > 512; }
+bool CutEngine::wide_cluster() const { return (flags_ & 16) || expect_vis_ > 256 || expect_m_ > 512; }
 
 void CutEngine::launch_k4_and_tail2(bool header_only)
 {
@@ -930,7 +935,7 @@ void CutEngine::launch_small(const CutParams &Pin, int mode, bool header_only)
 		for (u32 w = 0; w < (S.inc_len[r] + 63) / 64 && w < B200_MAXINC / 64; w++) S.zmask[(size_t)i * (B200_MAXINC / 64) + w] = 0;
 	}
 	S.he_off[c->n_vis] = H;
-	if (H > B200_HE_CAP) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
+	if (H > S.cap_he) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
 	for (u32 i = 0; i < c->n_vis; i++) he_owner_fill(S, i);
 	for (u32 e = 0; e < H; e++) he_eval(S, e);
 	for (u32 i = 0; i < c->n_vis; i++) {
@@ -1015,7 +1020,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 	auto launch_all = [&]() {
 		Pq.seq = ++seq_;
 		if (small) {
-			launch_small(Pq, expect_m_ > (B200_K4_SMALL * 7) / 8 ? 1 : 0, header_only);
+			launch_small(Pq, ((flags_ & 16) || expect_m_ > (B200_K4_SMALL * 7) / 8) ? 1 : 0, header_only);
 		} else {
 			launch_part_a(Pq);
 			launch_part_b(false);

@@ -12,7 +12,7 @@ __device__ __forceinline__ u64 b200_globaltimer() { u64 t; asm volatile("mov.u64
 #define K_THREADS 256
 #define POLY_EPS_D 1e-9   // POLY_EPS, bslv_poly.h:47
 #define SCAN_THREADS 1024
-#define ST_SKIP_A (ST_REDUNDANT | ST_OVF_A | ST_ERR_DEGENERATE)
+#define ST_SKIP_A (ST_REDUNDANT | ST_OVF_A | ST_ERR_DEGENERATE | ST_NEED_BIG)
 #define ST_SKIP_B (ST_SKIP_A | ST_OVF_B)
 
 // ------------------------------------------------------------------ block primitives
@@ -1133,8 +1133,14 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(DevS
 		if (rank == 0) S.he_off[n_vis] = H;
 	}
 	__syncthreads();
-	if (H > B200_HE_CAP) {                 // every CTA sees the same total; the status word itself is left alone (others may still read it)
-		if (rank == 0) tail_stage_header(S, ST_NEED_BIG, header_only);
+	if (H > S.cap_he) {                    // every CTA sees the same total and takes this branch
+		// The verdict goes into the control block itself (after a barrier: other CTAs may still be reading the status
+		// word above), not only into the staged copy: when the host has already queued k4_filter / k4_contain /
+		// k_tail2 behind this launch they must see it and do nothing.
+		TAIL_SYNC();
+		if (ctid == 0) c->status |= ST_NEED_BIG;
+		TAIL_SYNC();
+		if (rank == 0) tail_stage_header(S, 0, header_only);
 		TAIL_SYNC();
 		if (ctid == 0) tail_reset_for_next_cut(S);
 		return;

@@ -100,6 +100,7 @@ struct CutCtl {
 struct DevState {
 	int d;
 	u32 cap_rows, cap_inc, cap_adj, cap_facets, cap_padj, cap_pairs, cap_tiles;
+	u32 cap_he;          // half-edges the tail kernels' scratch holds (<= B200_HE_CAP; env B200_HE_CAP lowers it, test hook)
 	u64 cap_bits;
 	double *coord;
 	u32 *row_slot, *live, *ideal;

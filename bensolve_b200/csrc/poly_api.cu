@@ -37,6 +37,8 @@ struct Handle {                 // hung off the dead `ip` field of both polytope
 	std::vector<size_t> slab_pinc, slab_padj, slab_dinc, slab_dadj; // backing store of the host lists
 	unsigned flags = 0;
 	size_t lists_cap_p = 0, lists_cap_d = 0;   // slots the host poly_list arrays are sized for
+	double prof_apply_us = 0, prof_total_us = 0;   // B200_PHASES accumulators (per polytope: several are alive at once)
+	u64 prof_calls = 0;
 };
 
 static size_t g_default_dim; // fnc_dim, bslv_poly.c:28: read by the default callback
@@ -322,7 +324,6 @@ extern "C" int poly__add_vrtx(poly_args *args)
 	P.batch_first = (u32)args->primal.cnt;
 	CutDelta dl;
 	static const bool prof = getenv("B200_PHASES") != nullptr;
-	static double t_apply_us = 0, t_total_us = 0; static u64 n_calls = 0;
 	const auto tq0 = std::chrono::steady_clock::now();
 	const std::function<void(const CutDelta &)> early = [&](const CutDelta &e) { apply_delta(args, e); };
 	h->engine->cut(P, dl, &early);
@@ -337,9 +338,9 @@ extern "C" int poly__add_vrtx(poly_args *args)
 	h->lists_current = false;
 	if (prof) {
 		const auto tq2 = std::chrono::steady_clock::now();
-		t_apply_us += std::chrono::duration<double, std::micro>(tq2 - tq1).count();
-		t_total_us += std::chrono::duration<double, std::micro>(tq2 - tq0).count();
-		if (++n_calls % 2000 == 0) fprintf(stderr, "[b200] poly__add_vrtx: apply_delta %.1f us, cut+apply %.1f us (mean of %llu calls)\n", t_apply_us / n_calls, t_total_us / n_calls, (unsigned long long)n_calls);
+		h->prof_apply_us += std::chrono::duration<double, std::micro>(tq2 - tq1).count();
+		h->prof_total_us += std::chrono::duration<double, std::micro>(tq2 - tq0).count();
+		if (++h->prof_calls % 2000 == 0) fprintf(stderr, "[b200] poly__add_vrtx: apply_delta %.1f us, cut+apply %.1f us (mean of %llu calls)\n", h->prof_apply_us / h->prof_calls, h->prof_total_us / h->prof_calls, (unsigned long long)h->prof_calls);
 	}
 	return EXIT_SUCCESS;
 	GUARD_END("poly__add_vrtx")

@@ -8,7 +8,7 @@ import pytest
 from helpers import benson_files, check_benson_fixture
 
 IDS = lambda p: p.split("/")[-1][:-5]
-FLAG_EAGER_GC, FLAG_MULTI_KERNEL, FLAG_TAIL_PHASES = 2, 4, 8
+FLAG_EAGER_GC, FLAG_MULTI_KERNEL, FLAG_TAIL_PHASES, FLAG_FORCE_WIDE = 2, 4, 8, 16
 
 
 @pytest.mark.parametrize("path", benson_files(), ids=IDS)
@@ -36,3 +36,10 @@ def test_gpu_on_benson_traces(product_lib, oracle_lib, path):
 @pytest.mark.parametrize("path", [p for p in benson_files() if "ex11" in p or "ex07" in p], ids=IDS)
 def test_gpu_multi_kernel_path_on_benson_traces(product_lib, oracle_lib, path):
     check_benson_fixture(product_lib, path, checker=oracle_lib, flags=FLAG_MULTI_KERNEL | FLAG_EAGER_GC)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", benson_files(), ids=IDS)
+def test_gpu_forced_wide_cluster_on_benson_traces(product_lib, oracle_lib, path):
+    """Every cut of the real Benson runs through the kernel variants the bench uses (k_tail<16>, grid-wide K4, k_tail2<16>)."""
+    check_benson_fixture(product_lib, path, checker=oracle_lib, flags=FLAG_FORCE_WIDE)

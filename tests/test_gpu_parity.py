@@ -248,3 +248,50 @@ def test_gpu_random_mixed_stress(product_lib, oracle_lib, seed):
     tr = [P.mixed_polyhedron, P.lattice_polytope, P.random_offsets, P.tangent_polytope][kind](d, n, int(rng.integers(1, 10 ** 6))) \
         if not (kind == 0 and d < 3) else P.tangent_polytope(d, n, seed)
     run_pair(oracle_lib, product_lib, tr, exact=True, flags_b=[0, FLAG_EAGER_GC, FLAG_MULTI_KERNEL][seed % 3])
+
+
+# ---------------------------------------------------------------- the kernel variants the bench runs
+FLAG_FORCE_WIDE = 16   # every cut through k_tail<16> / k_tail2<16> (widest cluster) + the grid-wide k4_filter / k4_contain
+
+
+@pytest.mark.parametrize("dim,n,seed", [(6, 300, 88), (5, 1500, 88)])
+def test_gpu_bench_shape_matches_reference(product_lib, checker, dim, n, seed):
+    """The bench's own shape (random tangent polytope in R^6 / R^5) at the size the reference finishes in
+    seconds: > 256 visited vertices and > 512 new rows per late cut, i.e. the wide-cluster kernels the
+    headline number runs on -- compared with the reference object, not only with invariants."""
+    tr = P.tangent_polytope(dim, n, seed)
+    a, b = capi.PolyEngine(checker, dim), capi.PolyEngine(product_lib, dim)
+    ra, rb = P.replay(a, tr), P.replay(b, tr)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+    assert sb.n_points > 25000
+
+
+@pytest.mark.parametrize("tr", stepwise_traces(), ids=lambda t: t.name)
+def test_gpu_forced_wide_cluster_after_every_cut(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, stepwise=True, exact=True, flags_b=FLAG_FORCE_WIDE)
+
+
+@pytest.mark.parametrize("tr", small_traces()[::2] + medium_traces(), ids=lambda t: t.name)
+def test_gpu_forced_wide_cluster(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, exact=True, flags_b=FLAG_FORCE_WIDE)
+
+
+@pytest.mark.parametrize("tr", medium_traces(), ids=lambda t: t.name)
+def test_gpu_forced_wide_cluster_with_compaction(product_lib, checker, tr):
+    run_pair(checker, product_lib, tr, exact=True, flags_b=FLAG_FORCE_WIDE | FLAG_EAGER_GC)
+
+
+@pytest.fixture
+def small_he_cap(monkeypatch):
+    monkeypatch.setenv("B200_HE_CAP", "48")
+
+
+@pytest.mark.parametrize("tr", medium_traces()[:6], ids=lambda t: t.name)
+def test_gpu_tail_bails_out_with_queued_followers(product_lib, checker, small_he_cap, tr):
+    """Half-edge scratch of 48 entries: most cuts bail out of the tail (ST_NEED_BIG) while k4_filter (with its
+    early-header block), k4_contain and k_tail2 are already queued behind it; they must do nothing and the cut
+    must be redone by the multi-kernel path."""
+    run_pair(checker, product_lib, tr, exact=True, flags_b=FLAG_FORCE_WIDE)
