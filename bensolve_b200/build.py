@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 PRODUCT_SO = os.path.join(HERE, "libbslv_poly_b200.so")
 EMUL_SO = os.path.join(REPO, "tests", "_emul", "libbslv_poly_emul.so")
 SOURCES = ["poly_api.cu", "cut_engine.cu"]
-HEADERS = ["cut_types.h", "cut_bodies.h", "cut_kernels.cuh", "cut_engine.h"]
+HEADERS = ["cut_types.h", "cut_bodies.h", "cut_kernels.cuh", "cut_engine.h", "wave_bodies.h", "wave_kernels.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

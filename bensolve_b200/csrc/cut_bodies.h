@@ -341,6 +341,9 @@ B200_HD void emit_edge_inc(const DevState &S, const CutParams &P, u32 v, u32 k, 
 	load_short(S.inc_pool + iov, short_inc ? niv : 0, rv);
 	load_short(S.inc_pool + iok, short_inc ? nik : 0, rk);
 	u32 w = ipos;
+	// f goes where it keeps the list sorted: last when cuts run in halfspace order, possibly earlier when a wave
+	// carried out a later halfspace first
+	bool placed = false;
 	if (short_inc) {
 		const u32 m = common_mask_short(rv, niv, rk);
 		k4_assign_short(S, rv, m, f + 1);
@@ -349,6 +352,7 @@ B200_HD void emit_edge_inc(const DevState &S, const CutParams &P, u32 v, u32 k, 
 #endif
 		for (u32 t = 0; t < B200_SHORT; t++)
 			if ((m >> t) & 1u) {
+				if (!placed && rv[t] > f) { S.inc_pool[w++] = f; placed = true; }
 				S.inc_pool[w++] = rv[t];
 				B200_ATOMIC_ADD(&S.facet_cnt[rv[t]], 1u);
 			}
@@ -358,6 +362,7 @@ B200_HD void emit_edge_inc(const DevState &S, const CutParams &P, u32 v, u32 k, 
 		while (a < niv && b < nik) {
 			const u32 x = iv[a], y = ik[b];
 			if (x == y) {
+				if (!placed && x > f) { S.inc_pool[w++] = f; placed = true; }
 				S.inc_pool[w++] = x;
 				B200_ATOMIC_ADD(&S.facet_cnt[x], 1u);
 				k4_assign_one(S, x, f + 1);
@@ -366,7 +371,7 @@ B200_HD void emit_edge_inc(const DevState &S, const CutParams &P, u32 v, u32 k, 
 			b += (y <= x);
 		}
 	}
-	S.inc_pool[w++] = f;                      // facet_cnt[f] is set once to n_new by the plan stage
+	if (!placed) S.inc_pool[w++] = f;         // facet_cnt[f] is set once to n_new by the plan stage
 	S.inc_off[nw] = ipos;
 	S.inc_len[nw] = w - ipos;
 }
@@ -419,13 +424,15 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 	const u32 *iv = S.inc_pool + S.inc_off[v];
 	const u32 niv = S.inc_len[v];
 	u32 w = ipos;
+	bool placed = false;                      // f keeps the list sorted (see emit_edge_inc)
 	for (u32 a = 0; a < niv && a < B200_MAXINC; a++)
 		if ((mask[a >> 6] >> (a & 63)) & 1) {
+			if (!placed && iv[a] > f) { S.inc_pool[w++] = f; placed = true; }
 			S.inc_pool[w++] = iv[a];
 			B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
 			k4_assign_one(S, iv[a], f + 1);
 		}
-	S.inc_pool[w++] = f;                      // facet_cnt[f] is set once to n_new by the plan stage
+	if (!placed) S.inc_pool[w++] = f;         // facet_cnt[f] is set once to n_new by the plan stage
 	S.inc_off[nw] = ipos;
 	S.inc_len[nw] = w - ipos;
 }

@@ -19,8 +19,10 @@
 
 #ifndef B200_EMULATE
 #include "cut_kernels.cuh"
+#include "wave_kernels.cuh"
 #else
 #include "cut_bodies.h"
+#include "wave_bodies.h"
 #endif
 
 // ------------------------------------------------------------------ errors
@@ -314,6 +316,7 @@ CutEngine::~CutEngine()
 	for (void *p : ptrs) dfree(p);
 	dfree(gc_totals_);
 	drop_shadow();
+	wave_free();
 #ifndef B200_EMULATE
 	for (int i = 0; i < 4; i++) if (ev_[i]) cudaEventDestroy((cudaEvent_t)ev_[i]);
 	if (pinned_hdr_) cudaFreeHost(pinned_hdr_);
@@ -1515,4 +1518,534 @@ void CutEngine::download_structure(HostStructure &o)
 	d2h(o.adj_len.data(), S_.adj_len, (size_t)n * 4);
 	d2h(o.inc_pool.data(), S_.inc_pool, (size_t)hdr_.inc_used * 4);
 	d2h(o.adj_pool.data(), S_.adj_pool, (size_t)hdr_.adj_used * 4);
+}
+
+
+// ====================================================================================================
+// Wave path: the host side.  The device schedules itself (wave_bodies.h); the host enqueues iterations a few
+// ahead, watches a progress record in mapped host memory and steps in only when the scheduler halts: a halfspace
+// that has to run alone through the classic path, a capacity that has to grow, a compaction, the end.
+// ====================================================================================================
+static u32 env_u32(const char *name, u32 dflt)
+{
+	const char *e = getenv(name);
+	return e ? (u32)strtoul(e, nullptr, 10) : dflt;
+}
+template <class T> static void wave_fresh(T *&p, size_t n)
+{
+	dfree(p);
+	p = (T *)dalloc(n * sizeof(T));
+}
+
+void CutEngine::wave_free()
+{
+	void *ptrs[] = {WD_.wc, WD_.ctl, WD_.cur, WD_.list, WD_.wflag, WD_.fin_ctr, WD_.trace, WD_.mark, WD_.rc, WD_.vis, WD_.cnt3, WD_.base3, WD_.dead_slots, WD_.he_off, WD_.he_own, WD_.he_inc,
+	                WD_.he_k, WD_.he_rank, WD_.he_incpre, WD_.he_flag, WD_.zmask, WD_.padj, WD_.new_padj_off, WD_.new_padj_len, WD_.new_parent, WD_.deg,
+	                WD_.adj_fill, WD_.adj_base, WD_.pair_a, WD_.pair_b, WD_.surv_a, WD_.surv_b, WD_.facet_epoch, WD_.facet_local, WD_.dead_facets, WD_.bits};
+	for (void *p : ptrs) dfree(p);
+#ifndef B200_EMULATE
+	if (wave_progress_) cudaFreeHost(wave_progress_);
+#else
+	free(wave_progress_);
+#endif
+	wave_progress_ = nullptr;
+	memset(&WD_, 0, sizeof WD_);
+}
+
+// (re)size the wave scratch; the stream must be idle
+void CutEngine::wave_ensure_scratch(u32 n_facets, u32 pairs_per_pos, u64 bits_per_pos)
+{
+	const size_t L = B200_WAVE_LIST, NP = B200_WAVE_MAXW, NS = B200_WAVE_SLOTS;
+	if (!WD_.wc) {
+		WD_.wc = (WaveCtl *)dalloc(sizeof(WaveCtl));
+		WD_.ctl = (CutCtl *)dalloc(NS * sizeof(CutCtl));
+		WD_.cur = (CutParams *)dalloc(NS * sizeof(CutParams));
+		WD_.list = (u32 *)dalloc(NS * L * 4);
+		WD_.wflag = (u32 *)dalloc(NS * 4);
+		WD_.fin_ctr = (u32 *)dalloc(16);
+		if (getenv("B200_WAVE_TRACE")) WD_.trace = (u64 *)dalloc(256 * 8 * 8);
+		WD_.cap_he = S_.cap_he;
+		WD_.cap_new = S_.cap_he + (u32)L;          // new rows <= half-edges + on-plane copies
+		const size_t H = WD_.cap_he, NW = WD_.cap_new;
+		WD_.vis = (u32 *)dalloc(NP * L * 4);
+		WD_.cnt3 = (u32 *)dalloc(NP * 3 * L * 4);
+		WD_.base3 = (u32 *)dalloc(NP * 3 * L * 4);
+		WD_.dead_slots = (u32 *)dalloc(NP * L * 4);
+		WD_.he_off = (u32 *)dalloc(NP * (L + 1) * 4);
+		WD_.he_own = (u32 *)dalloc(NP * H * 4);
+		WD_.he_inc = (u32 *)dalloc(NP * H * 4);
+		WD_.he_k = (u32 *)dalloc(NP * H * 4);
+		WD_.he_rank = (u32 *)dalloc(NP * H * 4);
+		WD_.he_incpre = (u32 *)dalloc(NP * H * 4);
+		WD_.he_flag = (u8 *)dalloc(NP * H);
+		WD_.zmask = (u64 *)dalloc(NP * L * (B200_MAXINC / 64) * 8);
+		WD_.padj = (u32 *)dalloc(NP * NW * 4);
+		WD_.new_padj_off = (u32 *)dalloc(NP * NW * 4);
+		WD_.new_padj_len = (u32 *)dalloc(NP * NW * 4);
+		WD_.new_parent = (u32 *)dalloc(NP * NW * 4);
+		WD_.deg = (u32 *)dalloc(NP * NW * 4);
+		WD_.adj_fill = (u32 *)dalloc(NP * NW * 4);
+		WD_.adj_base = (u32 *)dalloc(NP * NW * 4);
+#ifndef B200_EMULATE
+		CK(cudaHostAlloc((void **)&wave_progress_, sizeof(WaveProgress), cudaHostAllocMapped));
+		memset((void *)wave_progress_, 0, sizeof(WaveProgress));
+		void *dp = nullptr;
+		CK(cudaHostGetDevicePointer(&dp, (void *)wave_progress_, 0));
+		WD_.progress = (WaveProgress *)dp;
+#else
+		wave_progress_ = (WaveProgress *)calloc(1, sizeof(WaveProgress));
+		WD_.progress = wave_progress_;
+#endif
+	}
+	if (wave_rows_ < S_.cap_rows) {                // fresh marks read 0, below every tag of a live epoch
+		wave_fresh(WD_.mark, S_.cap_rows);
+		wave_rows_ = S_.cap_rows;
+	}
+	if (WD_.cap_facets < n_facets) {
+		const u32 cap = (u32)std::max<u64>(n_facets, (u64)WD_.cap_facets * 2);
+		wave_fresh(WD_.facet_epoch, NP * cap);    // tags are facet id + 1, never 0
+		wave_fresh(WD_.facet_local, NP * cap);
+		wave_fresh(WD_.dead_facets, NP * cap);
+		WD_.cap_facets = cap;
+	}
+	if (WD_.cap_pairs < pairs_per_pos) {
+		const u32 cap = (u32)std::max<u64>(pairs_per_pos, (u64)WD_.cap_pairs * 2);
+		wave_fresh(WD_.pair_a, NP * cap);
+		wave_fresh(WD_.pair_b, NP * cap);
+		wave_fresh(WD_.surv_a, NP * cap);
+		wave_fresh(WD_.surv_b, NP * cap);
+		WD_.cap_pairs = cap;
+	}
+	if (WD_.cap_bits < bits_per_pos) {
+		const u64 cap = std::max<u64>(bits_per_pos, WD_.cap_bits * 2);
+		wave_fresh(WD_.bits, NP * cap);
+		WD_.cap_bits = cap;
+	}
+}
+
+void CutEngine::wave_sync_ctl(WaveCtl &wc)
+{
+#ifndef B200_EMULATE
+	CK(cudaSetDevice(g_device));
+	CK(cudaStreamSynchronize(STREAM));
+#endif
+	d2h(&wc, WD_.wc, sizeof wc);
+	d2h(&hdr_, S_.ctl, sizeof hdr_);
+}
+void CutEngine::wave_upload_ctl(const WaveCtl &wc)
+{
+	h2d(WD_.wc, &wc, sizeof wc);
+	wave_progress_->halt = wc.halt;
+	wave_progress_->iter = wc.iter;
+	wave_progress_->done_hs = wc.done_hs;
+}
+
+#ifndef B200_EMULATE
+template <class K, class... A> static void launch_clusters(K kernel, int n_clusters, int nc, cudaStream_t st, A... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(n_clusters * nc);
+	cfg.blockDim = dim3(TAIL_THREADS);
+	cfg.stream = st;
+	cudaLaunchAttribute at[2];
+	int na = 0;
+	at[na].id = cudaLaunchAttributeClusterDimension;
+	at[na].val.clusterDim.x = nc; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+	na++;
+	if (g_pdl) {
+		at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[na].val.programmaticStreamSerializationAllowed = 1;
+		na++;
+	}
+	cfg.attrs = at; cfg.numAttrs = na;
+	CK(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+template <int D> static void launch_wave_classify(const DevState &S, const WaveDev &W, int grid, cudaStream_t st)
+{
+	launch_dependent(k_wave_classify<D>, grid, K_THREADS, st, S, W);
+}
+
+// one iteration (from_stage 0), or only its pair test + adjacency build (1), or only its adjacency build (2)
+void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigned char *d_ideal)
+{
+	const int nclu = wave_max_clusters_, gk4 = num_sms_ * 4;
+	if (from_stage == 0) {
+		launch_dependent(k_wave_la_begin, 1, 64, STREAM, S_, WD_, d_vals, d_ideal);
+		const int gcl = num_sms_ * 4;
+		switch (d_) {
+		case 2: launch_wave_classify<2>(S_, WD_, gcl, STREAM); break;
+		case 3: launch_wave_classify<3>(S_, WD_, gcl, STREAM); break;
+		case 4: launch_wave_classify<4>(S_, WD_, gcl, STREAM); break;
+		case 5: launch_wave_classify<5>(S_, WD_, gcl, STREAM); break;
+		case 6: launch_wave_classify<6>(S_, WD_, gcl, STREAM); break;
+		case 7: launch_wave_classify<7>(S_, WD_, gcl, STREAM); break;
+		case 8: launch_wave_classify<8>(S_, WD_, gcl, STREAM); break;
+		default: launch_wave_classify<0>(S_, WD_, gcl, STREAM); break;
+		}
+		launch_clusters(k_wave_form<WAVE_NC>, 1, WAVE_NC, STREAM, S_, WD_);
+		launch_clusters(k_wave_tailA<WAVE_NC>, nclu, WAVE_NC, STREAM, S_, WD_);
+		launch_clusters(k_wave_tailB<WAVE_NC>, nclu, WAVE_NC, STREAM, S_, WD_);
+		stats_.kernel_launches += 5;
+	}
+	if (from_stage == 1) { k_wave_k4_reset<<<gk4, K_THREADS, 0, STREAM>>>(S_, WD_); stats_.kernel_launches++; }
+	if (from_stage <= 1) {
+		launch_dependent(k_wave_k4_filter, gk4, K_THREADS, STREAM, S_, WD_);
+		launch_dependent(k_wave_k4_contain, num_sms_ * 8, K_THREADS, STREAM, S_, WD_);
+		stats_.kernel_launches += 2;
+	}
+	launch_clusters(k_wave_tail2<WAVE_NC>, nclu, WAVE_NC, STREAM, S_, WD_);
+	stats_.kernel_launches++;
+	CK(cudaGetLastError());
+}
+#else
+// ---- host-side test double of the wave kernels: the same bodies, run serially
+static void emu_wave_classify(const DevState &S, const WaveDev &W)
+{
+	const WaveCtl *w = W.wc;
+	if (w->halt) return;
+	for (u32 k = 0; k < w->n_la; k++)
+		for (u32 r = 0; r < w->la_rows; r++)
+			if (bit_test(S.live, r)) wave_classify_row(S, W, w->la[k], r);
+}
+static void emu_wave_form(const DevState &S, const WaveDev &W)
+{
+	WaveCtl &w = *W.wc;
+	if (w.halt) return;
+	const u32 nc = wave_candidates(w);
+	for (u32 p = 0; p < nc; p++) W.wflag[p] = W.ctl[w.pending[p]].n_list > B200_WAVE_LIST ? 2u : 0u;
+	for (u32 p = 0; p < nc; p++)
+		for (u32 e = 0, n = std::min<u32>(W.ctl[w.pending[p]].n_list, B200_WAVE_LIST); e < n; e++) wave_mark_entry(S, W, w.pending[p], p, w.epoch, e);
+	for (u32 p = 1; p < nc; p++)
+		for (u32 e = 0, n = std::min<u32>(W.ctl[w.pending[p]].n_list, B200_WAVE_LIST); e < n; e++) wave_check_entry(S, W, w.pending[p], p, w.epoch, e);
+	wave_form_finish(w, W.wflag);
+	if (w.halt) wave_publish(W, w, S.ctl->nrows, S.ctl->n_live);
+}
+static void emu_wave_tailA(const DevState &S0, const WaveDev &W)
+{
+	const WaveCtl *w = W.wc;
+	if (w->halt) return;
+	for (u32 q = 0; q < w->n_wave; q++) {
+		const DevState S = wave_view(S0, W, w->wave[q], q);
+		CutCtl *c = S.ctl;
+		const u32 n_list = c->n_list;
+		std::vector<std::pair<u32, u8>> vis;
+		u32 n_strict = 0;
+		for (u32 x = 0; x < n_list; x++) {
+			const u32 ent = S.nplist[x], row = ent & B200_WV_ROW_MASK, code = ent >> B200_WV_ROW_BITS;
+			if (!bit_test(S.live, row)) continue;
+			if ((code & 3u) >= CLS_ZERO) vis.push_back({row, (u8)(code & 3u)});
+			n_strict += (code & B200_WV_STRICT) ? 1 : 0;
+		}
+		std::sort(vis.begin(), vis.end());
+		c->status = n_strict ? 0u : (u32)ST_REDUNDANT;
+		c->n_strict = n_strict;
+		c->min_strict_row = c->min_strict_slot = B200_NONE;
+		c->n_zp = c->n_zp_projected = 0;
+		c->n_vis = n_strict ? (u32)vis.size() : 0;
+		c->n_new = c->inc_new = c->padj_new = 0;
+		c->n_minus = c->n_zero = 0;
+		c->n_pairs = c->adj_new = c->n_dead_facets = 0;
+		c->n_live_scanned = 0;
+		c->n_local = c->wl = c->mpad = c->n_surv = 0;
+		c->scratch_flag = 0;
+		if (!n_strict) { S.facet_alive[S.cur->facet] = 0; continue; }
+		u32 H = 0;
+		for (u32 i = 0; i < c->n_vis; i++) {
+			const u32 r = vis[i].first;
+			S.vis[i] = r;
+			S.cls[r] = vis[i].second;
+			S.he_off[i] = H;
+			H += S.adj_len[r];
+			for (u32 x = 0; x < (S.inc_len[r] + 63) / 64 && x < B200_MAXINC / 64; x++) S.zmask[(size_t)i * (B200_MAXINC / 64) + x] = 0;
+		}
+		S.he_off[c->n_vis] = H;
+		if (H > S.cap_he) { c->status |= ST_NEED_BIG; continue; }
+		for (u32 i = 0; i < c->n_vis; i++) he_owner_fill(S, i);
+		for (u32 e = 0; e < H; e++) he_eval(S, e);
+		u32 carry[3] = {0, 0, 0};
+		for (u32 i = 0; i < c->n_vis; i++) {
+			he_count(S, i);
+			const u8 cl = S.cls[S.vis[i]];
+			c->n_minus += (cl == CLS_MINUS);
+			c->n_zero += (cl == CLS_ZERO);
+			for (int k = 0; k < 3; k++) { S.base3[3 * (size_t)i + k] = carry[k]; carry[k] += S.cnt3[3 * (size_t)i + k]; }
+		}
+		c->n_new = carry[0]; c->inc_new = carry[1]; c->padj_new = carry[2];
+		if (carry[0] > W.cap_new || carry[2] > W.cap_new) c->status |= ST_OVF_PADJ;
+	}
+}
+static void emu_wave_tailB(const DevState &S0, const WaveDev &W)
+{
+	WaveCtl &w = *W.wc;
+	if (w.halt || w.n_wave == 0) return;
+	WaveCut cut[B200_WAVE_MAXW];
+	for (u32 q = 0; q < w.n_wave; q++) wave_gather_cut(W, w, q, cut[q]);
+	WavePlan pl;
+	wave_plan(w, cut, S0.ctl->nrows, S0.ctl->inc_used, S0.ctl->n_live, S0.cap_rows, S0.cap_inc, W.cap_bits, pl);
+	std::vector<u32> tgt;
+	for (u32 p = 0; p < w.n_pending; p++) {
+		bool done = false;
+		for (u32 q2 = 0; q2 < pl.n_commit; q2++) done |= (w.wave[q2] == w.pending[p]);
+		if (!done) tgt.push_back(w.pending[p]);
+	}
+	const u32 slot_cnt0 = S0.ctl->slot_cnt, nrows0 = S0.ctl->nrows;
+	for (u32 q = w.n_wave; q-- > 0;) {            // any order is valid: run the wave backwards here
+		const DevState S = wave_view(S0, W, w.wave[q], q);
+		CutCtl *c = S.ctl;
+		const bool redundant = (c->status & ST_REDUNDANT) != 0;
+		if (q >= pl.n_commit) {
+			if (!redundant) for (u32 i = 0; i < c->n_vis; i++) reset_class(S, i);
+			c->status |= ST_WAVE_DEFER;
+			if (q == 0) {
+				w.n_commit = 0;
+				w.halt |= pl.halt;
+				w.halt_hs = pl.halt_hs;
+				w.halt_rows = pl.need_rows;
+				w.halt_inc = pl.need_inc;
+				w.halt_bits = pl.need_bits;
+				wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live);
+			}
+			continue;
+		}
+		if (q == 0) w.n_commit = pl.n_commit;
+		c->n_live = pl.live_before[q];
+		if (redundant) continue;
+		c->nrows = pl.rows_base[q];
+		c->slot_cnt = slot_cnt0 + (pl.rows_base[q] - nrows0);
+		c->inc_used = pl.inc_base[q];
+		S.facet_cnt[S.cur->facet] = c->n_new;
+		const CutParams &P = *S.cur;
+		const u32 H = S.he_off[c->n_vis];
+		for (u32 e = H; e-- > 0;) he_emit(S, P, e);
+		for (u32 i = 0; i < c->n_vis; i++) he_finish_vertex(S, P, i);
+		for (u32 i = 0; i < c->n_vis; i++) collect_dead_facets(S, i);
+		for (u32 t : tgt)
+			for (u32 j = 0; j < c->n_new; j++) wave_classify_row(S, W, t, c->nrows + j);
+		k4_plan(S);
+		for (u64 x = 0; x < (u64)c->n_local * (c->mpad / 64); x++) k4_zero_cols(S, x);
+		for (u32 j = 0; j < c->n_new; j++) k4_build_row(S, j);
+	}
+}
+static void emu_wave_k4(const DevState &S0, const WaveDev &W, bool reset)
+{
+	const WaveCtl *w = W.wc;
+	if (w->halt) return;
+	for (u32 q = 0; q < w->n_commit; q++) {
+		const DevState S = wave_view(S0, W, w->wave[q], q);
+		CutCtl *c = S.ctl;
+		if (c->status & (ST_REDUNDANT | ST_OVF_A | ST_OVF_B | ST_ERR_DEGENERATE | ST_NEED_BIG)) continue;
+		if (reset) { c->n_surv = c->n_pairs = 0; for (u32 j = 0; j < c->n_new; j++) S.deg[j] = 0; }
+		const u32 M = c->n_new;
+		for (u32 a = 0; a < M; a++)
+			for (u32 b = a + 1; b < M; b++) k4_filter_pair(S, a, b);
+		if (c->n_surv > S.cap_pairs) continue;
+		for (u32 sv = 0; sv < c->n_surv; sv++) k4_contain_pair(S, sv);
+	}
+}
+static void emu_wave_tail2(const DevState &S0, const WaveDev &W)
+{
+	WaveCtl &w = *W.wc;
+	if (w.halt || w.n_commit == 0) return;
+	u32 base = S0.ctl->adj_used, over = 0;
+	for (u32 q = 0; q < w.n_commit; q++) {
+		const DevState S = wave_view(S0, W, w.wave[q], q);
+		CutCtl *c = S.ctl;
+		c->adj_used = base;
+		c->adj_new = 0;
+		if (c->status & ST_REDUNDANT) continue;
+		if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) over = std::max(over, std::max(c->n_pairs, c->n_surv));
+		u32 sum = 0;
+		for (u32 j = 0; j < c->n_new; j++) sum += S.new_padj_len[j] + S.deg[j];
+		c->adj_new = sum;
+		base += sum;
+	}
+	if (over) { w.halt |= WH_GROW_PAIRS; w.halt_pairs = over; wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live); return; }
+	if ((u64)base > S0.cap_adj) { w.halt |= WH_GROW_ADJ; w.halt_adj = base; wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live); return; }
+	for (u32 q = 0; q < w.n_commit; q++) {
+		const DevState S = wave_view(S0, W, w.wave[q], q);
+		CutCtl *c = S.ctl;
+		if (c->status & ST_REDUNDANT) continue;
+		u32 carry = 0;
+		for (u32 j = 0; j < c->n_new; j++) { S.adj_base[j] = carry; carry += S.new_padj_len[j] + S.deg[j]; }
+		for (u32 j = 0; j < c->n_new; j++) adj_place(S, j);
+		for (u32 p = 0; p < c->n_pairs; p++) adj_pair_fill(S, p);
+		for (u32 j = 0; j < c->n_new; j++) adj_sort(S, j);
+	}
+	WaveCut cut[B200_WAVE_MAXW];
+	int rc[B200_WAVE_MAXW];
+	const u32 n_commit = w.n_commit;
+	for (u32 q = 0; q < n_commit; q++) wave_gather_cut(W, w, q, cut[q]);
+	CutCtl m = *S0.ctl;
+	wave_commit(w, m, cut, S0.d, rc);
+	*S0.ctl = m;
+	for (u32 q = 0; q < n_commit; q++) W.rc[cut[q].hs] = rc[q];
+	wave_publish(W, w, m.nrows, m.n_live);
+}
+void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigned char *d_ideal)
+{
+	if (from_stage == 0) {
+		WaveCtl &w = *WD_.wc;
+		wave_la_plan(w, S_.ctl->nrows);
+		for (u32 k = 0; k < w.n_la; k++) wave_la_init(S_, WD_, w, k, d_vals, d_ideal);
+		emu_wave_classify(S_, WD_);
+		emu_wave_form(S_, WD_);
+		emu_wave_tailA(S_, WD_);
+		emu_wave_tailB(S_, WD_);
+	}
+	if (from_stage <= 1) emu_wave_k4(S_, WD_, from_stage == 1);
+	emu_wave_tail2(S_, WD_);
+}
+#endif
+
+long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char *d_ideal, u64 n, u32 facet0, u32 batch_first, int *rc_out)
+{
+	static const u32 min_live = env_u32("B200_WAVE_MIN_LIVE", 20000);    // below: one launch per cut (classic path) wins
+	const bool tiny_test = (flags_ & 32) != 0;                            // test hook: waves from the first halfspace on
+	const bool enabled = (env_u32("B200_WAVES", 1) != 0 || tiny_test) && !(flags_ & (4 | 64)) && nranks_ == 1 && n < B200_WV_ROW_MASK;
+	std::vector<int> rc_host(n, -1);
+	long cuts = 0;
+	u64 i = 0;
+	auto serial = [&](u64 hs) {
+		const int rc = cut_from_device(d_vals, d_ideal, hs, facet0 + (u32)hs, batch_first);
+		rc_host[hs] = rc;
+		cuts += (rc == 0);
+	};
+	while (i < n && (!enabled || (!tiny_test && hdr_.n_live < min_live))) serial(i++);
+	if (i < n) {
+		// ---- wave mode from halfspace i on
+#ifndef B200_EMULATE
+		CK(cudaSetDevice(g_device));
+		CK(cudaStreamSynchronize(STREAM));
+		if (!wave_max_clusters_) {
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3(B200_WAVE_MAXW * WAVE_NC);
+			cfg.blockDim = dim3(TAIL_THREADS);
+			cudaLaunchAttribute at[1];
+			at[0].id = cudaLaunchAttributeClusterDimension;
+			at[0].val.clusterDim.x = WAVE_NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+			cfg.attrs = at; cfg.numAttrs = 1;
+			int na = 0, nb = 0, nc2 = 0;
+			CK(cudaOccupancyMaxActiveClusters(&na, k_wave_tailA<WAVE_NC>, &cfg));
+			CK(cudaOccupancyMaxActiveClusters(&nb, k_wave_tailB<WAVE_NC>, &cfg));
+			CK(cudaOccupancyMaxActiveClusters(&nc2, k_wave_tail2<WAVE_NC>, &cfg));
+			wave_max_clusters_ = std::max(1, std::min(std::min(na, nb), std::min(nc2, (int)B200_WAVE_MAXW)));
+		}
+#else
+		wave_max_clusters_ = B200_WAVE_MAXW;
+#endif
+		ensure_facets(facet0 + (u32)n + 1);
+		{
+			// pair-test scratch of one wave position: bit matrices for a cut of up to 2048 new rows with every facet a
+			// column (grown on demand beyond that), 2^17 candidate pairs
+			const u32 wl_ub = (facet0 + (u32)n + 64) / 64;
+			wave_ensure_scratch(facet0 + (u32)n + 1, std::max<u32>(1u << 17, WD_.cap_pairs), std::max<u64>(k4_words(wl_ub, 2048, wl_ub * 64), WD_.cap_bits));
+		}
+		if (wave_rc_cap_ < n) { wave_fresh(WD_.rc, n); wave_rc_cap_ = n; }
+		WaveCtl wc;
+		memset(&wc, 0, sizeof wc);
+		wc.n_total = (u32)n;
+		wc.facet0 = facet0;
+		wc.batch_first = batch_first;
+		wc.max_wave = std::max<u32>(1, std::min<u32>(env_u32("B200_WAVE_MAX", B200_WAVE_MAXW), (u32)wave_max_clusters_));
+		wc.cand = std::max<u32>(1, std::min<u32>(env_u32("B200_WAVE_CAND", 24), B200_WAVE_SLOTS));
+		wc.in_order = env_u32("B200_WAVE_IN_ORDER", 0);
+		wc.refill_below = std::max<u32>(1, std::min<u32>(env_u32("B200_WAVE_REFILL", 20), B200_WAVE_SLOTS));
+		wc.next_hs = wc.done_hs = (u32)i;
+		wc.epoch = wave_epoch_;
+		for (u32 s = 0; s < B200_WAVE_SLOTS; s++) wc.slot_hs[s] = B200_NONE;
+		wave_upload_ctl(wc);
+		const u32 depth = std::max<u32>(1, env_u32("B200_WAVE_DEPTH", 3));
+		u32 issued = 0;                       // iterations enqueued so far (compared with the device's count of completed ones)
+		int stage = 0;
+		u64 spins = 0, halts = 0;
+		for (;;) {
+			const u32 it = wave_progress_->iter, hl = wave_progress_->halt;
+			if (!hl) {
+				if (issued - it < depth) {
+					const double te = now_us();
+					wave_enqueue(stage, d_vals, d_ideal);
+					stats_.host_us[7] += now_us() - te;
+					stage = 0;
+					issued++;
+				}
+#ifndef B200_EMULATE
+				else if ((++spins & 0xffff) == 0) {         // make sure the stream is still healthy
+					cudaError_t e = cudaStreamQuery(STREAM);
+					if (e != cudaSuccess && e != cudaErrorNotReady) fail(std::string("CUDA error while a wave was running: ") + cudaGetErrorString(e));
+					if (e == cudaSuccess && wave_progress_->iter == it && !wave_progress_->halt && issued - it >= depth)
+						fail("bensolve_b200: the wave scheduler stopped without a halt record");
+				}
+#endif
+				continue;
+			}
+			// ---- the scheduler halted: everything enqueued behind the halt returns at once
+			wave_sync_ctl(wc);
+			stats_.wave_halts++;
+			issued = wc.iter;
+			stage = 0;
+			if (wc.halt & WH_DONE) break;
+			if (++halts > 8 * n + 64) fail("bensolve_b200: the wave scheduler does not make progress");
+			if (wc.halt & WH_SERIAL) {
+				if (wc.n_pending == 0 || wc.slot_hs[wc.pending[0]] != wc.halt_hs) fail("bensolve_b200: wave scheduler state is inconsistent");
+				const u32 slot = wc.pending[0];
+				serial(wc.halt_hs);                                   // (may grow and compact)
+				stats_.wave_serial++;
+				wc.slot_hs[slot] = B200_NONE;
+				for (u32 p = 1; p < wc.n_pending; p++) wc.pending[p - 1] = wc.pending[p];
+				wc.n_pending--;
+				wc.done_hs++;
+				wc.reclassify = 1;
+			} else if (wc.halt & WH_GROW) {
+				if (wc.halt_rows > S_.cap_rows) ensure_rows((u32)std::min<u64>(0xFFFF0000ull, std::max<u64>((u64)wc.halt_rows + 4096, (u64)S_.cap_rows + S_.cap_rows / 2)));
+				if (wc.halt_inc > S_.cap_inc) ensure_inc((u32)std::min<u64>(0xFFFF0000ull, std::max<u64>(wc.halt_inc, (u64)S_.cap_inc + S_.cap_inc / 2)));
+				if (wc.halt_bits > WD_.cap_bits) wave_ensure_scratch(WD_.cap_facets, WD_.cap_pairs, wc.halt_bits);
+			} else if (wc.halt & WH_GROW_ADJ) {
+				ensure_adj(wc.halt_adj);
+				stage = 2;
+			} else if (wc.halt & WH_GROW_PAIRS) {
+				wave_ensure_scratch(WD_.cap_facets, wc.halt_pairs + wc.halt_pairs / 2, WD_.cap_bits);
+				stage = 1;
+			} else if (wc.halt & WH_COMPACT) {
+				compact();
+				wc.reclassify = 1;
+			}
+			if (wc.done_hs >= wc.n_total) break;
+			wave_ensure_scratch(WD_.cap_facets, WD_.cap_pairs, WD_.cap_bits);   // the mark array follows the row capacity
+			wc.halt = 0;
+			wave_upload_ctl(wc);
+		}
+		wave_epoch_ = wc.epoch + 1;
+		// results and statistics of the wave run
+		std::vector<int> rc_dev(n);
+		d2h(rc_dev.data(), WD_.rc, n * sizeof(int));
+		for (u64 hs = i; hs < n; hs++)
+			if (rc_host[hs] < 0) rc_host[hs] = rc_dev[hs];
+		cuts += (long)wc.st_cuts;
+		stats_.cuts += wc.st_cuts; stats_.redundant += wc.st_redundant; stats_.vertex_evals += wc.st_evals; stats_.rows_scanned += wc.st_rows_scanned;
+		stats_.minus += wc.st_minus; stats_.zero += wc.st_zero; stats_.edge_vertices += wc.st_edge; stats_.copies += wc.st_copies;
+		stats_.pair_tests += wc.st_pair_tests; stats_.new_adjacent_pairs += wc.st_pairs; stats_.algorithmic_bytes += wc.st_bytes;
+		stats_.waves += wc.st_waves; stats_.wave_cuts += wc.st_cuts + wc.st_redundant; stats_.la_passes += wc.st_la_passes; stats_.wave_deferred += wc.st_deferred;
+		small_dirty_ = true;
+		expect_vis_ = expect_m_ = 0;
+		if (WD_.trace) {            // start of each kernel of the last iterations, relative to the iteration's first kernel
+			std::vector<u64> tr(256 * 8);
+			d2h(tr.data(), WD_.trace, tr.size() * 8);
+			const u32 last = wc.iter;
+			u64 prev_first = 0;
+			for (u32 it = last > 40 ? last - 40 : 0; it < last; it++) {
+				const u64 *t = tr.data() + ((it & 255u) << 3);
+				fprintf(stderr, "[b200] trace iter %u: +%.1f |", it, prev_first ? (double)(t[0] - prev_first) / 1e3 : 0.0);
+				for (int k = 1; k < 8; k++) fprintf(stderr, " %.1f", (double)((long long)(t[k] - t[0])) / 1e3);
+				fprintf(stderr, "\n");
+				prev_first = t[0];
+			}
+		}
+		if (getenv("B200_PHASES"))
+			fprintf(stderr, "[b200] waves: %llu iterations, %llu cuts (%.2f per wave), %llu look-ahead passes, %llu deferred, %llu serial, %llu halts; device %.1f us per iteration (first to last commit), host enqueue %.1f us per iteration\n",
+			        (unsigned long long)wc.st_waves, (unsigned long long)(wc.st_cuts + wc.st_redundant), (double)(wc.st_cuts + wc.st_redundant) / std::max<u64>(1, wc.st_waves),
+			        (unsigned long long)wc.st_la_passes, (unsigned long long)wc.st_deferred, (unsigned long long)stats_.wave_serial, (unsigned long long)stats_.wave_halts,
+			        (double)(wc.t_last - wc.t_first) / 1e3 / std::max<u64>(1, wc.st_waves), stats_.host_us[7] / std::max<u64>(1, wc.st_waves));
+	}
+	if (rc_out) for (u64 hs = 0; hs < n; hs++) rc_out[hs] = rc_host[hs];
+	return cuts;
 }

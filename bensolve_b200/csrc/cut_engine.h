@@ -44,6 +44,7 @@ struct EngineStats {
 	u64 sub_ns[16] = {0};
 	double host_us[8] = {0};
 	u64 redo_loops = 0;
+	u64 waves = 0, wave_cuts = 0, la_passes = 0, wave_deferred = 0, wave_serial = 0, wave_halts = 0;   // wave path
 };
 
 class CutEngine {
@@ -65,6 +66,11 @@ public:
 	// Device-resident batch path: halfspace i of `d_vals` (device memory, [n][d], default callback
 	// meaning), no delta transfer; only the 128-byte header comes back.  Returns 1 if redundant.
 	int cut_from_device(const double *d_vals, const unsigned char *d_ideal, u64 i, u32 facet, u32 batch_first);
+	// The whole batch: halfspaces 0..n-1 of `d_vals` become facets facet0..facet0+n-1.  Small polytopes go through
+	// cut_from_device one by one; from a few 10^4 live vertices on the wave path takes over (look-ahead
+	// classification, concurrent commuting cuts; cut_types.h "Wave path").  rc_out[i] = 1 if halfspace i was
+	// redundant.  Returns the number of cuts.
+	long cut_batch_from_device(const double *d_vals, const unsigned char *d_ideal, u64 n, u32 facet0, u32 batch_first, int *rc_out);
 	void download_mirror(MirrorDump &out, u32 n_facets);
 	void dual_adjacency(const std::vector<u32> &facet_rank, u32 n_live_facets, std::vector<u32> &pair_a, std::vector<u32> &pair_b);
 	void reserve(u64 rows, u64 inc_entries, u64 adj_entries);
@@ -112,6 +118,12 @@ private:
 	void bump_seq();
 	void ensure_stage(u64 need);
 	void maybe_compact();
+	// wave path
+	void wave_ensure_scratch(u32 n_facets, u32 pairs_per_pos, u64 bits_per_pos);
+	void wave_free();
+	void wave_enqueue(int from_stage, const double *d_vals, const unsigned char *d_ideal);
+	void wave_sync_ctl(WaveCtl &wc);        // stream idle; host copies of the wave and the main control block
+	void wave_upload_ctl(const WaveCtl &wc);
 
 	int d_;
 	unsigned flags_ = 0;
@@ -144,6 +156,12 @@ private:
 	void *shadow_[11] = {nullptr};      // second set of persistent arrays: target of the next compaction
 	bool shadow_valid_ = false;
 	u32 shadow_rows_ = 0, shadow_inc_ = 0, shadow_adj_ = 0;
+	WaveDev WD_{};                 // wave path scratch (allocated on first use)
+	u32 wave_rows_ = 0;            // rows the mark array covers
+	WaveProgress *wave_progress_ = nullptr;   // mapped pinned host memory (device alias in WD_.progress)
+	u32 wave_epoch_ = 1;
+	u64 wave_rc_cap_ = 0;
+	int wave_max_clusters_ = 0;    // co-resident clusters of the per-cut wave kernels (0 = not queried yet)
 	EngineStats stats_;
 };
 

@@ -406,30 +406,23 @@ __global__ void __launch_bounds__(K_THREADS) k4_build(DevState S)
 // written the delta record's payload to mapped host memory and has completed, so that block publishes a copy of
 // the control block plus the sequence number in the EARLY header: the host applies the record to its mirror while
 // the pair test and the adjacency build are still running.
-__global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr, int early)
+// tile pairs tp0, tp0 + stride, ... of one cut's pair space (all threads of the block)
+// number of tile pairs (ta <= tb) of a cut with M new rows
+__device__ __forceinline__ u32 k4_tile_pairs(u32 M)
+{
+	const u32 nt = (M + K4_T - 1) / K4_T;
+	return nt * (nt + 1) / 2;
+}
+__device__ __forceinline__ void k4_filter_body(const DevState &S, u32 thr, u32 M, u32 wl, u32 mpad, u32 tp0, u32 stride)
 {
 	__shared__ u64 sa[K4_WCH][K4_T], sb[K4_WCH][K4_T];
 	__shared__ u32 sva[K4_SV], svb[K4_SV], nsv, gbase;
-	cudaGridDependencySynchronize();      // programmatic dependent launch: wait for the producer grid here
-	if (blockIdx.x == 0 && threadIdx.x == 0) S.dbg[13] = b200_globaltimer();
-	const CutCtl *c = S.ctl;
-	if (early && blockIdx.x == gridDim.x - 1) {
-		if (threadIdx.x < 32 && !(c->status & ST_SKIP_B)) {
-			if (threadIdx.x < sizeof(CutCtl) / 4) ((volatile u32 *)(S.stage + B200_STAGE_EARLY))[threadIdx.x] = ((const u32 *)c)[threadIdx.x];
-			__threadfence_system();
-			__syncwarp();
-			if (threadIdx.x == 0) *(volatile u32 *)(S.stage + B200_STAGE_EARLY + B200_STAGE_SEQ) = S.cur->seq;
-		}
-		return;
-	}
-	if (c->status & ST_SKIP_B) return;
-	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad;
 	const u32 nt = (M + K4_T - 1) / K4_T;
 	const u32 j = threadIdx.x & (K4_T - 1), i0 = threadIdx.x >> 6;
-	const u32 nwork = gridDim.x - (early ? 1u : 0u);
-	for (u32 tp = blockIdx.x; tp < nt * nt; tp += nwork) {
-		const u32 ta = tp / nt, tb = tp % nt;
-		if (tb < ta) continue;                       // block-uniform
+	for (u32 tp = tp0; tp < nt * (nt + 1) / 2; tp += stride) {
+		u32 ta = 0, tb = tp;                         // tp-th pair of the upper triangle, row by row (block-uniform)
+		while (tb >= nt - ta) { tb -= nt - ta; ta++; }
+		tb += ta;
 		u32 cnt[K4_T / 4];
 #pragma unroll
 		for (int k = 0; k < K4_T / 4; k++) cnt[k] = 0;
@@ -471,6 +464,23 @@ __global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr, int 
 			if (gbase + q < S.cap_pairs) { S.surv_a[gbase + q] = sva[q]; S.surv_b[gbase + q] = svb[q]; }
 		__syncthreads();
 	}
+}
+__global__ void __launch_bounds__(K_THREADS) k4_filter(DevState S, u32 thr, int early)
+{
+	cudaGridDependencySynchronize();      // programmatic dependent launch: wait for the producer grid here
+	if (blockIdx.x == 0 && threadIdx.x == 0) S.dbg[13] = b200_globaltimer();
+	const CutCtl *c = S.ctl;
+	if (early && blockIdx.x == gridDim.x - 1) {
+		if (threadIdx.x < 32 && !(c->status & ST_SKIP_B)) {
+			if (threadIdx.x < sizeof(CutCtl) / 4) ((volatile u32 *)(S.stage + B200_STAGE_EARLY))[threadIdx.x] = ((const u32 *)c)[threadIdx.x];
+			__threadfence_system();
+			__syncwarp();
+			if (threadIdx.x == 0) *(volatile u32 *)(S.stage + B200_STAGE_EARLY + B200_STAGE_SEQ) = S.cur->seq;
+		}
+		return;
+	}
+	if (c->status & ST_SKIP_B) return;
+	k4_filter_body(S, thr, c->n_new, c->wl, c->mpad, blockIdx.x, gridDim.x - (early ? 1u : 0u));
 }
 
 // Containment test, one warp per surviving pair: the pair is adjacent iff no third new row contains
@@ -545,14 +555,36 @@ __device__ __forceinline__ bool k4_columns_verdict(const DevState &S, u32 a, u32
 		const u32 xw = x0 + lane;
 		u64 acc = 0;
 		if (xw < mw) acc = (xw + 1) * 64 <= M ? ~(u64)0 : (M > xw * 64 ? (((u64)1 << (M - xw * 64)) - 1) : 0);
-		for (u32 w = 0; w < wl; w++) {
-			u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];   // same value in every lane
-			while (m) {
-				const u32 col = w * 64 + (u32)__ffsll((long long)m) - 1;
-				m &= m - 1;
+		// narrow matrices (the usual case, <= 128 facets met by the new rows): the columns of the mask are fetched
+		// together -- a load per AND would make the test a chain of dependent L2 round trips; a simple vertex pair
+		// has d-2 of them
+		if (wl <= 2) {
+			u64 m0 = S.bits[a] & S.bits[b], m1 = wl > 1 ? (S.bits[(size_t)mpad + a] & S.bits[(size_t)mpad + b]) : 0;   // same in every lane
+			u64 v[8];
+#pragma unroll
+			for (u32 t = 0; t < 8; t++) {
+				u32 col = B200_NONE;
+				if (m0) { col = (u32)__ffsll((long long)m0) - 1; m0 &= m0 - 1; }
+				else if (m1) { col = 64 + (u32)__ffsll((long long)m1) - 1; m1 &= m1 - 1; }
+				v[t] = (col != B200_NONE && xw < mw) ? tb[(size_t)col * mw + xw] : ~(u64)0;
+			}
+#pragma unroll
+			for (u32 t = 0; t < 8; t++) acc &= v[t];
+			while (m0 | m1) {                      // more than 8 common facets (degenerate pairs)
+				u32 col;
+				if (m0) { col = (u32)__ffsll((long long)m0) - 1; m0 &= m0 - 1; }
+				else { col = 64 + (u32)__ffsll((long long)m1) - 1; m1 &= m1 - 1; }
 				if (xw < mw) acc &= tb[(size_t)col * mw + xw];
 			}
-		}
+		} else
+			for (u32 w = 0; w < wl; w++) {
+				u64 m = S.bits[(size_t)w * mpad + a] & S.bits[(size_t)w * mpad + b];   // same value in every lane
+				while (m) {
+					const u32 col = w * 64 + (u32)__ffsll((long long)m) - 1;
+					m &= m - 1;
+					if (xw < mw) acc &= tb[(size_t)col * mw + xw];
+				}
+			}
 		if ((a >> 6) == xw) acc &= ~((u64)1 << (a & 63));
 		if ((b >> 6) == xw) acc &= ~((u64)1 << (b & 63));
 		other = __any_sync(0xffffffffu, acc != 0);
@@ -566,13 +598,13 @@ __device__ __forceinline__ void k4_contain_warp(const DevState &S, const u64 *, 
 }
 
 template <bool COLUMNS>
-__device__ __forceinline__ void contain_block_rounds(const DevState &S, u32 *pra, u32 *prb, u32 &npr, u32 &pbase)
+__device__ __forceinline__ void contain_block_rounds(const DevState &S, u32 *pra, u32 *prb, u32 &npr, u32 &pbase, u32 bid, u32 nblocks)
 {
 	const CutCtl *c = S.ctl;
 	const u32 M = c->n_new, wl = c->wl, mpad = c->mpad, ns = c->n_surv;
 	const u32 lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
 	// adjacent pairs of a block round are collected in shared memory; one global atomic per round
-	for (u32 s0 = blockIdx.x * wpb; s0 < ns; s0 += gridDim.x * wpb) {   // block-uniform trip count
+	for (u32 s0 = bid * wpb; s0 < ns; s0 += nblocks * wpb) {   // block-uniform trip count
 		const u32 s = s0 + (threadIdx.x >> 5);
 		bool adj = false;
 		u32 a = 0, b = 0;
@@ -608,7 +640,7 @@ __global__ void __launch_bounds__(K_THREADS) k4_contain(DevState S)
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	if (c->n_surv > S.cap_pairs) return;             // overflow is flagged by k_adj_scan
-	contain_block_rounds<true>(S, pra, prb, npr, pbase);
+	contain_block_rounds<true>(S, pra, prb, npr, pbase, blockIdx.x, gridDim.x);
 }
 // K6 keeps the row-scan form: its columns are the 10^5..10^6 live vertices
 __global__ void __launch_bounds__(K_THREADS) k6_contain(DevState S)
@@ -617,7 +649,7 @@ __global__ void __launch_bounds__(K_THREADS) k6_contain(DevState S)
 	const CutCtl *c = S.ctl;
 	if (c->status & ST_SKIP_B) return;
 	if (c->n_surv > S.cap_pairs) return;
-	contain_block_rounds<false>(S, pra, prb, npr, pbase);
+	contain_block_rounds<false>(S, pra, prb, npr, pbase, blockIdx.x, gridDim.x);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_adj_scan(DevState S)

@@ -59,6 +59,7 @@ struct CutParams {
 	u32 batch_first; // primal.cnt when the host mirror was last coherent (sltn inheritance roots, bslv_poly.c:583-587)
 	u32 seq;         // sequence number the device publishes in the staged header when the record is complete
 	u32 pad;
+	double h1;       // sum |h_j| (wave path only: scale of the guard band of the look-ahead classification)
 };
 
 // Counters shared by the kernels of one cut; the host reads it back once per cut.
@@ -146,3 +147,101 @@ struct DevState {
 #define B200_K4_SMALL 256u
 #define B200_XCHG_CAP 4096u   // most non-PLUS rows one rank can report per cut (else the multi-kernel path runs unsharded)
 #define B200_XCHG_WORDS (4u + B200_XCHG_CAP)  // header {n_strict, min_strict_row, n_zp, n_entries} + entries (row | class << 30) // most new vertices whose pair test the single-CTA tail does itself
+
+
+// ====================================================================================================
+// Wave path (device-resident batches): look-ahead classification + concurrent independent cuts.
+//
+// The halfspaces of a batch are all known, so (1) ONE pass over the coordinates classifies every row against
+// up to B200_WAVE_SLOTS pending halfspaces (look-ahead K1) and keeps, per halfspace, the short list of rows that
+// are not safely PLUS; each later cut classifies only the few hundred rows it creates against the halfspaces
+// still pending; (2) cuts whose neighbourhoods do not touch commute, so a *wave* of such cuts runs concurrently,
+// one thread-block cluster per cut, through the same phases as a single cut.  DESIGN.md section 4 has the proof
+// sketch of the commutation rule (guard band, footprint marks).
+// ====================================================================================================
+#define B200_WAVE_SLOTS 32u      // pending halfspaces that hold a look-ahead list
+#define B200_WAVE_MAXW 16u       // most cuts in one wave (also bounded by the co-resident clusters of the device)
+#define B200_WAVE_LIST B200_VIS_MAX   // entries per look-ahead list (longer: that cut runs alone through the classic path)
+// list entry = row | code << 28; code bits 0-1 = class (CLS_PLUS here means: PLUS, but inside the guard band -- listed
+// for the conflict test only), bit 2 = strictly violated (t < thr - eps, the trigger of bslv_poly.c:126)
+#define B200_WV_ROW_BITS 28
+#define B200_WV_ROW_MASK 0x0FFFFFFFu
+#define B200_WV_STRICT 4u
+#define B200_WV_GUARD 1e-7       // relative width of the guard band (rounding errors of a new vertex are ~1e-15 relative)
+
+enum : u32 {                     // WaveCtl::halt
+	WH_DONE = 1u,                // every halfspace of the batch is processed
+	WH_SERIAL = 2u,              // halfspace halt_hs must run alone through the classic path (ZERO+ rows, list / half-edge / scratch overflow)
+	WH_GROW = 4u,                // rows / incidence pool too small for the next wave: halt_rows / halt_inc say how much is needed
+	WH_GROW_ADJ = 8u,            // adjacency pool too small: grow, then redo only the adjacency build of this wave
+	WH_COMPACT = 16u,            // dead rows outnumber live ones: compact, rebuild the look-ahead lists
+	WH_GROW_PAIRS = 32u          // pair buffers of a wave position too small: grow, then redo the pair test and the adjacency build
+};
+#define ST_WAVE_DEFER 2048u      // (CutCtl::status, wave path) this cut goes back to the pending list untouched
+
+struct WaveCtl {
+	// ---- batch description (host-written)
+	u32 n_total;                 // halfspaces in the batch
+	u32 facet0;                  // dual slot of halfspace 0
+	u32 batch_first;
+	u32 max_wave;                // <= B200_WAVE_MAXW: clusters the tail kernels are launched with
+	u32 cand;                    // pending slots examined when a wave is formed
+	u32 in_order;                // 1: a wave is a run of consecutive pending cuts (stops at the first conflict); 0: conflicting cuts are skipped
+	u32 refill_below;            // a look-ahead pass runs when fewer slots than this are pending
+	// ---- scheduler state
+	u32 next_hs;                 // next halfspace without a slot
+	u32 done_hs;                 // halfspaces processed
+	u32 n_pending;
+	u32 pending[B200_WAVE_SLOTS];   // slot ids, ascending halfspace index
+	u32 slot_hs[B200_WAVE_SLOTS];   // halfspace held by a slot, B200_NONE = free
+	u32 n_la;
+	u32 la[B200_WAVE_SLOTS];        // slots the next look-ahead pass classifies
+	u32 la_rows;                 // rows that pass covers
+	u32 reclassify;              // all pending lists are stale (serial cut, compaction): the next pass rebuilds them
+	u32 n_wave;
+	u32 wave[B200_WAVE_MAXW];       // slots of the current wave, ascending halfspace index
+	u32 n_commit;                // wave positions [0, n_commit) are carried out, the others deferred
+	u32 epoch;                   // tag of the footprint marks
+	u32 iter;                    // completed wave iterations
+	u32 halt, halt_hs, halt_rows, halt_inc, halt_adj, halt_pairs;
+	u32 la_new;                  // bit k: entry k of `la` is a halfspace that just received its slot (parameters to be built)
+	u32 pad0;
+	u64 halt_bits;
+	// ---- statistics (same meaning as EngineStats)
+	u64 st_cuts, st_redundant, st_evals, st_rows_scanned, st_minus, st_zero, st_edge, st_copies, st_pair_tests, st_pairs, st_bytes;
+	u64 st_waves, st_la_passes, st_deferred;
+	u64 t_first, t_last;         // %globaltimer of the first and the latest commit (diagnostics)
+};
+// The kernels stage WaveCtl in shared memory, let one thread work on the copy and write it back with all threads
+// (a single thread walking global memory pays a full round trip per access); what is updated with atomics
+// therefore lives outside it (WaveDev::wflag, WaveDev::fin_ctr).
+struct WaveCut {                 // what the plan and the commit need of one cut of the wave (gathered by parallel threads)
+	u32 status, n_new, inc_new, n_minus, n_zero, n_pairs, n_surv, adj_new, live_before, facet, hs, slot;
+};
+
+struct WaveProgress {            // mapped pinned host memory, written by the last kernel of an iteration
+	volatile u32 iter, done_hs, halt, nrows, n_live, pad[3];
+};
+
+struct WaveDev {                 // device pointers of the wave path (kernel argument, by value)
+	WaveCtl *wc;
+	CutCtl *ctl;                 // [B200_WAVE_SLOTS] per-slot control block: look-ahead accumulators, then the cut's counters and bases
+	CutParams *cur;              // [B200_WAVE_SLOTS]
+	u32 *list;                   // [B200_WAVE_SLOTS][B200_WAVE_LIST]
+	u32 *mark;                   // [cap_rows] footprint marks (epoch << 5 | 31 - pending position)
+	int *rc;                     // [n_total] return codes (0 cut, 1 redundant)
+	u32 *wflag;                  // [B200_WAVE_SLOTS] wave formation, by pending position: bit0 conflict, bit1 must run alone
+	u32 *fin_ctr;                // clusters of the last kernel of an iteration that have finished (the last one commits)
+	u64 *trace;                  // [256][8] %globaltimer at the start of each kernel of the last 256 iterations (diagnostics, B200_WAVE_TRACE)
+	WaveProgress *progress;
+	// scratch of one cut, replicated per wave position
+	u32 *vis, *cnt3, *base3, *dead_slots, *he_off, *he_own, *he_inc, *he_k, *he_rank, *he_incpre;
+	u8 *he_flag;
+	u64 *zmask;
+	u32 *padj, *new_padj_off, *new_padj_len, *new_parent, *deg, *adj_fill, *adj_base;
+	u32 *pair_a, *pair_b, *surv_a, *surv_b, *facet_epoch, *facet_local, *dead_facets;
+	u64 *bits;
+	u32 cap_new, cap_pairs, cap_facets;   // per wave position
+	u64 cap_bits;
+	u32 cap_he;
+};

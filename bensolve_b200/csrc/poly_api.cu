@@ -912,14 +912,9 @@ extern "C" long b200_poly_add_batch_device(poly_args *a, const double *d_vals, c
 		h->engine->reupload_coords(a->primal.data, a->primal.cnt);
 		h->host_may_have_edited = false;
 	}
-	long cuts = 0;
 	const auto t0 = std::chrono::steady_clock::now();
-	for (size_t i = 0; i < n; i++) {
-		const size_t f = mirror_append(D);
-		const int rc = h->engine->cut_from_device(d_vals, d_ideal, i, (u32)f, (u32)first_slot);
-		if (rc_out) rc_out[i] = rc;
-		cuts += (rc == 0);
-	}
+	for (size_t i = 0; i < n; i++) mirror_append(D);          // halfspace i becomes dual slot f0 + i whatever its fate (bslv_poly.c:109-116)
+	const long cuts = h->engine->cut_batch_from_device(d_vals, d_ideal, n, (u32)f0, (u32)first_slot, rc_out);
 	const auto t1 = std::chrono::steady_clock::now();
 	// dual rows: the points themselves (host copy of the device inputs) and their ideal flags
 	std::vector<double> hv(n * d);

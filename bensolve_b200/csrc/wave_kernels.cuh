@@ -1,0 +1,572 @@
+// sm_100a kernels of the wave path (see cut_types.h "Wave path" and wave_bodies.h).
+//
+// One iteration = one wave of commuting cuts:
+//   k_wave_la_begin   (1 thread)      decide whether a look-ahead pass runs, give free slots to the next halfspaces
+//   k_wave_classify   (whole grid)    look-ahead K1: every live row against the slots of this pass, HBM-bound,
+//                                     8*d bytes per row for up to 32 halfspaces instead of for one
+//   k_wave_form       (one cluster)   footprint marks + conflict test -> the slots of this wave
+//   k_wave_tailA      (cluster / cut) visited list, half-edges, sizes           (phases P0-P4 of k_tail)
+//   k_wave_tailB      (cluster / cut) bases, new rows, rewiring, retirement, dead facets, look-ahead lists of the
+//                                     still pending halfspaces amended with the new rows, K4 bit matrices (P5-P7)
+//   k_wave_k4_filter / k_wave_k4_contain (whole grid) pair test of all cuts of the wave
+//   k_wave_tail2      (cluster / cut) adjacency build; the cluster that finishes last commits the wave
+// Every kernel returns at once when the scheduler has halted (WaveCtl::halt): the host enqueues iterations ahead
+// without reading anything back, and only looks at a progress record in mapped host memory.
+#pragma once
+#include "cut_kernels.cuh"
+#include "wave_bodies.h"
+
+#define WV_TRACE(k) do { if (W.trace && blockIdx.x == 0 && threadIdx.x == 0) W.trace[((W.wc->iter & 255u) << 3) + (k)] = b200_globaltimer(); } while (0)
+#define WAVE_NC 8              // CTAs per cluster of the per-cut kernels: 16 clusters of 8 are co-resident on 148 SMs
+
+// all threads of the block copy `bytes` (a multiple of 4) -- the caller synchronises
+__device__ __forceinline__ void wv_copy_words(void *dst, const void *src, u32 bytes)
+{
+	for (u32 i = threadIdx.x; i < bytes / 4; i += blockDim.x) ((u32 *)dst)[i] = ((const u32 *)src)[i];
+}
+
+__global__ void __launch_bounds__(64) k_wave_la_begin(DevState S, WaveDev W, const double *vals, const unsigned char *ideal)
+{
+	__shared__ WaveCtl w;
+	cudaGridDependencySynchronize();
+	WV_TRACE(0);
+	wv_copy_words(&w, W.wc, sizeof w);
+	__syncthreads();
+	if (threadIdx.x == 0) wave_la_plan(w, S.ctl->nrows);
+	__syncthreads();
+	if (threadIdx.x < w.n_la) wave_la_init(S, W, w, threadIdx.x, vals, ideal);
+	wv_copy_words(W.wc, &w, sizeof w);
+}
+
+// Look-ahead K1.  Thread t of a block owns rows 2t, 2t+1 of a 512-row group (one double2 load per coordinate, a
+// contiguous 512-byte run per warp); the coordinates stay in registers while the halfspaces of the pass, staged in
+// shared memory, are evaluated against them one after the other -- strict left-to-right sums of separately rounded
+// products, as bslv_poly.c:123-125 computes them.  Rows inside the guard band are appended to the slot's list.
+template <int D>
+__global__ void __launch_bounds__(K_THREADS) k_wave_classify(DevState S, WaveDev W)
+{
+	constexpr int DD = D > 0 ? D : B200_MAXD;
+	__shared__ double sh[B200_WAVE_SLOTS][DD];
+	__shared__ double s_alpha[B200_WAVE_SLOTS], s_h1[B200_WAVE_SLOTS], s_thr[B200_WAVE_SLOTS][6];
+	__shared__ u32 s_slot[B200_WAVE_SLOTS];
+	cudaGridDependencySynchronize();
+	WV_TRACE(1);
+	const WaveCtl *w = W.wc;
+	const u32 n_la = w->n_la;
+	if (w->halt || n_la == 0) return;
+	const int d = D > 0 ? D : S.d;
+	for (u32 x = threadIdx.x; x < n_la; x += K_THREADS) {
+		const u32 slot = w->la[x];
+		const CutParams &P = W.cur[slot];
+		s_slot[x] = slot;
+		for (int j = 0; j < d; j++) sh[x][j] = P.h[j];
+		s_alpha[x] = P.alpha;
+		s_h1[x] = P.h1;
+		s_thr[x][0] = P.hi[0]; s_thr[x][1] = P.hi[1]; s_thr[x][2] = P.mid[0]; s_thr[x][3] = P.mid[1]; s_thr[x][4] = P.lo[0]; s_thr[x][5] = P.lo[1];
+	}
+	__syncthreads();
+	const size_t cap = S.cap_rows;
+	const u32 nrows = w->la_rows, ngroups = (nrows + 2 * K_THREADS - 1) / (2 * K_THREADS);
+	for (u32 g = blockIdx.x; g < ngroups; g += gridDim.x) {
+		const u32 r = g * 2 * K_THREADS + 2 * threadIdx.x;
+		const u32 lw = S.live[r >> 5] >> (r & 31), iw = S.ideal[r >> 5] >> (r & 31);
+		double2 x[DD];
+#pragma unroll
+		for (int j = 0; j < DD; j++)
+			if (j < d) x[j] = *reinterpret_cast<const double2 *>(S.coord + j * cap + r);
+		if (!(lw & 3u)) continue;
+		double xi0 = 0, xi1 = 0;
+#pragma unroll
+		for (int j = 0; j < DD; j++)
+			if (j < d) { xi0 = fmax(xi0, fabs(x[j].x)); xi1 = fmax(xi1, fabs(x[j].y)); }
+		for (u32 k = 0; k < n_la; k++) {
+			double t0 = __dmul_rn(sh[k][0], x[0].x), t1 = __dmul_rn(sh[k][0], x[0].y);
+#pragma unroll
+			for (int j = 1; j < DD; j++)
+				if (j < d) {
+					t0 = __dadd_rn(t0, __dmul_rn(sh[k][j], x[j].x));
+					t1 = __dadd_rn(t1, __dmul_rn(sh[k][j], x[j].y));
+				}
+			const double t[2] = {t0, t1}, xi[2] = {xi0, xi1};
+#pragma unroll
+			for (int s = 0; s < 2; s++) {
+				if (!((lw >> s) & 1u)) continue;
+				const int id = (iw >> s) & 1u;
+				const double thr = id ? 0.0 : s_alpha[k];
+				const double g2 = B200_WV_GUARD * (fabs(thr) + s_h1[k] * xi[s]);
+				if (t[s] > s_thr[k][id] + g2) continue;                                   // safely PLUS
+				u32 code = t[s] > s_thr[k][id] ? CLS_PLUS : t[s] > s_thr[k][2 + id] ? CLS_ZP : t[s] > s_thr[k][4 + id] ? CLS_ZERO : CLS_MINUS;
+				if (t[s] < s_thr[k][4 + id]) code |= B200_WV_STRICT;
+				wave_list_append(W, s_slot[k], r + s, code);
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------- wave formation (one cluster)
+template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_form(DevState S, WaveDev W)
+{
+	__shared__ WaveCtl w;
+	__shared__ u32 off[B200_WAVE_SLOTS + 1], nl[B200_WAVE_SLOTS], fl[B200_WAVE_SLOTS];
+	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
+	cudaGridDependencySynchronize();
+	WV_TRACE(2);
+	wv_copy_words(&w, W.wc, sizeof w);
+	__syncthreads();
+	if (w.halt) return;
+	const u32 nc = wave_candidates(w);
+	if (threadIdx.x < nc) {
+		const u32 n = W.ctl[w.pending[threadIdx.x]].n_list;
+		nl[threadIdx.x] = min(n, (u32)B200_WAVE_LIST);
+		if (rank == 0) W.wflag[threadIdx.x] = n > B200_WAVE_LIST ? 2u : 0u;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		u32 t = 0;
+		for (u32 p = 0; p < nc; p++) { off[p] = t; t += nl[p]; }
+		off[nc] = t;
+	}
+	__syncthreads();
+	TAIL_SYNC();
+	const u32 total = off[nc], epoch = w.epoch;
+	// marks: the rows of every candidate's list and their neighbours
+	TAIL_LOOP(x, total) {
+		u32 p = 0;
+		while (off[p + 1] <= x) p++;
+		wave_mark_entry(S, W, w.pending[p], p, epoch, x - off[p]);
+	}
+	TAIL_SYNC();
+	// a candidate conflicts when a row of its list carries the mark of an earlier candidate
+	TAIL_LOOP(x, total) {
+		u32 p = 0;
+		while (off[p + 1] <= x) p++;
+		if (p) wave_check_entry(S, W, w.pending[p], p, epoch, x - off[p]);
+	}
+	TAIL_SYNC();
+	if (rank == 0) {
+		if (threadIdx.x < nc) fl[threadIdx.x] = __ldcg(W.wflag + threadIdx.x);
+		__syncthreads();
+		if (threadIdx.x == 0) wave_form_finish(w, fl);
+		__syncthreads();
+		wv_copy_words(W.wc, &w, sizeof w);
+		if (w.halt && threadIdx.x == 0) wave_publish(W, w, S.ctl->nrows, S.ctl->n_live);
+	}
+}
+
+// ---------------------------------------------------------------- per-cut kernels: one cluster per cut of the wave
+// phases P0-P4 of k_tail on the slot's look-ahead list; nothing shared is mutated except the class bytes of the
+// visited rows (undone if the cut is deferred)
+template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tailA(DevState S0, WaveDev W)
+{
+	__shared__ u32 ws[99];
+	__shared__ u32 slist[B200_VIS_MAX];
+	__shared__ u32 soff[B200_VIS_MAX + 1];
+	__shared__ u32 s_nvis, s_nstrict;
+	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x, q = blockIdx.x / NC;
+	cudaGridDependencySynchronize();
+	WV_TRACE(3);
+	const WaveCtl *w = W.wc;
+	if (w->halt || q >= w->n_wave) return;
+	const u32 slot = w->wave[q];
+	const DevState S = wave_view(S0, W, slot, q);
+	CutCtl *c = S.ctl;
+	// ---- P0: stage the list; visited rows = live entries classed ZERO or MINUS; trigger = a live strictly violated row
+	const u32 n_list = c->n_list;                  // <= B200_WAVE_LIST (longer lists never join a wave)
+	if (threadIdx.x == 0) { s_nvis = 0; s_nstrict = 0; }
+	__syncthreads();
+	{
+		u32 nv = 0, ns = 0;
+		for (u32 x = threadIdx.x; x < n_list; x += TAIL_THREADS) {
+			const u32 ent = S.nplist[x], row = ent & B200_WV_ROW_MASK, code = ent >> B200_WV_ROW_BITS;
+			const bool alive = bit_test(S.live, row);
+			const bool visited = alive && (code & 3u) >= CLS_ZERO;
+			slist[x] = visited ? row : B200_NONE;
+			nv += visited;
+			ns += alive && (code & B200_WV_STRICT);
+		}
+		nv = __reduce_add_sync(0xffffffffu, nv);
+		ns = __reduce_add_sync(0xffffffffu, ns);
+		if ((threadIdx.x & 31) == 0) { if (nv) atomicAdd(&s_nvis, nv); if (ns) atomicAdd(&s_nstrict, ns); }
+	}
+	__syncthreads();
+	const u32 n_vis = s_nvis, n_strict = s_nstrict;
+	if (ctid == 0) {
+		c->status = n_strict ? 0u : (u32)ST_REDUNDANT;
+		c->n_strict = n_strict;
+		c->min_strict_row = c->min_strict_slot = B200_NONE;
+		c->n_zp = c->n_zp_projected = 0;
+		c->n_vis = n_strict ? n_vis : 0;
+		c->n_new = c->inc_new = c->padj_new = 0;
+		c->n_minus = c->n_zero = 0;
+		c->n_pairs = c->adj_new = c->n_dead_facets = 0;
+		c->n_live_scanned = 0;
+		c->n_local = c->wl = c->mpad = c->n_surv = 0;
+		c->scratch_flag = 0;
+		if (!n_strict) S.facet_alive[S.cur->facet] = 0;        // nothing to cut: redundant (bslv_poly.c:132-136)
+	}
+	if (!n_strict) return;                                      // (every CTA of the cluster sees the same count)
+	if (n_vis > n_strict) TAIL_LOOP(x, n_vis * (B200_MAXINC / 64)) S.zmask[x] = 0;
+	{
+		// rank sort into the ascending visited list; CTA 0 also marks the classes
+		const u32 per = (n_list + NC - 1) / NC, e0 = rank * per, e1 = min(n_list, e0 + per);
+		const u32 part = threadIdx.x & 7;
+		for (u32 eb = e0; eb < e1; eb += TAIL_THREADS / 8) {      // block-uniform trip count
+			const u32 i = eb + (threadIdx.x >> 3);
+			const u32 key = i < e1 ? slist[i] : B200_NONE;
+			u32 rk = 0;
+			for (u32 x = part; x < n_list; x += 8) rk += (slist[x] < key);
+			rk += __shfl_xor_sync(0xffffffffu, rk, 1);
+			rk += __shfl_xor_sync(0xffffffffu, rk, 2);
+			rk += __shfl_xor_sync(0xffffffffu, rk, 4);
+			if (part == 0 && key != B200_NONE) {
+				S.vis[rk] = key;
+				S.cls[key] = (u8)((S.nplist[i] >> B200_WV_ROW_BITS) & 3u);
+			}
+		}
+	}
+	TAIL_SYNC();
+	// ---- P2: half-edge offsets (every CTA, into shared memory)
+	for (u32 x = threadIdx.x; x < n_vis; x += TAIL_THREADS) slist[x] = S.vis[x];
+	u32 H = 0;
+	for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
+		u32 i = base + threadIdx.x, v = 0, tot;
+		if (i < n_vis) v = S.adj_len[slist[i]];
+		u32 e = block_excl_scan(v, ws, tot);
+		if (i < n_vis) {
+			soff[i] = H + e;
+			if (rank == 0) S.he_off[i] = H + e;
+		}
+		H += tot;
+	}
+	if (threadIdx.x == 0) {
+		soff[n_vis] = H;
+		if (rank == 0) S.he_off[n_vis] = H;
+	}
+	__syncthreads();
+	if (H > S.cap_he) {                          // too large for the scratch of a wave position: runs alone
+		if (ctid == 0) c->status |= ST_NEED_BIG;
+		return;
+	}
+	// ---- P3: evaluate every (visited vertex, neighbour) pair
+	TAIL_SPREAD(e, H) {
+		u32 lo = 0, hi = n_vis;
+		while (hi - lo > 1) {
+			const u32 mid = (lo + hi) >> 1;
+			if (soff[mid] <= e) lo = mid;
+			else hi = mid;
+		}
+		S.he_own[e] = lo;
+		he_eval_at(S, e, lo, slist[lo], soff[lo]);
+	}
+	TAIL_SYNC();
+	// ---- P4a: sizes per visited vertex
+	{
+		u32 nm = 0, nz = 0;
+		bool bad = false;
+		TAIL_SPREAD(i, n_vis) {
+			const u32 v = slist[i];
+			const u8 cl = S.cls[v];
+			u32 cnt[3];
+			bad |= !he_count_core(S, i, v, cl, soff[i], soff[i + 1], cnt);
+			S.cnt3[3 * (size_t)i + 0] = cnt[0];
+			S.cnt3[3 * (size_t)i + 1] = cnt[1];
+			S.cnt3[3 * (size_t)i + 2] = cnt[2];
+			nm += (cl == CLS_MINUS);
+			nz += (cl == CLS_ZERO);
+		}
+		nm = __reduce_add_sync(0xffffffffu, nm);
+		nz = __reduce_add_sync(0xffffffffu, nz);
+		if ((threadIdx.x & 31) == 0) {
+			if (nm) atomicAdd(&c->n_minus, nm);
+			if (nz) atomicAdd(&c->n_zero, nz);
+		}
+		if (bad) atomicOr(&c->status, (u32)ST_ERR_DEGENERATE);
+	}
+	TAIL_SYNC();
+	// ---- P4b: offsets (CTA 0 stores them; k_wave_tailB reads them after the launch boundary)
+	if (rank == 0) {
+		u32 carry[3] = {0, 0, 0};
+		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
+			const u32 i = base + threadIdx.x;
+			u32 v3[3] = {0, 0, 0}, e3[3], tot3[3];
+			if (i < n_vis) {
+#pragma unroll
+				for (int k = 0; k < 3; k++) v3[k] = S.cnt3[3 * (size_t)i + k];
+			}
+			block_excl_scan3(v3, ws, e3, tot3);
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				if (i < n_vis) S.base3[3 * (size_t)i + k] = carry[k] + e3[k];
+				carry[k] += tot3[k];
+			}
+		}
+		if (threadIdx.x == 0) {
+			c->n_new = carry[0];
+			c->inc_new = carry[1];
+			c->padj_new = carry[2];
+			if (carry[0] > W.cap_new || carry[2] > W.cap_new) atomicOr(&c->status, (u32)ST_OVF_PADJ);
+		}
+	}
+}
+
+// phases P5-P7 of k_tail for the cuts that are carried out, at the bases wave_plan gives them
+template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tailB(DevState S0, WaveDev W)
+{
+	__shared__ WaveCtl w;
+	__shared__ WaveCut cut[B200_WAVE_MAXW];
+	__shared__ WavePlan pl;
+	__shared__ u32 tgt[B200_WAVE_SLOTS], n_tgt;
+	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x, q = blockIdx.x / NC;
+	cudaGridDependencySynchronize();
+	WV_TRACE(4);
+	wv_copy_words(&w, W.wc, sizeof w);
+	__syncthreads();
+	if (w.halt || q >= w.n_wave) return;
+	if (threadIdx.x < w.n_wave) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);
+	if (threadIdx.x == 32) n_tgt = 0;
+	__syncthreads();
+	if (threadIdx.x == 0) wave_plan(w, cut, S0.ctl->nrows, S0.ctl->inc_used, S0.ctl->n_live, S0.cap_rows, S0.cap_inc, W.cap_bits, pl);
+	__syncthreads();
+	// look-ahead lists the new rows of this cut are classified into: every pending slot this wave does not carry out
+	if (threadIdx.x < w.n_pending) {
+		const u32 s2 = w.pending[threadIdx.x];
+		bool done = false;
+		for (u32 q2 = 0; q2 < pl.n_commit; q2++) done |= (w.wave[q2] == s2);
+		if (!done) tgt[atomicAdd(&n_tgt, 1u)] = s2;
+	}
+	__syncthreads();
+	const u32 slot = w.wave[q];
+	const DevState S = wave_view(S0, W, slot, q);
+	CutCtl *c = S.ctl;
+	const bool redundant = (cut[q].status & ST_REDUNDANT) != 0;
+	if (q >= pl.n_commit) {                         // deferred: back to the pending list untouched
+		if (!redundant) TAIL_SPREAD(i, c->n_vis) reset_class(S, i);
+		if (ctid == 0) {
+			c->status |= ST_WAVE_DEFER;
+			if (q == 0) {                           // not even the first cut of the wave fits: the host has to act
+				WaveCtl *g = W.wc;
+				g->n_commit = 0;
+				g->halt |= pl.halt;
+				g->halt_hs = pl.halt_hs;
+				g->halt_rows = pl.need_rows;
+				g->halt_inc = pl.need_inc;
+				g->halt_bits = pl.need_bits;
+				w.halt |= pl.halt;
+				wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live);
+			}
+		}
+		return;
+	}
+	if (ctid == 0) {
+		if (q == 0) W.wc->n_commit = pl.n_commit;
+		c->n_live = pl.live_before[q];              // (statistics)
+		if (!redundant) {
+			c->nrows = pl.rows_base[q];
+			c->slot_cnt = S0.ctl->slot_cnt + (pl.rows_base[q] - S0.ctl->nrows);
+			c->inc_used = pl.inc_base[q];
+			S.facet_cnt[S.cur->facet] = cut[q].n_new;   // every new row lies on the new facet
+		}
+	}
+	if (redundant) return;
+	TAIL_SYNC();
+	const CutParams &P = *S.cur;
+	const u32 n_vis = c->n_vis, H = S.he_off[n_vis], M = c->n_new;
+	// ---- P5: new rows + rewiring (per half-edge) and copies + retirement (per vertex)
+	TAIL_SPREAD(x, 2 * H) {
+		const int part = x >= H;
+		he_emit_part(S, P, part ? x - H : x, part);
+	}
+	TAIL_SPREAD(i, n_vis) he_finish_vertex(S, P, i);
+	TAIL_SYNC();
+	// ---- P6: dead facets ‖ K4 matrix shape, clearing of the column matrix ‖ the new rows against the pending halfspaces
+	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 63) & ~63u;
+	if (ctid == 0) k4_plan(S);                      // (cannot overflow: wave_plan checked the upper bound)
+	{
+		u64 *tb = k4_tbits(S, wl, mpad);
+		for (u64 x = ctid; x < (u64)c->n_local * (mpad / 64); x += NC * TAIL_THREADS) tb[x] = 0;
+	}
+	TAIL_SPREAD(i, n_vis) collect_dead_facets(S, i);
+	{
+		const u32 first = c->nrows, nt = n_tgt;
+		for (u32 x = ctid; x < M * nt; x += NC * TAIL_THREADS) wave_classify_row(S, W, tgt[x / M], first + x % M);
+	}
+	TAIL_SYNC();
+	// ---- P7: K4 bit matrices
+	{
+		const u32 nrows = c->nrows, f = P.facet;
+		TAIL_SPREAD(j, M) k4_build_row_at(S, j, nrows, f, wl, mpad);
+	}
+}
+
+// pair test of every carried-out cut of the wave; tile pairs / survivor rounds of all cuts are dealt round-robin
+__global__ void __launch_bounds__(K_THREADS) k_wave_k4_filter(DevState S0, WaveDev W)
+{
+	__shared__ u32 s_slot[B200_WAVE_MAXW], s_M[B200_WAVE_MAXW], s_wl[B200_WAVE_MAXW], s_mpad[B200_WAVE_MAXW], s_n;
+	cudaGridDependencySynchronize();
+	WV_TRACE(5);
+	const WaveCtl *w = W.wc;
+	if (threadIdx.x == 0) s_n = w->halt ? 0u : w->n_commit;
+	if (threadIdx.x < B200_WAVE_MAXW) {              // shapes of all cuts by parallel threads (no serial walk through global memory)
+		const u32 slot = w->wave[threadIdx.x];
+		const CutCtl *c = W.ctl + (slot < B200_WAVE_SLOTS ? slot : 0);
+		s_slot[threadIdx.x] = slot;
+		s_M[threadIdx.x] = (c->status & ST_SKIP_B) ? 0u : c->n_new;
+		s_wl[threadIdx.x] = c->wl;
+		s_mpad[threadIdx.x] = c->mpad;
+	}
+	__syncthreads();
+	u32 base = 0;
+	for (u32 q = 0; q < s_n; q++) {
+		if (!s_M[q]) continue;
+		const DevState S = wave_view(S0, W, s_slot[q], q);
+		k4_filter_body(S, k4_threshold(S, true), s_M[q], s_wl[q], s_mpad[q], (blockIdx.x + gridDim.x - base % gridDim.x) % gridDim.x, gridDim.x);
+		base += k4_tile_pairs(s_M[q]);
+	}
+}
+__global__ void __launch_bounds__(K_THREADS) k_wave_k4_contain(DevState S0, WaveDev W)
+{
+	__shared__ u32 pra[K_THREADS / 32], prb[K_THREADS / 32], npr, pbase;
+	__shared__ u32 s_slot[B200_WAVE_MAXW], s_ns[B200_WAVE_MAXW], s_n;
+	cudaGridDependencySynchronize();
+	WV_TRACE(6);
+	const WaveCtl *w = W.wc;
+	if (threadIdx.x == 0) s_n = w->halt ? 0u : w->n_commit;
+	if (threadIdx.x < B200_WAVE_MAXW) {
+		const u32 slot = w->wave[threadIdx.x];
+		const CutCtl *c = W.ctl + (slot < B200_WAVE_SLOTS ? slot : 0);
+		s_slot[threadIdx.x] = slot;
+		s_ns[threadIdx.x] = ((c->status & ST_SKIP_B) || c->n_surv > W.cap_pairs) ? 0u : c->n_surv;   // k_wave_tail2 reports the overflow
+	}
+	__syncthreads();
+	u32 base = 0;
+	for (u32 q = 0; q < s_n; q++) {
+		if (!s_ns[q]) continue;
+		const DevState S = wave_view(S0, W, s_slot[q], q);
+		contain_block_rounds<true>(S, pra, prb, npr, pbase, (blockIdx.x + gridDim.x - base % gridDim.x) % gridDim.x, gridDim.x);
+		base += (s_ns[q] + K_THREADS / 32 - 1) / (K_THREADS / 32);
+	}
+}
+// before the pair test is redone with larger buffers
+__global__ void __launch_bounds__(K_THREADS) k_wave_k4_reset(DevState S0, WaveDev W)
+{
+	const WaveCtl *w = W.wc;
+	for (u32 q = 0; q < w->n_commit; q++) {
+		const DevState S = wave_view(S0, W, w->wave[q], q);
+		if (S.ctl->status & ST_SKIP_B) continue;
+		if (blockIdx.x == 0 && threadIdx.x == 0) { S.ctl->n_surv = 0; S.ctl->n_pairs = 0; }
+		B200_GRID_STRIDE(j, S.ctl->n_new) S.deg[j] = 0;
+	}
+}
+
+// adjacency build (k_tail2) at the wave's bases; the cluster that finishes last commits the wave and publishes progress
+template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail2(DevState S0, WaveDev W)
+{
+	__shared__ WaveCtl w;
+	__shared__ WaveCut cut[B200_WAVE_MAXW];
+	__shared__ CutCtl mctl;
+	__shared__ u32 ws[33];
+	__shared__ u32 s_adj[B200_WAVE_MAXW], s_last;
+	__shared__ int s_rc[B200_WAVE_MAXW];
+	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x, q = blockIdx.x / NC;
+	cudaGridDependencySynchronize();
+	WV_TRACE(7);
+	wv_copy_words(&w, W.wc, sizeof w);
+	__syncthreads();
+	if (w.halt || q >= w.n_commit) return;
+	const u32 n_commit = w.n_commit;
+	const DevState S = wave_view(S0, W, w.wave[q], q);
+	CutCtl *c = S.ctl;
+	const u32 OVF_P = 8u, OVF_A = 16u;
+	u32 total_adj = 0, over_pairs = 0;               // (thread 0 of CTA 0: what the halt record reports)
+	// ---- adjacency entries every cut of the wave appends (PLUS neighbours + new-facet neighbours of its new rows):
+	// every cluster derives all of them, so the bases need no communication
+	if (rank == 0) {
+		if (threadIdx.x < n_commit) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);
+		if (threadIdx.x < B200_WAVE_MAXW) s_adj[threadIdx.x] = 0;
+		__syncthreads();
+		{
+			// warp wid sums a share of cut q2 = wid % n_commit (the warps of one cut interleave)
+			const u32 wid = threadIdx.x >> 5, lane = threadIdx.x & 31, q2 = wid % n_commit, part = wid / n_commit;
+			const u32 nparts = (TAIL_THREADS / 32 - q2 + n_commit - 1) / n_commit;
+			if (!(cut[q2].status & ST_SKIP_B)) {
+				const DevState V = wave_view(S0, W, cut[q2].slot, q2);
+				u32 sum = 0;
+				for (u32 j = part * 32 + lane; j < cut[q2].n_new; j += nparts * 32) sum += V.new_padj_len[j] + V.deg[j];
+				sum = __reduce_add_sync(0xffffffffu, sum);
+				if (lane == 0 && sum) atomicAdd(&s_adj[q2], sum);
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			u32 base = S0.ctl->adj_used, mine = base, over = 0;
+			for (u32 q2 = 0; q2 < n_commit; q2++) {
+				if (q2 == q) mine = base;
+				base += s_adj[q2];
+				if (!(cut[q2].status & ST_SKIP_B) && (cut[q2].n_pairs > W.cap_pairs || cut[q2].n_surv > W.cap_pairs)) over = max(over, max(cut[q2].n_pairs, cut[q2].n_surv));
+			}
+			u32 fl = 0;
+			if (over) fl |= OVF_P;
+			else if ((u64)base > S0.cap_adj) fl |= OVF_A;
+			c->adj_used = mine;
+			c->adj_new = s_adj[q];
+			c->scratch_flag = fl;
+			total_adj = base;
+			over_pairs = over;
+		}
+	}
+	TAIL_SYNC();
+	const u32 fl = c->scratch_flag;
+	const bool redundant = (c->status & ST_REDUNDANT) != 0;
+	if (!fl && !redundant) {
+		if (rank == 0) {
+			const u32 n = c->n_new;
+			u32 carry = 0;
+			for (u32 base = 0; base < n; base += TAIL_THREADS) {
+				u32 j = base + threadIdx.x, v = j < n ? S.new_padj_len[j] + S.deg[j] : 0, tot;
+				u32 e = block_excl_scan(v, ws, tot);
+				if (j < n) S.adj_base[j] = carry + e;
+				carry += tot;
+			}
+		}
+		TAIL_SYNC();
+		TAIL_SPREAD(j, c->n_new) adj_place(S, j);
+		TAIL_SPREAD(p, c->n_pairs) adj_pair_fill(S, p);
+		TAIL_SYNC();
+		TAIL_SPREAD(j, c->n_new) adj_sort(S, j);
+	}
+	TAIL_SYNC();
+	if (rank != 0) return;
+	if (threadIdx.x == 0) {
+		__threadfence();
+		s_last = atomicAdd(W.fin_ctr, 1u) == n_commit - 1;
+	}
+	__syncthreads();
+	if (!s_last) return;                             // every other cluster of the wave is done: this CTA commits
+	__threadfence();
+	if (fl) {
+		if (threadIdx.x == 0) {
+			*W.fin_ctr = 0;
+			WaveCtl *g = W.wc;
+			if (fl & OVF_P) { g->halt |= WH_GROW_PAIRS; g->halt_pairs = over_pairs; w.halt |= WH_GROW_PAIRS; }
+			else { g->halt |= WH_GROW_ADJ; g->halt_adj = total_adj; w.halt |= WH_GROW_ADJ; }
+			wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live);
+		}
+		return;
+	}
+	if (threadIdx.x < n_commit) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);   // (adj_new of every cut is final now)
+	wv_copy_words(&mctl, S0.ctl, sizeof mctl);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		*W.fin_ctr = 0;
+		wave_commit(w, mctl, cut, S0.d, s_rc);
+		const u64 now = b200_globaltimer();
+		if (!w.t_first) w.t_first = now;
+		w.t_last = now;
+	}
+	__syncthreads();
+	wv_copy_words(W.wc, &w, sizeof w);
+	wv_copy_words(S0.ctl, &mctl, sizeof mctl);
+	if (threadIdx.x < n_commit) W.rc[cut[threadIdx.x].hs] = s_rc[threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x == 0) wave_publish(W, w, mctl.nrows, mctl.n_live);
+}

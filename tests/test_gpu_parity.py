@@ -295,3 +295,46 @@ def test_gpu_tail_bails_out_with_queued_followers(product_lib, checker, small_he
     early-header block), k4_contain and k_tail2 are already queued behind it; they must do nothing and the cut
     must be redone by the multi-kernel path."""
     run_pair(checker, product_lib, tr, exact=True, flags_b=FLAG_FORCE_WIDE)
+
+
+# ---------------------------------------------------------------- wave path (device-resident batches)
+FLAG_WAVES_ALWAYS = 32   # look-ahead classification + concurrent commuting cuts from the first halfspace on
+
+
+@pytest.mark.parametrize("tr", small_traces()[::2] + medium_traces(), ids=lambda t: t.name)
+@pytest.mark.parametrize("chunk", [0, 7])
+def test_gpu_wave_path(product_lib, checker, tr, chunk):
+    a, b = capi.PolyEngine(checker, tr.dim), capi.PolyEngine(product_lib, tr.dim, flags=FLAG_WAVES_ALWAYS)
+    ra, rb = P.replay(a, tr), P.replay_batched(b, tr, chunk)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+
+
+@pytest.mark.parametrize("env", [{"B200_WAVE_IN_ORDER": "1"}, {"B200_WAVE_MAX": "3", "B200_WAVE_CAND": "5", "B200_WAVE_REFILL": "2"},
+                                 {"B200_TINY_CAPS": "1"}, {"B200_HE_CAP": "48"}], ids=lambda e: "-".join(e))
+@pytest.mark.parametrize("tr", medium_traces(), ids=lambda t: t.name)
+def test_gpu_wave_path_variants(product_lib, checker, monkeypatch, env, tr):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    a, b = capi.PolyEngine(checker, tr.dim), capi.PolyEngine(product_lib, tr.dim, flags=FLAG_WAVES_ALWAYS)
+    ra, rb = P.replay(a, tr), P.replay_batched(b, tr, 0)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+
+
+@pytest.mark.parametrize("dim,n,seed", [(6, 300, 88), (5, 1500, 88), (4, 3000, 21)])
+def test_gpu_wave_path_bench_shape_matches_reference(product_lib, checker, dim, n, seed):
+    """The bench's `value` path (b200_poly_add_batch -> waves) on the bench's shape against the reference object."""
+    tr = P.tangent_polytope(dim, n, seed)
+    a, b = capi.PolyEngine(checker, dim), capi.PolyEngine(product_lib, dim, flags=FLAG_WAVES_ALWAYS)
+    ra, rb = P.replay(a, tr), P.replay_batched(b, tr, 0)
+    sa, sb = a.state(), b.state()
+    st = b.stats()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+    assert st["rows_scanned"] < st["vertex_evals"]

@@ -311,3 +311,45 @@ def test_product_fails_loudly_without_gpu(tmp_path):
     assert res.returncode != 0
     assert "UNREACHABLE" not in res.stdout
     assert "no CUDA device" in res.stderr and "no CPU fallback" in res.stderr
+
+
+# ---------------------------------------------------------------- wave path (device-resident batches)
+FLAG_WAVES_ALWAYS = 32   # look-ahead classification + concurrent commuting cuts from the first halfspace on
+
+
+@pytest.mark.parametrize("tr", small_traces()[::2] + medium_traces(), ids=lambda t: t.name)
+@pytest.mark.parametrize("chunk", [0, 7])
+def test_host_logic_wave_path(oracle_lib, emul_lib, tr, chunk):
+    """The scheduler of the wave path (look-ahead lists, footprint marks, out-of-order waves, deferral, serial
+    fall-back for ZERO+ rows, commit) on the host test double against the oracle fed one halfspace per call."""
+    a, b = capi.PolyEngine(oracle_lib, tr.dim), capi.PolyEngine(emul_lib, tr.dim, flags=FLAG_WAVES_ALWAYS)
+    ra, rb = P.replay(a, tr), P.replay_batched(b, tr, chunk)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+
+
+@pytest.mark.parametrize("env", [{"B200_WAVE_IN_ORDER": "1"}, {"B200_WAVE_MAX": "3", "B200_WAVE_CAND": "5", "B200_WAVE_REFILL": "2"},
+                                 {"B200_TINY_CAPS": "1"}, {"B200_HE_CAP": "48"}], ids=lambda e: "-".join(e))
+@pytest.mark.parametrize("tr", medium_traces(), ids=lambda t: t.name)
+def test_host_logic_wave_path_variants(oracle_lib, emul_lib, monkeypatch, env, tr):
+    """In-order waves, tiny windows, capacities that must grow mid-wave, cuts too large for a wave position."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    a, b = capi.PolyEngine(oracle_lib, tr.dim), capi.PolyEngine(emul_lib, tr.dim, flags=FLAG_WAVES_ALWAYS)
+    ra, rb = P.replay(a, tr), P.replay_batched(b, tr, 0)
+    sa, sb = a.state(), b.state()
+    a.kill(); b.kill()
+    assert ra == rb
+    capi.compare_states(sa, sb, exact_coords=True)
+
+
+def test_host_logic_wave_statistics(emul_lib):
+    tr = P.tangent_polytope(5, 400, 3)
+    e = capi.PolyEngine(emul_lib, 5, flags=FLAG_WAVES_ALWAYS)
+    rcs = P.replay_batched(e, tr, 0)
+    st = e.stats()
+    e.kill()
+    assert st["cuts"] == len(rcs) - sum(rcs) and st["vertex_evals"] > 0 and st["algorithmic_bytes"] > 0
+    assert st["rows_scanned"] < st["vertex_evals"]      # one pass over the coordinates serves many halfspaces
