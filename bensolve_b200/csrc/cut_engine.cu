@@ -1563,7 +1563,7 @@ void CutEngine::wave_ensure_scratch(u32 n_facets, u32 pairs_per_pos, u64 bits_pe
 		WD_.list = (u32 *)dalloc(NS * L * 4);
 		WD_.wflag = (u32 *)dalloc(NS * 4);
 		WD_.fin_ctr = (u32 *)dalloc(16);
-		if (getenv("B200_WAVE_TRACE")) WD_.trace = (u64 *)dalloc(256 * 8 * 8);
+		if (getenv("B200_WAVE_TRACE")) WD_.trace = (u64 *)dalloc(256 * 64 * 8);
 		WD_.cap_he = S_.cap_he;
 		WD_.cap_new = S_.cap_he + (u32)L;          // new rows <= half-edges + on-plane copies
 		const size_t H = WD_.cap_he, NW = WD_.cap_new;
@@ -1670,7 +1670,7 @@ void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigne
 {
 	const int nclu = wave_max_clusters_, gk4 = num_sms_ * 4;
 	if (from_stage == 0) {
-		launch_dependent(k_wave_la_begin, 1, 64, STREAM, S_, WD_, d_vals, d_ideal);
+		launch_dependent(k_wave_begin, 1, 64, STREAM, S_, WD_, d_vals, d_ideal);
 		const int gcl = num_sms_ * 4;
 		switch (d_) {
 		case 2: launch_wave_classify<2>(S_, WD_, gcl, STREAM); break;
@@ -1682,10 +1682,11 @@ void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigne
 		case 8: launch_wave_classify<8>(S_, WD_, gcl, STREAM); break;
 		default: launch_wave_classify<0>(S_, WD_, gcl, STREAM); break;
 		}
-		launch_clusters(k_wave_form<WAVE_NC>, 1, WAVE_NC, STREAM, S_, WD_);
+		launch_dependent(k_wave_mark, num_sms_, K_THREADS, STREAM, S_, WD_);
+		launch_dependent(k_wave_check, num_sms_, K_THREADS, STREAM, S_, WD_);
 		launch_clusters(k_wave_tailA<WAVE_NC>, nclu, WAVE_NC, STREAM, S_, WD_);
 		launch_clusters(k_wave_tailB<WAVE_NC>, nclu, WAVE_NC, STREAM, S_, WD_);
-		stats_.kernel_launches += 5;
+		stats_.kernel_launches += 6;
 	}
 	if (from_stage == 1) { k_wave_k4_reset<<<gk4, K_THREADS, 0, STREAM>>>(S_, WD_); stats_.kernel_launches++; }
 	if (from_stage <= 1) {
@@ -1839,54 +1840,60 @@ static void emu_wave_k4(const DevState &S0, const WaveDev &W, bool reset)
 		for (u32 a = 0; a < M; a++)
 			for (u32 b = a + 1; b < M; b++) k4_filter_pair(S, a, b);
 		if (c->n_surv > S.cap_pairs) continue;
-		for (u32 sv = 0; sv < c->n_surv; sv++) k4_contain_pair(S, sv);
+		for (u32 sv = 0; sv < c->n_surv; sv++) {
+			const u32 a = S.surv_a[sv], b = S.surv_b[sv];
+			if (k4_adjacent_by_columns(S, a, b, c->n_new, c->wl, c->mpad)) { wave_flag_adjacent(S, sv, a, b); c->n_pairs++; }
+		}
 	}
 }
 static void emu_wave_tail2(const DevState &S0, const WaveDev &W)
 {
 	WaveCtl &w = *W.wc;
 	if (w.halt || w.n_commit == 0) return;
-	u32 base = S0.ctl->adj_used, over = 0;
-	for (u32 q = 0; q < w.n_commit; q++) {
-		const DevState S = wave_view(S0, W, w.wave[q], q);
-		CutCtl *c = S.ctl;
-		c->adj_used = base;
-		c->adj_new = 0;
-		if (c->status & ST_REDUNDANT) continue;
-		if (c->n_pairs > S.cap_pairs || c->n_surv > S.cap_pairs) over = std::max(over, std::max(c->n_pairs, c->n_surv));
-		u32 sum = 0;
-		for (u32 j = 0; j < c->n_new; j++) sum += S.new_padj_len[j] + S.deg[j];
-		c->adj_new = sum;
-		base += sum;
-	}
-	if (over) { w.halt |= WH_GROW_PAIRS; w.halt_pairs = over; wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live); return; }
-	if ((u64)base > S0.cap_adj) { w.halt |= WH_GROW_ADJ; w.halt_adj = base; wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live); return; }
+	WaveCut cut[B200_WAVE_MAXW];
+	u32 adj_base[B200_WAVE_MAXW], adj_new[B200_WAVE_MAXW], need_adj, need_pairs;
+	for (u32 q = 0; q < w.n_commit; q++) wave_gather_cut(W, w, q, cut[q]);
+	const u32 fl = wave_adj_plan(cut, w.n_commit, S0.ctl->adj_used, S0.cap_adj, W.cap_pairs, adj_base, adj_new, need_adj, need_pairs);
+	for (u32 q = 0; q < w.n_commit; q++) { W.ctl[w.wave[q]].adj_used = adj_base[q]; W.ctl[w.wave[q]].adj_new = adj_new[q]; }
+	if (fl & 8u) { w.halt |= WH_GROW_PAIRS; w.halt_pairs = need_pairs; wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live); return; }
+	if (fl & 16u) { w.halt |= WH_GROW_ADJ; w.halt_adj = need_adj; wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live); return; }
 	for (u32 q = 0; q < w.n_commit; q++) {
 		const DevState S = wave_view(S0, W, w.wave[q], q);
 		CutCtl *c = S.ctl;
 		if (c->status & ST_REDUNDANT) continue;
 		u32 carry = 0;
 		for (u32 j = 0; j < c->n_new; j++) { S.adj_base[j] = carry; carry += S.new_padj_len[j] + S.deg[j]; }
+		if (carry != c->adj_new) fail("wave adjacency plan disagrees with the scan");
 		for (u32 j = 0; j < c->n_new; j++) adj_place(S, j);
-		for (u32 p = 0; p < c->n_pairs; p++) adj_pair_fill(S, p);
+		for (u32 sv = 0; sv < c->n_surv; sv++) adj_pair_fill_surv(S, sv);
 		for (u32 j = 0; j < c->n_new; j++) adj_sort(S, j);
 	}
-	WaveCut cut[B200_WAVE_MAXW];
-	int rc[B200_WAVE_MAXW];
+}
+static void emu_wave_begin(const DevState &S, const WaveDev &W, const double *vals, const unsigned char *ideal)
+{
+	WaveCtl &w = *W.wc;
+	if (w.halt) return;
 	const u32 n_commit = w.n_commit;
-	for (u32 q = 0; q < n_commit; q++) wave_gather_cut(W, w, q, cut[q]);
-	CutCtl m = *S0.ctl;
-	wave_commit(w, m, cut, S0.d, rc);
-	*S0.ctl = m;
-	for (u32 q = 0; q < n_commit; q++) W.rc[cut[q].hs] = rc[q];
-	wave_publish(W, w, m.nrows, m.n_live);
+	if (n_commit) {
+		WaveCut cut[B200_WAVE_MAXW];
+		int rc[B200_WAVE_MAXW];
+		for (u32 q = 0; q < n_commit; q++) wave_gather_cut(W, w, q, cut[q]);
+		CutCtl m = *S.ctl;
+		wave_commit(w, m, cut, S.d, rc);
+		*S.ctl = m;
+		for (u32 q = 0; q < n_commit; q++) W.rc[cut[q].hs] = rc[q];
+	}
+	w.iter++;
+	if (!w.halt) {
+		wave_la_plan(w, S.ctl->nrows);
+		for (u32 k = 0; k < w.n_la; k++) wave_la_init(S, W, w, k, vals, ideal);
+	}
+	wave_publish(W, w, S.ctl->nrows, S.ctl->n_live);
 }
 void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigned char *d_ideal)
 {
 	if (from_stage == 0) {
-		WaveCtl &w = *WD_.wc;
-		wave_la_plan(w, S_.ctl->nrows);
-		for (u32 k = 0; k < w.n_la; k++) wave_la_init(S_, WD_, w, k, d_vals, d_ideal);
+		emu_wave_begin(S_, WD_, d_vals, d_ideal);
 		emu_wave_classify(S_, WD_);
 		emu_wave_form(S_, WD_);
 		emu_wave_tailA(S_, WD_);
@@ -2028,14 +2035,21 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 		small_dirty_ = true;
 		expect_vis_ = expect_m_ = 0;
 		if (WD_.trace) {            // start of each kernel of the last iterations, relative to the iteration's first kernel
-			std::vector<u64> tr(256 * 8);
+			std::vector<u64> tr(256 * 64);
 			d2h(tr.data(), WD_.trace, tr.size() * 8);
 			const u32 last = wc.iter;
 			u64 prev_first = 0;
-			for (u32 it = last > 40 ? last - 40 : 0; it < last; it++) {
-				const u64 *t = tr.data() + ((it & 255u) << 3);
-				fprintf(stderr, "[b200] trace iter %u: +%.1f |", it, prev_first ? (double)(t[0] - prev_first) / 1e3 : 0.0);
-				for (int k = 1; k < 8; k++) fprintf(stderr, " %.1f", (double)((long long)(t[k] - t[0])) / 1e3);
+			for (u32 it = last > 24 ? last - 24 : 0; it < last; it++) {
+				const u64 *t = tr.data() + ((it & 255u) << 6);
+				fprintf(stderr, "[b200] trace iter %u: +%.1f | kernels", it, prev_first ? (double)(t[0] - prev_first) / 1e3 : 0.0);
+				for (int k = 1; k < 9; k++) fprintf(stderr, " %.1f", (double)((long long)(t[k] - t[0])) / 1e3);
+				const int grp[3][2] = {{16, 22}, {24, 29}, {32, 36}};
+				const int kern[3] = {4, 5, 8};
+				const char *nm[3] = {"tailA", "tailB", "tail2"};
+				for (int g = 0; g < 3; g++) {
+					fprintf(stderr, " | %s", nm[g]);
+					for (int k = grp[g][0]; k <= grp[g][1]; k++) fprintf(stderr, " %.1f", (double)((long long)(t[k] - t[kern[g]])) / 1e3);
+				}
 				fprintf(stderr, "\n");
 				prev_first = t[0];
 			}

@@ -216,7 +216,7 @@ struct WaveCtl {
 // (a single thread walking global memory pays a full round trip per access); what is updated with atomics
 // therefore lives outside it (WaveDev::wflag, WaveDev::fin_ctr).
 struct WaveCut {                 // what the plan and the commit need of one cut of the wave (gathered by parallel threads)
-	u32 status, n_new, inc_new, n_minus, n_zero, n_pairs, n_surv, adj_new, live_before, facet, hs, slot;
+	u32 status, n_new, inc_new, padj_new, n_minus, n_zero, n_pairs, n_surv, adj_new, live_before, facet, hs, slot;
 };
 
 struct WaveProgress {            // mapped pinned host memory, written by the last kernel of an iteration

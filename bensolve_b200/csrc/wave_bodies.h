@@ -232,7 +232,7 @@ B200_HD void wave_gather_cut(const WaveDev &W, const WaveCtl &w, u32 q, WaveCut 
 	const u32 slot = w.wave[q];
 	const volatile CutCtl *c = W.ctl + slot;      // (volatile: other clusters of the running kernel may just have written it)
 	o.status = c->status; o.n_new = c->n_new; o.inc_new = c->inc_new; o.n_minus = c->n_minus; o.n_zero = c->n_zero;
-	o.n_pairs = c->n_pairs; o.n_surv = c->n_surv; o.adj_new = c->adj_new; o.live_before = c->n_live;
+	o.n_pairs = c->n_pairs; o.n_surv = c->n_surv; o.adj_new = c->adj_new; o.live_before = c->n_live; o.padj_new = c->padj_new;
 	o.facet = W.cur[slot].facet;
 	o.hs = w.slot_hs[slot];
 	o.slot = slot;
@@ -274,7 +274,31 @@ B200_HD void wave_plan(const WaveCtl &w, const WaveCut *cut, u32 nrows, u32 inc_
 	}
 }
 
-// ---------------------------------------------------------------- commit (the cluster that finishes last)
+// ---------------------------------------------------------------- pair test results (wave path)
+// The containment kernel does not compact the adjacent pairs into a second list (a position per pair means an
+// atomic with a return value per block round): it flags the survivor in place; the adjacency build walks the
+// survivor list.  The number of adjacent pairs is only needed as a sum (adjacency entries = PLUS neighbours + 2 * pairs).
+#define B200_SURV_ADJ 0x80000000u
+B200_HD void wave_flag_adjacent(const DevState &S, u32 s, u32 a, u32 b)
+{
+	S.surv_a[s] = a | B200_SURV_ADJ;
+	B200_ATOMIC_ADD(&S.deg[a], 1u);
+	B200_ATOMIC_ADD(&S.deg[b], 1u);
+}
+B200_HD void adj_pair_fill_surv(const DevState &S, u32 s)
+{
+	u32 a = S.surv_a[s];
+	if (!(a & B200_SURV_ADJ)) return;
+	a &= ~B200_SURV_ADJ;
+	const u32 b = S.surv_b[s];
+	const u32 nrows = S.ctl->nrows, used = S.ctl->adj_used;
+	const u32 oa = used + S.adj_base[a] + S.new_padj_len[a], ob = used + S.adj_base[b] + S.new_padj_len[b];
+	const u32 pa = B200_ATOMIC_ADD(&S.adj_fill[a], 1u), pb = B200_ATOMIC_ADD(&S.adj_fill[b], 1u);
+	S.adj_pool[oa + pa] = nrows + b;
+	S.adj_pool[ob + pb] = nrows + a;
+}
+
+// ---------------------------------------------------------------- commit (first kernel of the next iteration)
 // On copies of the wave's and the polytope's control block; rc[q] receives the return code of wave position q.
 B200_HD void wave_commit(WaveCtl &w, CutCtl &m, const WaveCut *cut, int dim, int *rc)
 {
@@ -320,9 +344,27 @@ B200_HD void wave_commit(WaveCtl &w, CutCtl &m, const WaveCut *cut, int dim, int
 	w.n_pending = keep;
 	w.done_hs += w.n_commit;
 	w.n_wave = w.n_commit = 0;
-	w.iter++;
 	if (w.done_hs >= w.n_total) w.halt |= WH_DONE;
 	else if (m.nrows != m.n_live && m.nrows >= 4 * B200_TILE && m.nrows >= 2 * m.n_live) w.halt |= WH_COMPACT;
+}
+// adjacency entries cut q of the wave appends = PLUS neighbours of its new rows + two per adjacent pair; where each
+// cut's block starts; whether the pool / the pair buffers hold it.  flags: 8 = pair buffers, 16 = adjacency pool.
+B200_HD u32 wave_adj_plan(const WaveCut *cut, u32 n_commit, u32 adj_used, u32 cap_adj, u32 cap_pairs, u32 *adj_base, u32 *adj_new, u32 &need_adj, u32 &need_pairs)
+{
+	u32 base = adj_used, over = 0;
+	for (u32 q = 0; q < n_commit; q++) {
+		adj_base[q] = base;
+		adj_new[q] = 0;
+		if (cut[q].status & ST_REDUNDANT) continue;
+		if (cut[q].n_surv > cap_pairs) over = over > cut[q].n_surv ? over : cut[q].n_surv;
+		adj_new[q] = cut[q].padj_new + 2 * cut[q].n_pairs;
+		base += adj_new[q];
+	}
+	need_adj = base;
+	need_pairs = over;
+	if (over) return 8u;
+	if ((u64)base > cap_adj) return 16u;
+	return 0;
 }
 B200_HD void wave_publish(const WaveDev &W, const WaveCtl &w, u32 nrows, u32 n_live)
 {

@@ -1,22 +1,26 @@
 // sm_100a kernels of the wave path (see cut_types.h "Wave path" and wave_bodies.h).
 //
 // One iteration = one wave of commuting cuts:
-//   k_wave_la_begin   (1 thread)      decide whether a look-ahead pass runs, give free slots to the next halfspaces
+//   k_wave_begin      (one CTA)       commit of the previous wave (counters, return codes, pending list, progress
+//                                     record); decide whether a look-ahead pass runs, give free slots to the next halfspaces
 //   k_wave_classify   (whole grid)    look-ahead K1: every live row against the slots of this pass, HBM-bound,
 //                                     8*d bytes per row for up to 32 halfspaces instead of for one
-//   k_wave_form       (one cluster)   footprint marks + conflict test -> the slots of this wave
+//   k_wave_mark       (whole grid)    footprint marks of the candidate cuts (scattered atomics: LSU work for all SMs)
+//   k_wave_check      (whole grid)    conflict test; the block that finishes last selects the slots of this wave
 //   k_wave_tailA      (cluster / cut) visited list, half-edges, sizes           (phases P0-P4 of k_tail)
 //   k_wave_tailB      (cluster / cut) bases, new rows, rewiring, retirement, dead facets, look-ahead lists of the
 //                                     still pending halfspaces amended with the new rows, K4 bit matrices (P5-P7)
 //   k_wave_k4_filter / k_wave_k4_contain (whole grid) pair test of all cuts of the wave
-//   k_wave_tail2      (cluster / cut) adjacency build; the cluster that finishes last commits the wave
+//   k_wave_tail2      (cluster / cut) adjacency build
 // Every kernel returns at once when the scheduler has halted (WaveCtl::halt): the host enqueues iterations ahead
 // without reading anything back, and only looks at a progress record in mapped host memory.
 #pragma once
 #include "cut_kernels.cuh"
 #include "wave_bodies.h"
 
-#define WV_TRACE(k) do { if (W.trace && blockIdx.x == 0 && threadIdx.x == 0) W.trace[((W.wc->iter & 255u) << 3) + (k)] = b200_globaltimer(); } while (0)
+#define WV_TRACE(k) do { if (W.trace && blockIdx.x == 0 && threadIdx.x == 0) W.trace[((W.wc->iter & 255u) << 6) + (k)] = b200_globaltimer(); } while (0)
+// phase stamps inside a kernel (block 0 = CTA 0 of the first cluster)
+#define WV_TP(k) do { if (W.trace && blockIdx.x == 0 && threadIdx.x == 0) W.trace[((w_iter & 255u) << 6) + (k)] = b200_globaltimer(); } while (0)
 #define WAVE_NC 8              // CTAs per cluster of the per-cut kernels: 16 clusters of 8 are co-resident on 148 SMs
 
 // all threads of the block copy `bytes` (a multiple of 4) -- the caller synchronises
@@ -25,17 +29,43 @@ __device__ __forceinline__ void wv_copy_words(void *dst, const void *src, u32 by
 	for (u32 i = threadIdx.x; i < bytes / 4; i += blockDim.x) ((u32 *)dst)[i] = ((const u32 *)src)[i];
 }
 
-__global__ void __launch_bounds__(64) k_wave_la_begin(DevState S, WaveDev W, const double *vals, const unsigned char *ideal)
+__global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const double *vals, const unsigned char *ideal)
 {
 	__shared__ WaveCtl w;
+	__shared__ WaveCut cut[B200_WAVE_MAXW];
+	__shared__ CutCtl mctl;
+	__shared__ int s_rc[B200_WAVE_MAXW];
+	__shared__ u32 s_hs[B200_WAVE_MAXW];
 	cudaGridDependencySynchronize();
-	WV_TRACE(0);
+	const u64 t_begin = b200_globaltimer();
 	wv_copy_words(&w, W.wc, sizeof w);
+	wv_copy_words(&mctl, S.ctl, sizeof mctl);
 	__syncthreads();
-	if (threadIdx.x == 0) wave_la_plan(w, S.ctl->nrows);
+	if (w.halt) return;
+	// ---- the previous wave's adjacency build has completed: commit it
+	const u32 n_commit = w.n_commit;
+	if (n_commit) {
+		if (threadIdx.x < n_commit) { wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]); s_hs[threadIdx.x] = cut[threadIdx.x].hs; }
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			wave_commit(w, mctl, cut, S.d, s_rc);
+			const u64 now = b200_globaltimer();
+			if (!w.t_first) w.t_first = now;
+			w.t_last = now;
+		}
+		__syncthreads();
+		if (threadIdx.x < n_commit) W.rc[s_hs[threadIdx.x]] = s_rc[threadIdx.x];
+		wv_copy_words(S.ctl, &mctl, sizeof mctl);
+	}
+	if (threadIdx.x == 0) {
+		w.iter++;
+		if (W.trace) W.trace[(w.iter & 255u) << 6] = t_begin;
+		if (!w.halt) wave_la_plan(w, mctl.nrows);
+	}
 	__syncthreads();
-	if (threadIdx.x < w.n_la) wave_la_init(S, W, w, threadIdx.x, vals, ideal);
+	if (!w.halt && threadIdx.x < w.n_la) wave_la_init(S, W, w, threadIdx.x, vals, ideal);
 	wv_copy_words(W.wc, &w, sizeof w);
+	if (threadIdx.x == 0) wave_publish(W, w, mctl.nrows, mctl.n_live);
 }
 
 // Look-ahead K1.  Thread t of a block owns rows 2t, 2t+1 of a 512-row group (one double2 load per coordinate, a
@@ -103,23 +133,14 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_classify(DevState S, WaveDev
 	}
 }
 
-// ---------------------------------------------------------------- wave formation (one cluster)
-template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_form(DevState S, WaveDev W)
+// ---------------------------------------------------------------- wave formation (two grid-wide kernels)
+// candidate p's list occupies [off[p], off[p+1]) of a flat index space every block derives for itself
+__device__ __forceinline__ u32 wave_stage_candidates(const WaveDev &W, WaveCtl &w, u32 *off, u32 *nl)
 {
-	__shared__ WaveCtl w;
-	__shared__ u32 off[B200_WAVE_SLOTS + 1], nl[B200_WAVE_SLOTS], fl[B200_WAVE_SLOTS];
-	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x;
-	cudaGridDependencySynchronize();
-	WV_TRACE(2);
 	wv_copy_words(&w, W.wc, sizeof w);
 	__syncthreads();
-	if (w.halt) return;
-	const u32 nc = wave_candidates(w);
-	if (threadIdx.x < nc) {
-		const u32 n = W.ctl[w.pending[threadIdx.x]].n_list;
-		nl[threadIdx.x] = min(n, (u32)B200_WAVE_LIST);
-		if (rank == 0) W.wflag[threadIdx.x] = n > B200_WAVE_LIST ? 2u : 0u;
-	}
+	const u32 nc = w.halt ? 0u : wave_candidates(w);
+	if (threadIdx.x < nc) nl[threadIdx.x] = min(W.ctl[w.pending[threadIdx.x]].n_list, (u32)B200_WAVE_LIST);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		u32 t = 0;
@@ -127,30 +148,57 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_form
 		off[nc] = t;
 	}
 	__syncthreads();
-	TAIL_SYNC();
+	return nc;
+}
+__global__ void __launch_bounds__(K_THREADS) k_wave_mark(DevState S, WaveDev W)
+{
+	__shared__ WaveCtl w;
+	__shared__ u32 off[B200_WAVE_SLOTS + 1], nl[B200_WAVE_SLOTS];
+	cudaGridDependencySynchronize();
+	WV_TRACE(2);
+	const u32 nc = wave_stage_candidates(W, w, off, nl);
+	if (!nc) return;
+	if (blockIdx.x == 0 && threadIdx.x < nc) W.wflag[threadIdx.x] = W.ctl[w.pending[threadIdx.x]].n_list > B200_WAVE_LIST ? 2u : 0u;
 	const u32 total = off[nc], epoch = w.epoch;
-	// marks: the rows of every candidate's list and their neighbours
-	TAIL_LOOP(x, total) {
+	for (u32 x = blockIdx.x * K_THREADS + threadIdx.x; x < total; x += gridDim.x * K_THREADS) {
 		u32 p = 0;
 		while (off[p + 1] <= x) p++;
 		wave_mark_entry(S, W, w.pending[p], p, epoch, x - off[p]);
 	}
-	TAIL_SYNC();
-	// a candidate conflicts when a row of its list carries the mark of an earlier candidate
-	TAIL_LOOP(x, total) {
+}
+// a candidate conflicts when a row of its list carries the mark of an earlier candidate; the block that finishes
+// last selects the wave
+__global__ void __launch_bounds__(K_THREADS) k_wave_check(DevState S, WaveDev W)
+{
+	__shared__ WaveCtl w;
+	__shared__ u32 off[B200_WAVE_SLOTS + 1], nl[B200_WAVE_SLOTS], fl[B200_WAVE_SLOTS], s_last;
+	cudaGridDependencySynchronize();
+	WV_TRACE(3);
+	const u32 nc = wave_stage_candidates(W, w, off, nl);
+	if (w.halt) return;
+	const u32 total = off[nc], epoch = w.epoch;
+	for (u32 x = blockIdx.x * K_THREADS + threadIdx.x; x < total; x += gridDim.x * K_THREADS) {
 		u32 p = 0;
 		while (off[p + 1] <= x) p++;
 		if (p) wave_check_entry(S, W, w.pending[p], p, epoch, x - off[p]);
 	}
-	TAIL_SYNC();
-	if (rank == 0) {
-		if (threadIdx.x < nc) fl[threadIdx.x] = __ldcg(W.wflag + threadIdx.x);
-		__syncthreads();
-		if (threadIdx.x == 0) wave_form_finish(w, fl);
-		__syncthreads();
-		wv_copy_words(W.wc, &w, sizeof w);
-		if (w.halt && threadIdx.x == 0) wave_publish(W, w, S.ctl->nrows, S.ctl->n_live);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		s_last = atomicAdd(W.fin_ctr, 1u) == gridDim.x - 1;
 	}
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	if (threadIdx.x < nc) fl[threadIdx.x] = __ldcg(W.wflag + threadIdx.x);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		*W.fin_ctr = 0;
+		wave_form_finish(w, fl);
+	}
+	__syncthreads();
+	wv_copy_words(W.wc, &w, sizeof w);
+	if (w.halt && threadIdx.x == 0) wave_publish(W, w, S.ctl->nrows, S.ctl->n_live);
 }
 
 // ---------------------------------------------------------------- per-cut kernels: one cluster per cut of the wave
@@ -164,12 +212,14 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	__shared__ u32 s_nvis, s_nstrict;
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x, q = blockIdx.x / NC;
 	cudaGridDependencySynchronize();
-	WV_TRACE(3);
+	WV_TRACE(4);
 	const WaveCtl *w = W.wc;
 	if (w->halt || q >= w->n_wave) return;
 	const u32 slot = w->wave[q];
 	const DevState S = wave_view(S0, W, slot, q);
 	CutCtl *c = S.ctl;
+	const u32 w_iter = w->iter;
+	WV_TP(16);
 	// ---- P0: stage the list; visited rows = live entries classed ZERO or MINUS; trigger = a live strictly violated row
 	const u32 n_list = c->n_list;                  // <= B200_WAVE_LIST (longer lists never join a wave)
 	if (threadIdx.x == 0) { s_nvis = 0; s_nstrict = 0; }
@@ -190,6 +240,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	}
 	__syncthreads();
 	const u32 n_vis = s_nvis, n_strict = s_nstrict;
+	WV_TP(17);
 	if (ctid == 0) {
 		c->status = n_strict ? 0u : (u32)ST_REDUNDANT;
 		c->n_strict = n_strict;
@@ -226,6 +277,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	}
 	TAIL_SYNC();
 	// ---- P2: half-edge offsets (every CTA, into shared memory)
+	WV_TP(18);
 	for (u32 x = threadIdx.x; x < n_vis; x += TAIL_THREADS) slist[x] = S.vis[x];
 	u32 H = 0;
 	for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
@@ -248,6 +300,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 		return;
 	}
 	// ---- P3: evaluate every (visited vertex, neighbour) pair
+	WV_TP(19);
 	TAIL_SPREAD(e, H) {
 		u32 lo = 0, hi = n_vis;
 		while (hi - lo > 1) {
@@ -260,6 +313,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	}
 	TAIL_SYNC();
 	// ---- P4a: sizes per visited vertex
+	WV_TP(20);
 	{
 		u32 nm = 0, nz = 0;
 		bool bad = false;
@@ -284,6 +338,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	}
 	TAIL_SYNC();
 	// ---- P4b: offsets (CTA 0 stores them; k_wave_tailB reads them after the launch boundary)
+	WV_TP(21);
 	if (rank == 0) {
 		u32 carry[3] = {0, 0, 0};
 		for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
@@ -307,6 +362,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 			if (carry[0] > W.cap_new || carry[2] > W.cap_new) atomicOr(&c->status, (u32)ST_OVF_PADJ);
 		}
 	}
+	WV_TP(22);
 }
 
 // phases P5-P7 of k_tail for the cuts that are carried out, at the bases wave_plan gives them
@@ -318,10 +374,12 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	__shared__ u32 tgt[B200_WAVE_SLOTS], n_tgt;
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x, q = blockIdx.x / NC;
 	cudaGridDependencySynchronize();
-	WV_TRACE(4);
+	WV_TRACE(5);
 	wv_copy_words(&w, W.wc, sizeof w);
 	__syncthreads();
 	if (w.halt || q >= w.n_wave) return;
+	const u32 w_iter = w.iter;
+	WV_TP(24);
 	if (threadIdx.x < w.n_wave) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);
 	if (threadIdx.x == 32) n_tgt = 0;
 	__syncthreads();
@@ -335,6 +393,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 		if (!done) tgt[atomicAdd(&n_tgt, 1u)] = s2;
 	}
 	__syncthreads();
+	WV_TP(25);
 	const u32 slot = w.wave[q];
 	const DevState S = wave_view(S0, W, slot, q);
 	CutCtl *c = S.ctl;
@@ -369,6 +428,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	}
 	if (redundant) return;
 	TAIL_SYNC();
+	WV_TP(26);
 	const CutParams &P = *S.cur;
 	const u32 n_vis = c->n_vis, H = S.he_off[n_vis], M = c->n_new;
 	// ---- P5: new rows + rewiring (per half-edge) and copies + retirement (per vertex)
@@ -378,6 +438,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	}
 	TAIL_SPREAD(i, n_vis) he_finish_vertex(S, P, i);
 	TAIL_SYNC();
+	WV_TP(27);
 	// ---- P6: dead facets ‖ K4 matrix shape, clearing of the column matrix ‖ the new rows against the pending halfspaces
 	const u32 wl = (c->n_local + 63) / 64, mpad = (M + 63) & ~63u;
 	if (ctid == 0) k4_plan(S);                      // (cannot overflow: wave_plan checked the upper bound)
@@ -391,11 +452,13 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 		for (u32 x = ctid; x < M * nt; x += NC * TAIL_THREADS) wave_classify_row(S, W, tgt[x / M], first + x % M);
 	}
 	TAIL_SYNC();
+	WV_TP(28);
 	// ---- P7: K4 bit matrices
 	{
 		const u32 nrows = c->nrows, f = P.facet;
 		TAIL_SPREAD(j, M) k4_build_row_at(S, j, nrows, f, wl, mpad);
 	}
+	WV_TP(29);
 }
 
 // pair test of every carried-out cut of the wave; tile pairs / survivor rounds of all cuts are dealt round-robin
@@ -403,7 +466,7 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_k4_filter(DevState S0, WaveD
 {
 	__shared__ u32 s_slot[B200_WAVE_MAXW], s_M[B200_WAVE_MAXW], s_wl[B200_WAVE_MAXW], s_mpad[B200_WAVE_MAXW], s_n;
 	cudaGridDependencySynchronize();
-	WV_TRACE(5);
+	WV_TRACE(6);
 	const WaveCtl *w = W.wc;
 	if (threadIdx.x == 0) s_n = w->halt ? 0u : w->n_commit;
 	if (threadIdx.x < B200_WAVE_MAXW) {              // shapes of all cuts by parallel threads (no serial walk through global memory)
@@ -425,10 +488,9 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_k4_filter(DevState S0, WaveD
 }
 __global__ void __launch_bounds__(K_THREADS) k_wave_k4_contain(DevState S0, WaveDev W)
 {
-	__shared__ u32 pra[K_THREADS / 32], prb[K_THREADS / 32], npr, pbase;
-	__shared__ u32 s_slot[B200_WAVE_MAXW], s_ns[B200_WAVE_MAXW], s_n;
+	__shared__ u32 s_slot[B200_WAVE_MAXW], s_ns[B200_WAVE_MAXW], s_M[B200_WAVE_MAXW], s_wl[B200_WAVE_MAXW], s_mpad[B200_WAVE_MAXW], s_off[B200_WAVE_MAXW + 1], s_n;
 	cudaGridDependencySynchronize();
-	WV_TRACE(6);
+	WV_TRACE(7);
 	const WaveCtl *w = W.wc;
 	if (threadIdx.x == 0) s_n = w->halt ? 0u : w->n_commit;
 	if (threadIdx.x < B200_WAVE_MAXW) {
@@ -436,15 +498,36 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_k4_contain(DevState S0, Wave
 		const CutCtl *c = W.ctl + (slot < B200_WAVE_SLOTS ? slot : 0);
 		s_slot[threadIdx.x] = slot;
 		s_ns[threadIdx.x] = ((c->status & ST_SKIP_B) || c->n_surv > W.cap_pairs) ? 0u : c->n_surv;   // k_wave_tail2 reports the overflow
+		s_M[threadIdx.x] = c->n_new;
+		s_wl[threadIdx.x] = c->wl;
+		s_mpad[threadIdx.x] = c->mpad;
 	}
 	__syncthreads();
-	u32 base = 0;
-	for (u32 q = 0; q < s_n; q++) {
-		if (!s_ns[q]) continue;
-		const DevState S = wave_view(S0, W, s_slot[q], q);
-		contain_block_rounds<true>(S, pra, prb, npr, pbase, (blockIdx.x + gridDim.x - base % gridDim.x) % gridDim.x, gridDim.x);
-		base += (s_ns[q] + K_THREADS / 32 - 1) / (K_THREADS / 32);
+	if (threadIdx.x == 0) {
+		u32 t = 0;
+		for (u32 q = 0; q < s_n; q++) { s_off[q] = t; t += s_ns[q]; }
+		s_off[s_n] = t;
 	}
+	__syncthreads();
+	// one warp per surviving pair, over the survivors of all cuts of the wave; an adjacent pair is flagged in place
+	const u32 lane = threadIdx.x & 31, nwarps = gridDim.x * (K_THREADS / 32), total = s_off[s_n];
+	u32 cur_q = B200_NONE, found = 0;
+	for (u32 g = blockIdx.x * (K_THREADS / 32) + (threadIdx.x >> 5); g < total; g += nwarps) {
+		u32 q = 0;
+		while (s_off[q + 1] <= g) q++;
+		if (q != cur_q) {                            // (warp-uniform) pair count of the cut this warp is leaving
+			if (cur_q != B200_NONE && found && lane == 0) atomicAdd(&W.ctl[s_slot[cur_q]].n_pairs, found);
+			cur_q = q;
+			found = 0;
+		}
+		const DevState S = wave_view(S0, W, s_slot[q], q);
+		const u32 sv = g - s_off[q], a = S.surv_a[sv], b = S.surv_b[sv];
+		if (k4_columns_verdict(S, a, b, lane, s_M[q], s_wl[q], s_mpad[q])) {
+			if (lane == 0) wave_flag_adjacent(S, sv, a, b);
+			found++;
+		}
+	}
+	if (cur_q != B200_NONE && found && lane == 0) atomicAdd(&W.ctl[s_slot[cur_q]].n_pairs, found);
 }
 // before the pair test is redone with larger buffers
 __global__ void __launch_bounds__(K_THREADS) k_wave_k4_reset(DevState S0, WaveDev W)
@@ -458,115 +541,60 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_k4_reset(DevState S0, WaveDe
 	}
 }
 
-// adjacency build (k_tail2) at the wave's bases; the cluster that finishes last commits the wave and publishes progress
+// adjacency build (k_tail2) at the wave's bases (every cluster derives them from the same counters); the commit is
+// left to the first kernel of the next iteration
 template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail2(DevState S0, WaveDev W)
 {
 	__shared__ WaveCtl w;
 	__shared__ WaveCut cut[B200_WAVE_MAXW];
-	__shared__ CutCtl mctl;
 	__shared__ u32 ws[33];
-	__shared__ u32 s_adj[B200_WAVE_MAXW], s_last;
-	__shared__ int s_rc[B200_WAVE_MAXW];
+	__shared__ u32 s_base[B200_WAVE_MAXW], s_new[B200_WAVE_MAXW], s_fl;
 	const u32 rank = tail_rank<NC>(), ctid = rank * TAIL_THREADS + threadIdx.x, q = blockIdx.x / NC;
 	cudaGridDependencySynchronize();
-	WV_TRACE(7);
+	WV_TRACE(8);
 	wv_copy_words(&w, W.wc, sizeof w);
 	__syncthreads();
 	if (w.halt || q >= w.n_commit) return;
+	const u32 w_iter = w.iter;
+	WV_TP(32);
 	const u32 n_commit = w.n_commit;
+	if (threadIdx.x < n_commit) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);
+	__syncthreads();
 	const DevState S = wave_view(S0, W, w.wave[q], q);
 	CutCtl *c = S.ctl;
-	const u32 OVF_P = 8u, OVF_A = 16u;
-	u32 total_adj = 0, over_pairs = 0;               // (thread 0 of CTA 0: what the halt record reports)
-	// ---- adjacency entries every cut of the wave appends (PLUS neighbours + new-facet neighbours of its new rows):
-	// every cluster derives all of them, so the bases need no communication
-	if (rank == 0) {
-		if (threadIdx.x < n_commit) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);
-		if (threadIdx.x < B200_WAVE_MAXW) s_adj[threadIdx.x] = 0;
-		__syncthreads();
-		{
-			// warp wid sums a share of cut q2 = wid % n_commit (the warps of one cut interleave)
-			const u32 wid = threadIdx.x >> 5, lane = threadIdx.x & 31, q2 = wid % n_commit, part = wid / n_commit;
-			const u32 nparts = (TAIL_THREADS / 32 - q2 + n_commit - 1) / n_commit;
-			if (!(cut[q2].status & ST_SKIP_B)) {
-				const DevState V = wave_view(S0, W, cut[q2].slot, q2);
-				u32 sum = 0;
-				for (u32 j = part * 32 + lane; j < cut[q2].n_new; j += nparts * 32) sum += V.new_padj_len[j] + V.deg[j];
-				sum = __reduce_add_sync(0xffffffffu, sum);
-				if (lane == 0 && sum) atomicAdd(&s_adj[q2], sum);
-			}
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			u32 base = S0.ctl->adj_used, mine = base, over = 0;
-			for (u32 q2 = 0; q2 < n_commit; q2++) {
-				if (q2 == q) mine = base;
-				base += s_adj[q2];
-				if (!(cut[q2].status & ST_SKIP_B) && (cut[q2].n_pairs > W.cap_pairs || cut[q2].n_surv > W.cap_pairs)) over = max(over, max(cut[q2].n_pairs, cut[q2].n_surv));
-			}
-			u32 fl = 0;
-			if (over) fl |= OVF_P;
-			else if ((u64)base > S0.cap_adj) fl |= OVF_A;
-			c->adj_used = mine;
-			c->adj_new = s_adj[q];
-			c->scratch_flag = fl;
-			total_adj = base;
-			over_pairs = over;
-		}
-	}
-	TAIL_SYNC();
-	const u32 fl = c->scratch_flag;
-	const bool redundant = (c->status & ST_REDUNDANT) != 0;
-	if (!fl && !redundant) {
+	if (threadIdx.x == 0) {
+		u32 need_adj, need_pairs;
+		s_fl = wave_adj_plan(cut, n_commit, S0.ctl->adj_used, S0.cap_adj, W.cap_pairs, s_base, s_new, need_adj, need_pairs);
 		if (rank == 0) {
-			const u32 n = c->n_new;
-			u32 carry = 0;
-			for (u32 base = 0; base < n; base += TAIL_THREADS) {
-				u32 j = base + threadIdx.x, v = j < n ? S.new_padj_len[j] + S.deg[j] : 0, tot;
-				u32 e = block_excl_scan(v, ws, tot);
-				if (j < n) S.adj_base[j] = carry + e;
-				carry += tot;
+			c->adj_used = s_base[q];
+			c->adj_new = s_new[q];
+			if (q == 0 && s_fl) {                    // the host grows the buffer and has this kernel (and the pair test) redone
+				WaveCtl *g = W.wc;
+				if (s_fl & 8u) { g->halt |= WH_GROW_PAIRS; g->halt_pairs = need_pairs; w.halt |= WH_GROW_PAIRS; }
+				else { g->halt |= WH_GROW_ADJ; g->halt_adj = need_adj; w.halt |= WH_GROW_ADJ; }
+				wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live);
 			}
 		}
-		TAIL_SYNC();
-		TAIL_SPREAD(j, c->n_new) adj_place(S, j);
-		TAIL_SPREAD(p, c->n_pairs) adj_pair_fill(S, p);
-		TAIL_SYNC();
-		TAIL_SPREAD(j, c->n_new) adj_sort(S, j);
+	}
+	__syncthreads();
+	WV_TP(33);
+	if (s_fl || (cut[q].status & ST_REDUNDANT)) return;
+	const u32 n = cut[q].n_new;
+	if (rank == 0) {
+		u32 carry = 0;
+		for (u32 base = 0; base < n; base += TAIL_THREADS) {
+			u32 j = base + threadIdx.x, v = j < n ? S.new_padj_len[j] + S.deg[j] : 0, tot;
+			u32 e = block_excl_scan(v, ws, tot);
+			if (j < n) S.adj_base[j] = carry + e;
+			carry += tot;
+		}
 	}
 	TAIL_SYNC();
-	if (rank != 0) return;
-	if (threadIdx.x == 0) {
-		__threadfence();
-		s_last = atomicAdd(W.fin_ctr, 1u) == n_commit - 1;
-	}
-	__syncthreads();
-	if (!s_last) return;                             // every other cluster of the wave is done: this CTA commits
-	__threadfence();
-	if (fl) {
-		if (threadIdx.x == 0) {
-			*W.fin_ctr = 0;
-			WaveCtl *g = W.wc;
-			if (fl & OVF_P) { g->halt |= WH_GROW_PAIRS; g->halt_pairs = over_pairs; w.halt |= WH_GROW_PAIRS; }
-			else { g->halt |= WH_GROW_ADJ; g->halt_adj = total_adj; w.halt |= WH_GROW_ADJ; }
-			wave_publish(W, w, S0.ctl->nrows, S0.ctl->n_live);
-		}
-		return;
-	}
-	if (threadIdx.x < n_commit) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);   // (adj_new of every cut is final now)
-	wv_copy_words(&mctl, S0.ctl, sizeof mctl);
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		*W.fin_ctr = 0;
-		wave_commit(w, mctl, cut, S0.d, s_rc);
-		const u64 now = b200_globaltimer();
-		if (!w.t_first) w.t_first = now;
-		w.t_last = now;
-	}
-	__syncthreads();
-	wv_copy_words(W.wc, &w, sizeof w);
-	wv_copy_words(S0.ctl, &mctl, sizeof mctl);
-	if (threadIdx.x < n_commit) W.rc[cut[threadIdx.x].hs] = s_rc[threadIdx.x];
-	__syncthreads();
-	if (threadIdx.x == 0) wave_publish(W, w, mctl.nrows, mctl.n_live);
+	WV_TP(34);
+	TAIL_SPREAD(j, n) adj_place(S, j);
+	TAIL_SPREAD(sv, cut[q].n_surv) adj_pair_fill_surv(S, sv);
+	TAIL_SYNC();
+	WV_TP(35);
+	TAIL_SPREAD(j, n) adj_sort(S, j);
+	WV_TP(36);
 }
