@@ -79,14 +79,28 @@ static void bind_device()
 	CK(cudaSetDevice(g_device));
 }
 #define STREAM ((cudaStream_t)stream_)
+// (cudaMallocAsync with the release threshold lifted was tried for these: growing arrays through the stream-ordered
+// pool made the compaction's shadow allocation 5-10x slower -- the pool remaps physical memory to build large
+// blocks -- so storage is plain cudaMalloc, and growth is kept rare instead: see grow_to().)
+static double g_t_malloc = 0, g_t_memset = 0, g_t_free = 0;   // B200_PHASES report (us, process-wide)
 static void *dalloc(size_t bytes)
 {
 	void *p = nullptr;
+	const double t0 = now_us();
 	CK(cudaMalloc(&p, bytes ? bytes : 16));
+	const double t1 = now_us();
 	CK(cudaMemset(p, 0, bytes ? bytes : 16));
+	g_t_malloc += t1 - t0;
+	g_t_memset += now_us() - t1;
 	return p;
 }
-static void dfree(void *p) { if (p) cudaFree(p); }
+static void dfree(void *p)
+{
+	if (!p) return;
+	const double t0 = now_us();
+	cudaFree(p);
+	g_t_free += now_us() - t0;
+}
 static void d2d(void *dst, const void *src, size_t n) { if (n) CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToDevice)); }
 static void h2d(void *dst, const void *src, size_t n) { if (n) CK(cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice)); }
 static void d2h(void *dst, const void *src, size_t n) { if (n) CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost)); }
@@ -196,6 +210,18 @@ void b200_comm_stop() { g_comm = Comm(); }
 int b200_comm_set_callback(b200_allgather_fn fn) { g_comm.callback = fn; return 0; }
 #endif
 
+struct GrowTimer {          // host time spent growing device storage (reported with B200_PHASES)
+	double *acc, t0;
+	const char *what;
+	GrowTimer(double *a, const char *w) : acc(a), t0(now_us()), what(w) {}
+	~GrowTimer()
+	{
+		const double dt = now_us() - t0;
+		acc[8] += dt; acc[9] += 1;
+		static const bool verbose = getenv("B200_PHASES") != nullptr;
+		if (verbose && dt > 2000) fprintf(stderr, "[b200] growth step %s: %.1f ms (process totals so far: cudaMalloc %.1f, cudaMemset %.1f, cudaFree %.1f ms)\n", what, dt / 1e3, g_t_malloc / 1e3, g_t_memset / 1e3, g_t_free / 1e3);
+	}
+};
 template <class T> static void regrow(T *&p, size_t new_n, size_t keep_n)
 {
 	T *q = (T *)dalloc(new_n * sizeof(T));
@@ -205,6 +231,14 @@ template <class T> static void regrow(T *&p, size_t new_n, size_t keep_n)
 }
 
 static u32 round_up(u64 x, u32 m) { return (u32)(((x + m - 1) / m) * m); }
+// New capacity of a growing array.  A growth step costs a cudaMalloc (0.3 ms whatever the size) + copy + cudaFree
+// (0.3 ms, device-synchronising) PER ARRAY, so it is the number of steps that matters: arrays below `quad_below`
+// entries grow 4x, larger ones 2x.  32-bit indices.
+static u32 grow_to(u64 need, u64 have, u64 quad_below)
+{
+	const u64 f = have < quad_below ? 4 : 2;
+	return (u32)std::min<u64>(0xFFFF0000ull, std::max<u64>(need, have * f));
+}
 
 // ------------------------------------------------------------------ construction
 CutEngine::CutEngine(int dim) : d_(dim)
@@ -280,9 +314,9 @@ CutEngine::CutEngine(int dim) : d_(dim)
 		ensure_facets(8);
 		return;
 	}
-	ensure_rows(4 * B200_TILE);
-	ensure_inc(1u << 16);
-	ensure_adj(1u << 16);
+	ensure_rows(1u << 17);               // (a few tens of MB in all: nothing on a 180 GB device, and ten growth steps saved)
+	ensure_inc(1u << 20);
+	ensure_adj(1u << 20);
 	ensure_padj(1u << 14);
 	ensure_pairs(1u << 16);
 	ensure_bits(1u << 16);
@@ -299,20 +333,19 @@ CutEngine::~CutEngine()
 		fprintf(stderr, "[b200] sub-phases (thread 0 of CTA 0):");
 		for (int k = 0; k < 14; k++) fprintf(stderr, " s%d=%.1fus", k, stats_.sub_ns[k] / 1e3 / std::max<u64>(1, stats_.cuts));
 		fprintf(stderr, "\n");
-		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu (host ms in compaction %.1f, of which shadow allocation %.1f)\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions, stats_.host_us[5] / 1e3, stats_.host_us[6] / 1e3);
+		fprintf(stderr, "[b200] host us per cut: launch=%.1f wait=%.1f redo=%.1f unpack+gc=%.1f total_in_cut=%.1f redo_loops=%llu compactions=%llu (host ms in compaction %.1f, of which shadow allocation %.1f); device growth %.1f ms in %.0f events\n", stats_.host_us[0] / std::max<u64>(1, stats_.cuts), stats_.host_us[1] / std::max<u64>(1, stats_.cuts), stats_.host_us[2] / std::max<u64>(1, stats_.cuts), stats_.host_us[3] / std::max<u64>(1, stats_.cuts), stats_.host_us[4] / std::max<u64>(1, stats_.cuts), (unsigned long long)stats_.redo_loops, (unsigned long long)stats_.compactions, stats_.host_us[5] / 1e3, stats_.host_us[6] / 1e3, stats_.host_us[8] / 1e3, stats_.host_us[9]);
 	}
 #ifndef B200_EMULATE
 	cudaSetDevice(g_device);
 	if (stream_) cudaStreamSynchronize(STREAM);
 #endif
 	void *ptrs[] = {S_.coord, S_.row_slot, S_.root, flush_buf_, S_.live, S_.ideal, S_.inc_off, S_.inc_len, S_.adj_off, S_.adj_len,
-	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, S_.cls, S_.tile_cnt, S_.tile_base,
-	                S_.vis, S_.cnt3, S_.base3, S_.padj, S_.new_padj_off, S_.new_padj_len, S_.new_parent, S_.deg,
-	                S_.adj_fill, S_.adj_base, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits,
+	                S_.inc_pool, S_.adj_pool, S_.facet_cnt, S_.facet_alive, row_scratch_,
+	                S_.padj, S_.pair_a, S_.pair_b, S_.surv_a, S_.surv_b, S_.facet_epoch, S_.facet_local, S_.bits,
 #ifdef B200_EMULATE
 	                S_.stage,
 #endif
-	                S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.dead_slots, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 	dfree(gc_totals_);
 	drop_shadow();
@@ -340,11 +373,12 @@ void CutEngine::drop_shadow()
 void CutEngine::ensure_rows(u32 need)
 {
 	if (need <= S_.cap_rows) return;
+	GrowTimer gt(stats_.host_us, "ensure_rows");
 	// the multi-GPU exchange packs (row | class << 30) into one word (k_xchg_pack / k_xchg_merge)
 	if (nranks_ > 1 && need > (1u << 30)) fail("bensolve_b200: more than 2^30 rows are not supported with several ranks");
 	drop_shadow();
 	const u32 old = S_.cap_rows, keep = hdr_.nrows;
-	const u32 cap = round_up(std::max<u64>(need, (u64)old * 2), B200_TILE);
+	const u32 cap = round_up(grow_to(need, old, 1ull << 21), B200_TILE);
 #ifndef B200_EMULATE
 	if (stream_) CK(cudaStreamSynchronize(STREAM));
 #endif
@@ -360,42 +394,54 @@ void CutEngine::ensure_rows(u32 need)
 	regrow(S_.inc_len, cap, keep);
 	regrow(S_.adj_off, cap, keep);
 	regrow(S_.adj_len, cap, keep);
-	regrow(S_.cls, cap, 0);
-	regrow(S_.vis, cap, 0);
-	regrow(S_.cnt3, (size_t)3 * cap, 0);
-	regrow(S_.base3, (size_t)3 * cap, 0);
-	regrow(S_.new_padj_off, cap, 0);
-	regrow(S_.new_padj_len, cap, 0);
-	regrow(S_.new_parent, cap, 0);
-	regrow(S_.deg, cap, 0);
-	regrow(S_.adj_fill, cap, 0);
-	regrow(S_.adj_base, cap, 0);
-	regrow(S_.dead_slots, cap, 0);
-	S_.cap_tiles = cap / B200_TILE;
-	regrow(S_.tile_cnt, S_.cap_tiles, 0);
-	regrow(S_.tile_base, S_.cap_tiles, 0);
+	// the per-cut scratch arrays indexed by row hold nothing across a growth step: one block for all of them
+	// (13 arrays = 13 x (cudaMalloc + cudaFree) otherwise), carved at 256-byte boundaries
+	{
+		S_.cap_tiles = cap / B200_TILE;
+		const size_t c4 = (((size_t)cap * 4 + 255) & ~(size_t)255), c1 = (((size_t)cap + 255) & ~(size_t)255), t4 = (((size_t)S_.cap_tiles * 4 + 255) & ~(size_t)255);
+		dfree(row_scratch_);
+		row_scratch_ = dalloc(c1 + 14 * c4 + 2 * t4);
+		char *q = (char *)row_scratch_;
+		auto take = [&](size_t bytes) { char *r = q; q += bytes; return r; };
+		S_.cls = (u8 *)take(c1);
+		S_.vis = (u32 *)take(c4);
+		S_.cnt3 = (u32 *)take(3 * c4);
+		S_.base3 = (u32 *)take(3 * c4);
+		S_.new_padj_off = (u32 *)take(c4);
+		S_.new_padj_len = (u32 *)take(c4);
+		S_.new_parent = (u32 *)take(c4);
+		S_.deg = (u32 *)take(c4);
+		S_.adj_fill = (u32 *)take(c4);
+		S_.adj_base = (u32 *)take(c4);
+		S_.dead_slots = (u32 *)take(c4);
+		S_.tile_cnt = (u32 *)take(t4);
+		S_.tile_base = (u32 *)take(t4);
+	}
 	small_dirty_ = true;
 	S_.cap_rows = cap;
 }
 void CutEngine::ensure_inc(u32 need)
 {
 	if (need <= S_.cap_inc) return;
+	GrowTimer gt(stats_.host_us, "ensure_inc");
 	drop_shadow();
-	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_inc * 2);
+	u32 cap = grow_to(need, S_.cap_inc, 1ull << 24);
 	regrow(S_.inc_pool, cap, hdr_.inc_used);
 	S_.cap_inc = cap;
 }
 void CutEngine::ensure_adj(u32 need)
 {
 	if (need <= S_.cap_adj) return;
+	GrowTimer gt(stats_.host_us, "ensure_adj");
 	drop_shadow();
-	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_adj * 2);
+	u32 cap = grow_to(need, S_.cap_adj, 1ull << 24);
 	regrow(S_.adj_pool, cap, hdr_.adj_used);
 	S_.cap_adj = cap;
 }
 void CutEngine::ensure_padj(u32 need)
 {
 	if (need <= S_.cap_padj) return;
+	GrowTimer gt(stats_.host_us, "ensure_padj");
 	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_padj * 2);
 	regrow(S_.padj, cap, 0);
 	S_.cap_padj = cap;
@@ -403,6 +449,7 @@ void CutEngine::ensure_padj(u32 need)
 void CutEngine::ensure_pairs(u32 need)
 {
 	if (need <= S_.cap_pairs) return;
+	GrowTimer gt(stats_.host_us, "ensure_pairs");
 	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_pairs * 2);
 	regrow(S_.pair_a, cap, 0);
 	regrow(S_.pair_b, cap, 0);
@@ -413,6 +460,7 @@ void CutEngine::ensure_pairs(u32 need)
 void CutEngine::ensure_bits(u64 need)
 {
 	if (need <= S_.cap_bits) return;
+	GrowTimer gt(stats_.host_us, "ensure_bits");
 	u64 cap = std::max<u64>(need, S_.cap_bits * 2);
 	regrow(S_.bits, cap, 0);
 	S_.cap_bits = cap;
@@ -420,6 +468,7 @@ void CutEngine::ensure_bits(u64 need)
 void CutEngine::ensure_stage(u64 need)
 {
 	if (need <= S_.cap_stage) return;
+	GrowTimer gt(stats_.host_us, "ensure_stage");
 	const u64 cap = std::max<u64>(need, S_.cap_stage * 2);
 #ifndef B200_EMULATE
 	// mapped pinned host memory: the kernels write the delta record straight into it (no D2H copy)
@@ -440,6 +489,7 @@ void CutEngine::ensure_stage(u64 need)
 void CutEngine::ensure_facets(u32 need)
 {
 	if (need <= S_.cap_facets) return;
+	GrowTimer gt(stats_.host_us, "ensure_facets");
 	u32 cap = (u32)std::max<u64>(need, (u64)S_.cap_facets * 2);
 	regrow(S_.facet_cnt, cap, S_.cap_facets);
 	regrow(S_.facet_alive, cap, S_.cap_facets);
@@ -2043,10 +2093,10 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 				const u64 *t = tr.data() + ((it & 255u) << 6);
 				fprintf(stderr, "[b200] trace iter %u: +%.1f | kernels", it, prev_first ? (double)(t[0] - prev_first) / 1e3 : 0.0);
 				for (int k = 1; k < 9; k++) fprintf(stderr, " %.1f", (double)((long long)(t[k] - t[0])) / 1e3);
-				const int grp[3][2] = {{16, 22}, {24, 29}, {32, 36}};
-				const int kern[3] = {4, 5, 8};
-				const char *nm[3] = {"tailA", "tailB", "tail2"};
-				for (int g = 0; g < 3; g++) {
+				const int grp[4][2] = {{16, 22}, {24, 29}, {32, 36}, {40, 45}};
+				const int kern[4] = {4, 5, 8, 0};
+				const char *nm[4] = {"tailA", "tailB", "tail2", "begin"};
+				for (int g = 0; g < 4; g++) {
 					fprintf(stderr, " | %s", nm[g]);
 					for (int k = grp[g][0]; k <= grp[g][1]; k++) fprintf(stderr, " %.1f", (double)((long long)(t[k] - t[kern[g]])) / 1e3);
 				}

@@ -42,7 +42,7 @@ struct EngineStats {
 	double classify_ms = 0, cut_ms = 0;
 	u64 phase_ns[16] = {0};
 	u64 sub_ns[16] = {0};
-	double host_us[8] = {0};
+	double host_us[12] = {0};     // [8] device growth (ensure_*), [9] growth events
 	u64 redo_loops = 0;
 	u64 waves = 0, wave_cuts = 0, la_passes = 0, wave_deferred = 0, wave_serial = 0, wave_halts = 0;   // wave path
 };
@@ -153,6 +153,7 @@ private:
 	const unsigned char *dev_ideal_ = nullptr;
 	u64 dev_index_ = 0;
 	void *flush_buf_ = nullptr;
+	void *row_scratch_ = nullptr;       // one block behind the per-cut scratch arrays indexed by row (S_.cls .. S_.tile_base)
 	void *shadow_[11] = {nullptr};      // second set of persistent arrays: target of the next compaction
 	bool shadow_valid_ = false;
 	u32 shadow_rows_ = 0, shadow_inc_ = 0, shadow_adj_ = 0;

@@ -19,6 +19,7 @@
 #include <chrono>
 #include <thread>
 #include <mutex>
+#include <sys/mman.h>
 #include <vector>
 
 #include "../../include/bensolve_b200.h"
@@ -78,9 +79,9 @@ size_t big_limit()
 	static const size_t lim = [] { const char *e = getenv("B200_HOST_CACHE_MB"); return (size_t)(e ? atol(e) : 1024) << 20; }();
 	return lim;
 }
-void *big_alloc(size_t bytes)       // a block of at least `bytes`
+void *big_take(size_t bytes)        // a recycled block of at least `bytes`, or NULL
 {
-	if (bytes >= BIG_MIN) {
+	{
 		std::lock_guard<std::mutex> lk(g_big.mu);
 		size_t best = (size_t)-1;
 		for (size_t i = 0; i < g_big.held.size(); i++)
@@ -92,7 +93,7 @@ void *big_alloc(size_t bytes)       // a block of at least `bytes`
 			return e.p;
 		}
 	}
-	return malloc(bytes);
+	return NULL;
 }
 void big_free(void *p, size_t bytes)
 {
@@ -109,6 +110,27 @@ void big_free(void *p, size_t bytes)
 }
 }   // namespace
 
+// First touch of a fresh coordinate block costs ~0.5 ms per MB in page faults, on the thread that applies the delta
+// records.  A helper thread pre-faults the newly grown tail with MADV_POPULATE_WRITE (contents untouched, so it is safe
+// beside the writer) while the caller waits for the device anyway.  One request at a time; joined before the block
+// moves or is freed.
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+static std::thread &populate_thread() { static std::thread *t = new std::thread(); return *t; }   // (never destroyed: no join at exit)
+static void populate_wait() { if (populate_thread().joinable()) populate_thread().join(); }
+static void populate_async(char *from, size_t bytes)
+{
+	static const bool on = [] { const char *e = getenv("B200_HOST_POPULATE"); return !e || atoi(e) != 0; }();
+	if (!on || bytes < ((size_t)1 << 22)) return;
+	const uintptr_t lo = ((uintptr_t)from + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)from + bytes) & ~(uintptr_t)4095;
+	if (hi <= lo) return;
+	populate_thread() = std::thread([lo, hi] {
+		for (uintptr_t a = lo; a < hi; a += (size_t)1 << 19)          // in small slices: the call holds the address-space lock cudaMalloc / cudaFree need
+			if (madvise((void *)a, std::min<size_t>((size_t)1 << 19, hi - a), MADV_POPULATE_WRITE) != 0) break;
+	});
+}
+
 static void mirror_alloc(polytope *p)
 {
 	const size_t cap = SLOTS_PER_BLOCK;
@@ -123,20 +145,32 @@ static void mirror_alloc(polytope *p)
 	p->sltn = (vrtx_strg *)calloc(1, sizeof(vrtx_strg));
 }
 
+static double g_mirror_grow_us = 0;       // B200_PHASES report only (process-wide, unsynchronised)
+struct MirrorGrowTimer {
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	~MirrorGrowTimer() { g_mirror_grow_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
+};
 static void mirror_reserve(polytope *p, size_t slots)
 {
 	size_t cap = p->blcks * SLOTS_PER_BLOCK;
 	if (slots < cap) return;              // keep one spare slot, as the reference does (bslv_poly.c:418)
+	MirrorGrowTimer mgt;
 	size_t nb = p->blcks;
 	while (nb * SLOTS_PER_BLOCK <= slots) nb *= 2;
 	const size_t ncap = nb * SLOTS_PER_BLOCK;
 	const size_t row = std::max<size_t>(p->dim, 1) * sizeof(double), old_bytes = cap * row, new_bytes = ncap * row;
-	if (new_bytes >= BIG_MIN) {           // large: possibly a recycled block (see big_alloc)
-		double *nd = (double *)big_alloc(new_bytes);
-		if (!nd) die("mirror_reserve", "out of host memory");
-		memcpy(nd, p->data, p->cnt * row);
-		big_free(p->data, old_bytes);
-		p->data = nd;
+	if (new_bytes >= BIG_MIN) {           // large: a recycled block (see big_alloc) if one fits ...
+		populate_wait();
+		double *nd = (double *)big_take(new_bytes);
+		if (nd) {
+			memcpy(nd, p->data, p->cnt * row);
+			big_free(p->data, old_bytes);
+			p->data = nd;
+		} else {                          // ... else grow in place: glibc moves the pages of a large block (mremap), no copy,
+			p->data = (double *)realloc(p->data, new_bytes);      // no second round of first-touch faults
+			if (!p->data) die("mirror_reserve", "out of host memory");
+			populate_async((char *)p->data + old_bytes, new_bytes - old_bytes);
+		}
 	} else
 		p->data = (double *)realloc(p->data, new_bytes);
 	p->data_primg = (double *)realloc(p->data_primg, ncap * std::max<size_t>(p->dim_primg, 1) * sizeof(double));
@@ -169,6 +203,7 @@ static size_t mirror_append(polytope *p)      // add_vrtx, bslv_poly.c:416-447
 
 static void mirror_free(polytope *p)
 {
+	populate_wait();
 	big_free(p->data, p->blcks * SLOTS_PER_BLOCK * std::max<size_t>(p->dim, 1) * sizeof(double));
 	free(p->data_primg); free(p->adjacence); free(p->incidence);
 	free(p->used); free(p->ideal); free(p->sltn);
@@ -230,6 +265,7 @@ extern "C" void poly__initialise(poly_args *args)
 extern "C" void poly__kill(poly_args *args)
 {
 	Handle *h = handle_of(&args->primal);
+	if (getenv("B200_PHASES")) fprintf(stderr, "[b200] host mirror growth so far in this process: %.1f ms\n", g_mirror_grow_us / 1e3);
 	delete h->engine;
 	h->magic = 0;
 	delete h;

@@ -42,11 +42,14 @@ __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const 
 	wv_copy_words(&mctl, S.ctl, sizeof mctl);
 	__syncthreads();
 	if (w.halt) return;
+	u64 *tr = (W.trace && threadIdx.x == 0) ? W.trace + (((w.iter + 1) & 255u) << 6) : nullptr;
+	if (tr) tr[40] = b200_globaltimer();
 	// ---- the previous wave's adjacency build has completed: commit it
 	const u32 n_commit = w.n_commit;
 	if (n_commit) {
 		if (threadIdx.x < n_commit) { wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]); s_hs[threadIdx.x] = cut[threadIdx.x].hs; }
 		__syncthreads();
+		if (tr) tr[41] = b200_globaltimer();
 		if (threadIdx.x == 0) {
 			wave_commit(w, mctl, cut, S.d, s_rc);
 			const u64 now = b200_globaltimer();
@@ -57,15 +60,19 @@ __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const 
 		if (threadIdx.x < n_commit) W.rc[s_hs[threadIdx.x]] = s_rc[threadIdx.x];
 		wv_copy_words(S.ctl, &mctl, sizeof mctl);
 	}
+	if (tr) tr[42] = b200_globaltimer();
 	if (threadIdx.x == 0) {
 		w.iter++;
 		if (W.trace) W.trace[(w.iter & 255u) << 6] = t_begin;
 		if (!w.halt) wave_la_plan(w, mctl.nrows);
 	}
 	__syncthreads();
+	if (tr) tr[43] = b200_globaltimer();
 	if (!w.halt && threadIdx.x < w.n_la) wave_la_init(S, W, w, threadIdx.x, vals, ideal);
 	wv_copy_words(W.wc, &w, sizeof w);
+	if (tr) tr[44] = b200_globaltimer();
 	if (threadIdx.x == 0) wave_publish(W, w, mctl.nrows, mctl.n_live);
+	if (tr) tr[45] = b200_globaltimer();
 }
 
 // Look-ahead K1.  Thread t of a block owns rows 2t, 2t+1 of a 512-row group (one double2 load per coordinate, a
