@@ -30,6 +30,7 @@ static thread_local std::string g_last_error;
 void b200_set_error(const std::string &msg) { g_last_error = msg; }
 const char *b200_get_error() { return g_last_error.c_str(); }
 
+static double g_t_malloc = 0, g_t_memset = 0, g_t_free = 0;   // B200_PHASES report (us, process-wide)
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 [[noreturn]] static void fail(const std::string &msg)
@@ -82,7 +83,6 @@ static void bind_device()
 // (cudaMallocAsync with the release threshold lifted was tried for these: growing arrays through the stream-ordered
 // pool made the compaction's shadow allocation 5-10x slower -- the pool remaps physical memory to build large
 // blocks -- so storage is plain cudaMalloc, and growth is kept rare instead: see grow_to().)
-static double g_t_malloc = 0, g_t_memset = 0, g_t_free = 0;   // B200_PHASES report (us, process-wide)
 static void *dalloc(size_t bytes)
 {
 	void *p = nullptr;
