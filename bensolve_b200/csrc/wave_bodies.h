@@ -307,7 +307,7 @@ B200_HD void wave_commit(WaveCtl &w, CutCtl &m, const WaveCut *cut, int dim, int
 	for (u32 q = 0; q < w.n_commit; q++) {
 		const WaveCut &c = cut[q];
 		if (c.status & ST_REDUNDANT) {
-			const u64 N = m.n_live;
+			const u64 N = c.live_before;          // (= the running live count: k_wave_tailB stores it for every carried-out position)
 			evals += N;
 			red++;
 			bytes += N * (8 * d + 1);

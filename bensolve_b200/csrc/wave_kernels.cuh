@@ -29,6 +29,110 @@ __device__ __forceinline__ void wv_copy_words(void *dst, const void *src, u32 by
 	for (u32 i = threadIdx.x; i < bytes / 4; i += blockDim.x) ((u32 *)dst)[i] = ((const u32 *)src)[i];
 }
 
+// wave_commit and wave_la_plan (wave_bodies.h) by the lanes of one warp: a single thread walking the control block in
+// shared memory takes 6 + 4 us for them (every access a dependent 30-cycle round trip), the warp 1 us.  Same
+// arithmetic, term by term; lane q owns wave position q in the commit and slot q in the plan.
+static_assert(B200_WAVE_SLOTS == 32 && B200_WAVE_MAXW <= 32, "one lane per slot / wave position");
+__device__ __forceinline__ u64 wv_sum64(u64 v)
+{
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ void wave_commit_warp(WaveCtl &w, CutCtl &m, const WaveCut *cut, int dim, int *rc)
+{
+	const u32 lane = threadIdx.x & 31, n_commit = w.n_commit, n_wave = w.n_wave, n_pending = w.n_pending;
+	const u64 d = (u64)dim;
+	u64 evals = 0, bytes = 0, pt = 0;
+	u32 cuts = 0, red = 0, mn = 0, zr = 0, ed = 0, pr = 0, rows = 0, inc = 0, adj = 0, gone = 0, done_slots = 0;
+	if (lane < n_commit) {
+		const WaveCut c = cut[lane];
+		const u64 N = c.live_before;
+		evals = N;
+		if (c.status & ST_REDUNDANT) {
+			red = 1;
+			bytes = N * (8 * d + 1);
+			rc[lane] = 1;
+		} else {
+			const u64 nm = c.n_minus, nz = c.n_zero, M = c.n_new, E = M - nz, Wd = ((u64)c.facet + 64) / 64, A = c.n_pairs;
+			cuts = 1; mn = c.n_minus; zr = c.n_zero; ed = (u32)E; pr = c.n_pairs;
+			pt = M * (M - (M ? 1 : 0)) / 2;
+			bytes = N * (8 * d + 1) + N + 4 * (nm + nz) + E * (24 * d + 24 * Wd) + nz * (16 * d + 16 * Wd) + 8 * M * Wd + 8 * A;
+			rows = c.n_new; inc = c.inc_new; adj = c.adj_new; gone = c.n_minus + c.n_zero;
+			rc[lane] = 0;
+		}
+		done_slots = 1u << w.wave[lane];
+	}
+	evals = wv_sum64(evals); bytes = wv_sum64(bytes); pt = wv_sum64(pt);
+	cuts = __reduce_add_sync(0xffffffffu, cuts); red = __reduce_add_sync(0xffffffffu, red);
+	mn = __reduce_add_sync(0xffffffffu, mn); zr = __reduce_add_sync(0xffffffffu, zr);
+	ed = __reduce_add_sync(0xffffffffu, ed); pr = __reduce_add_sync(0xffffffffu, pr);
+	rows = __reduce_add_sync(0xffffffffu, rows); inc = __reduce_add_sync(0xffffffffu, inc);
+	adj = __reduce_add_sync(0xffffffffu, adj); gone = __reduce_add_sync(0xffffffffu, gone);
+	done_slots = __reduce_or_sync(0xffffffffu, done_slots);
+	// the committed slots leave the pending list (order kept)
+	const u32 slot = lane < n_pending ? w.pending[lane] : 0u;
+	const bool keep = lane < n_pending && !((done_slots >> slot) & 1u);
+	const u32 kept = __ballot_sync(0xffffffffu, keep);
+	if (keep) w.pending[__popc(kept & ((1u << lane) - 1u))] = slot;
+	if ((done_slots >> lane) & 1u) w.slot_hs[lane] = B200_NONE;
+	if (lane == 0) {
+		w.st_evals += evals; w.st_bytes += bytes; w.st_cuts += cuts; w.st_redundant += red; w.st_minus += mn; w.st_zero += zr;
+		w.st_edge += ed; w.st_copies += zr; w.st_pair_tests += pt; w.st_pairs += pr;
+		w.st_deferred += n_wave - n_commit;
+		m.n_live = m.n_live + rows - gone;
+		m.nrows += rows;
+		m.slot_cnt += rows;
+		m.inc_used += inc;
+		m.adj_used += adj;
+		w.n_pending = __popc(kept);
+		w.done_hs += n_commit;
+		w.n_wave = w.n_commit = 0;
+		if (w.done_hs >= w.n_total) w.halt |= WH_DONE;
+		else if (m.nrows != m.n_live && m.nrows >= 4 * B200_TILE && m.nrows >= 2 * m.n_live) w.halt |= WH_COMPACT;
+	}
+	__syncwarp();
+}
+__device__ __forceinline__ void wave_la_plan_warp(WaveCtl &w, u32 nrows)
+{
+	const u32 lane = threadIdx.x & 31;
+	u32 n_la = 0, la_new = 0, n_pending = w.n_pending;
+	const u32 next_hs = w.next_hs, halt = w.halt, reclassify = w.reclassify;
+	__syncwarp();
+	if (!halt) {
+		if (reclassify) {                    // every pending list is stale: rebuild them in this pass
+			if (lane < n_pending) w.la[lane] = w.pending[lane];
+			n_la = n_pending;
+		}
+		if (n_pending < w.refill_below || n_la) {
+			const bool is_free = w.slot_hs[lane] == B200_NONE;
+			const u32 fm = __ballot_sync(0xffffffffu, is_free);
+			const u32 k = min(min((u32)B200_WAVE_SLOTS - n_pending, w.n_total - next_hs), (u32)__popc(fm));
+			const u32 r = __popc(fm & ((1u << lane) - 1u));
+			if (is_free && r < k) {          // the r-th free slot (ascending) takes the r-th next halfspace
+				w.slot_hs[lane] = next_hs + r;
+				w.pending[n_pending + r] = lane;
+				w.la[n_la + r] = lane;
+			}
+			la_new = (k >= 32 ? 0xffffffffu : ((1u << k) - 1u)) << n_la;
+			n_la += k;
+			n_pending += k;
+		}
+	}
+	if (lane == 0) {
+		if (!halt) {
+			w.reclassify = 0;
+			w.next_hs = next_hs + (n_pending - w.n_pending);
+			w.n_pending = n_pending;
+			if (n_la) { w.st_la_passes++; w.st_rows_scanned += nrows; }
+		}
+		w.n_la = n_la;
+		w.la_new = la_new;
+		if (!halt) w.la_rows = nrows;
+	}
+	__syncwarp();
+}
+
 __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const double *vals, const unsigned char *ideal)
 {
 	__shared__ WaveCtl w;
@@ -50,24 +154,30 @@ __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const 
 		if (threadIdx.x < n_commit) { wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]); s_hs[threadIdx.x] = cut[threadIdx.x].hs; }
 		__syncthreads();
 		if (tr) tr[41] = b200_globaltimer();
-		if (threadIdx.x == 0) {
-			wave_commit(w, mctl, cut, S.d, s_rc);
-			const u64 now = b200_globaltimer();
-			if (!w.t_first) w.t_first = now;
-			w.t_last = now;
-		}
-		__syncthreads();
-		if (threadIdx.x < n_commit) W.rc[s_hs[threadIdx.x]] = s_rc[threadIdx.x];
-		wv_copy_words(S.ctl, &mctl, sizeof mctl);
 	}
-	if (tr) tr[42] = b200_globaltimer();
-	if (threadIdx.x == 0) {
-		w.iter++;
-		if (W.trace) W.trace[(w.iter & 255u) << 6] = t_begin;
-		if (!w.halt) wave_la_plan(w, mctl.nrows);
+	if (threadIdx.x < 32) {
+		if (n_commit) {
+			wave_commit_warp(w, mctl, cut, S.d, s_rc);
+			if (threadIdx.x == 0) {
+				const u64 now = b200_globaltimer();
+				if (!w.t_first) w.t_first = now;
+				w.t_last = now;
+			}
+		}
+		if (tr) tr[42] = b200_globaltimer();
+		if (threadIdx.x == 0) {
+			w.iter++;
+			if (W.trace) W.trace[(w.iter & 255u) << 6] = t_begin;
+		}
+		__syncwarp();
+		wave_la_plan_warp(w, mctl.nrows);
 	}
 	__syncthreads();
 	if (tr) tr[43] = b200_globaltimer();
+	if (n_commit) {
+		if (threadIdx.x < n_commit) W.rc[s_hs[threadIdx.x]] = s_rc[threadIdx.x];
+		wv_copy_words(S.ctl, &mctl, sizeof mctl);
+	}
 	if (!w.halt && threadIdx.x < w.n_la) wave_la_init(S, W, w, threadIdx.x, vals, ideal);
 	wv_copy_words(W.wc, &w, sizeof w);
 	if (tr) tr[44] = b200_globaltimer();
