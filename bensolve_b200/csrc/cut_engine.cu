@@ -30,6 +30,11 @@ static thread_local std::string g_last_error;
 void b200_set_error(const std::string &msg) { g_last_error = msg; }
 const char *b200_get_error() { return g_last_error.c_str(); }
 
+static unsigned env_u32_early(const char *name, unsigned dflt)
+{
+	const char *e = getenv(name);
+	return e ? (unsigned)strtoul(e, nullptr, 10) : dflt;
+}
 static double g_t_malloc = 0, g_t_memset = 0, g_t_free = 0;   // B200_PHASES report (us, process-wide)
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -239,6 +244,89 @@ static u32 grow_to(u64 need, u64 have, u64 quad_below)
 	const u64 f = have < quad_below ? 4 : 2;
 	return (u32)std::min<u64>(0xFFFF0000ull, std::max<u64>(need, have * f));
 }
+
+// ------------------------------------------------------------------ multi-GPU look-ahead exchange area (one per process)
+// Receive area + flag words of this rank, exported with cudaIpc and mapped by every peer (and theirs by us); the
+// handles travel through one NCCL all-gather when the first device-resident batch of the process starts.  The pass
+// counter is process-wide and monotone (engines run one after the other on the calling thread, every rank issues the
+// same calls), so a flag word left by an earlier polytope never looks like a future pass.
+struct XArea {
+	bool tried = false, ok = false;
+	unsigned long long *send = nullptr, *recv = nullptr;
+	u32 *flag = nullptr;
+	unsigned long long *peer_recv[B200_X_MAXRANKS] = {nullptr};
+	u32 *peer_flag[B200_X_MAXRANKS] = {nullptr};
+	u32 seq = 0;
+};
+static XArea g_x;
+#ifndef B200_EMULATE
+static void xarea_setup(cudaStream_t st)
+{
+	if (g_x.tried) return;
+	g_x.tried = true;
+	const int G = g_comm.nranks, me = g_comm.rank;
+	if (G < 2 || G > B200_X_MAXRANKS || !g_comm.nccl_comm) return;
+	if (const char *e = getenv("B200_WAVE_SHARD")) if (atoi(e) == 0) return;
+	// every rank must take part in the all-gather below whatever happens locally: collect the local verdict first
+	struct Rec { cudaIpcMemHandle_t recv, flag; int ok; int pad[15]; } mine, *all = nullptr;
+	static_assert(sizeof(Rec) == 192, "exchange record");
+	memset(&mine, 0, sizeof mine);
+	const size_t recv_bytes = (size_t)G * 2 * B200_X_WORDS * 8;
+	bool ok = cudaMalloc((void **)&g_x.recv, recv_bytes) == cudaSuccess && cudaMalloc((void **)&g_x.flag, (size_t)G * 128) == cudaSuccess &&
+	          cudaMalloc((void **)&g_x.send, (size_t)B200_X_WORDS * 8) == cudaSuccess;
+	if (ok) {
+		cudaMemset(g_x.recv, 0, recv_bytes);
+		cudaMemset(g_x.flag, 0, (size_t)G * 128);
+		cudaMemset(g_x.send, 0, (size_t)B200_X_WORDS * 8);
+		ok = cudaIpcGetMemHandle(&mine.recv, g_x.recv) == cudaSuccess && cudaIpcGetMemHandle(&mine.flag, g_x.flag) == cudaSuccess;
+	}
+	(void)cudaGetLastError();
+	mine.ok = ok ? 1 : 0;
+	Rec *d_send = (Rec *)dalloc(sizeof(Rec)), *d_recv = (Rec *)dalloc(sizeof(Rec) * G);
+	h2d(d_send, &mine, sizeof mine);
+	nccl_check(g_nccl.all_gather(d_send, d_recv, sizeof(Rec), 0 /* ncclChar */, g_comm.nccl_comm, st), "ncclAllGather (ipc handles)");
+	CK(cudaStreamSynchronize(st));
+	std::vector<Rec> got(G);
+	d2h(got.data(), d_recv, sizeof(Rec) * G);
+	dfree(d_send); dfree(d_recv);
+	all = got.data();
+	for (int g = 0; g < G; g++) ok = ok && all[g].ok;
+	// opening may fail on one rank only (no peer access between two devices): a second all-gather settles the verdict
+	if (ok) {
+		for (int g = 0; g < G && ok; g++) {
+			if (g == me) continue;
+			void *a = nullptr, *b = nullptr;
+			ok = cudaIpcOpenMemHandle(&a, all[g].recv, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+			     cudaIpcOpenMemHandle(&b, all[g].flag, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+			g_x.peer_recv[g] = (unsigned long long *)a;
+			g_x.peer_flag[g] = (u32 *)b;
+		}
+		(void)cudaGetLastError();
+	}
+	int *d_v = (int *)dalloc(64), *d_vs = (int *)dalloc((size_t)64 * G);
+	int verdict[16] = {ok ? 1 : 0};
+	h2d(d_v, verdict, 64);
+	nccl_check(g_nccl.all_gather(d_v, d_vs, 64, 0, g_comm.nccl_comm, st), "ncclAllGather (ipc verdict)");
+	CK(cudaStreamSynchronize(st));
+	std::vector<int> vs((size_t)16 * G);
+	d2h(vs.data(), d_vs, (size_t)64 * G);
+	dfree(d_v); dfree(d_vs);
+	for (int g = 0; g < G; g++) ok = ok && vs[(size_t)16 * g];
+	g_x.ok = ok;
+	if (!ok && me == 0) fprintf(stderr, "[b200] peer-mapped exchange area unavailable: look-ahead passes stay replicated on every rank\n");
+}
+#else
+static void xarea_setup()
+{
+	if (g_x.tried) return;
+	g_x.tried = true;
+	const int G = g_comm.nranks;
+	if (G < 2 || G > B200_X_MAXRANKS || !g_comm.callback) return;
+	g_x.send = (unsigned long long *)calloc(B200_X_WORDS, 8);
+	g_x.recv = (unsigned long long *)calloc((size_t)G * B200_X_WORDS, 8);
+	g_x.ok = true;
+}
+#endif
 
 // ------------------------------------------------------------------ construction
 CutEngine::CutEngine(int dim) : d_(dim)
@@ -650,6 +738,7 @@ void CutEngine::launch_k1_lists(const CutParams &P, const double *dv, const unsi
 		}
 	}
 	if (sharded && nranks_ > 1) {        // exchange: pack -> all-gather over NVLink -> merge
+		stats_.sharded_cuts++;
 		k_xchg_pack<<<1, TAIL_THREADS, 0, STREAM>>>(S_);
 		nccl_check(g_nccl.all_gather(S_.xchg_send, S_.xchg_recv, (size_t)B200_XCHG_WORDS * 4, 0 /* ncclChar */, g_comm.nccl_comm, STREAM), "ncclAllGather");
 		k_xchg_merge<<<1, TAIL_THREADS, 0, STREAM>>>(S_, (u32)nranks_);
@@ -705,9 +794,9 @@ void CutEngine::launch_small(const CutParams &P, int mode, bool header_only)
 	const bool force_wide = (flags_ & 16) != 0;     // test hook: every cut through the widest cluster + the grid-wide pair test
 	const bool tiny = !force_wide && expect_vis_ <= one_cta_max && (expect_m_ <= B200_K4_SMALL / 2 || mode == 1);
 	// a polytope of a few thousand rows is classified inside the single-CTA tail: one launch per cut
-	const bool fused = tiny && hdr_.nrows <= fuse_max_rows && !dev_vals_ && nranks_ == 1;
+	const bool fused = tiny && hdr_.nrows <= fuse_max_rows && !dev_vals_ && !shard_now();
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
-	if (!fused) launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_, true);
+	if (!fused) launch_k1_lists(P, dev_vals_, dev_ideal_, dev_index_, shard_now());
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[1], STREAM));
 	const int mode_bits = mode | (fused ? TAIL_MODE_FUSED_K1 : 0);
 	const int ho = header_only ? 1 : 0;
@@ -976,8 +1065,10 @@ void CutEngine::launch_small(const CutParams &Pin, int mode, bool header_only)
 	CutCtl *c = S.ctl;
 	const CutParams P = emu_params(S, Pin, dev_vals_, dev_ideal_, dev_index_);
 	u32 tlo, thi;
-	tile_range(true, tlo, thi);
-	if (!emu_classify(S, P, tlo * B200_TILE, thi * B200_TILE, nranks_)) { launch_part_c(header_only); return; }
+	const bool shard = shard_now();
+	tile_range(shard, tlo, thi);
+	if (shard) stats_.sharded_cuts++;
+	if (!emu_classify(S, P, tlo * B200_TILE, thi * B200_TILE, shard ? nranks_ : 1)) { launch_part_c(header_only); return; }
 	if (c->n_vis > B200_VIS_MAX) { c->status |= ST_NEED_BIG; launch_part_c(header_only); return; }
 	emu_zp(S, P);
 	u32 H = 0;
@@ -1024,6 +1115,14 @@ void CutEngine::fetch_delta()
 }
 #endif
 
+// Is K1 of the next cut split across the ranks?  The exchange (pack, NCCL all-gather, merge) costs three launches and
+// ~25 us of collective latency per cut, K1 ~10 us per 10^6 rows: below a few million rows every rank classifies all
+// rows itself and nothing is exchanged (the ranks stay bit-identical either way).
+bool CutEngine::shard_now() const
+{
+	static const u32 min_rows = env_u32_early("B200_SHARD_MIN_ROWS", 4000000);
+	return nranks_ > 1 && hdr_.nrows >= min_rows;
+}
 // this rank's share of the tiles (all of them on one GPU); ranges ascend with the rank
 void CutEngine::tile_range(bool sharded, u32 &lo, u32 &hi) const
 {
@@ -1732,6 +1831,11 @@ void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigne
 		case 8: launch_wave_classify<8>(S_, WD_, gcl, STREAM); break;
 		default: launch_wave_classify<0>(S_, WD_, gcl, STREAM); break;
 		}
+		if (WD_.xsend) {                    // several GPUs: records of a sharded pass to the peers, theirs into our lists
+			launch_dependent(k_wave_xpush, (int)WD_.nranks, K_THREADS, STREAM, S_, WD_);
+			launch_dependent(k_wave_xmerge, (int)WD_.nranks * 4, K_THREADS, STREAM, S_, WD_);
+			stats_.kernel_launches += 2;
+		}
 		launch_dependent(k_wave_mark, num_sms_, K_THREADS, STREAM, S_, WD_);
 		launch_dependent(k_wave_check, num_sms_, K_THREADS, STREAM, S_, WD_);
 		launch_clusters(k_wave_tailA<WAVE_NC>, nclu, WAVE_NC, STREAM, S_, WD_);
@@ -1752,11 +1856,29 @@ void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigne
 // ---- host-side test double of the wave kernels: the same bodies, run serially
 static void emu_wave_classify(const DevState &S, const WaveDev &W)
 {
-	const WaveCtl *w = W.wc;
+	WaveCtl *w = W.wc;
 	if (w->halt) return;
+	u32 r_lo = 0, r_hi = w->la_rows;
+	if (w->shard) {                      // this rank's row groups, entries into the exchange record
+		const u32 ngroups = (w->la_rows + B200_WV_GROUP - 1) / B200_WV_GROUP;
+		u32 g_lo, g_hi;
+		wave_shard_range(W, ngroups, g_lo, g_hi);
+		r_lo = std::min<u32>(w->la_rows, g_lo * B200_WV_GROUP);
+		r_hi = std::min<u32>(w->la_rows, g_hi * B200_WV_GROUP);
+	}
 	for (u32 k = 0; k < w->n_la; k++)
-		for (u32 r = 0; r < w->la_rows; r++)
-			if (bit_test(S.live, r)) wave_classify_row(S, W, w->la[k], r);
+		for (u32 r = r_lo; r < r_hi; r++)
+			if (bit_test(S.live, r)) wave_classify_row(S, W, w->la[k], r, w->shard != 0);
+	if (!w->shard) return;
+	// exchange (all-gather through the host callback), then every record into the lists
+	g_comm.callback(W.xsend, W.xrecv, (size_t)B200_X_WORDS * 8);
+	for (u32 g = 0; g < W.nranks; g++) {
+		const unsigned long long *rec = W.xrecv + (size_t)g * B200_X_WORDS;
+		if (rec[1] != w->xseq) fail("multi-rank test double: exchange record of another pass");
+		if (rec[0] > B200_X_CAP) { w->halt |= WH_XOVER; continue; }
+		for (u32 x = 0; x < (u32)rec[0]; x++) wave_merge_entry(W, rec[2 + x]);
+	}
+	if (w->halt) wave_publish(W, *w, S.ctl->nrows, S.ctl->n_live);
 }
 static void emu_wave_form(const DevState &S, const WaveDev &W)
 {
@@ -1936,6 +2058,8 @@ static void emu_wave_begin(const DevState &S, const WaveDev &W, const double *va
 	w.iter++;
 	if (!w.halt) {
 		wave_la_plan(w, S.ctl->nrows);
+		wave_shard_plan(w, W, S.ctl->nrows);
+		if (w.shard) { W.xsend[0] = 0; W.xsend[1] = w.xseq; }
 		for (u32 k = 0; k < w.n_la; k++) wave_la_init(S, W, w, k, vals, ideal);
 	}
 	wave_publish(W, w, S.ctl->nrows, S.ctl->n_live);
@@ -1958,7 +2082,7 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 {
 	static const u32 min_live = env_u32("B200_WAVE_MIN_LIVE", 20000);    // below: one launch per cut (classic path) wins
 	const bool tiny_test = (flags_ & 32) != 0;                            // test hook: waves from the first halfspace on
-	const bool enabled = (env_u32("B200_WAVES", 1) != 0 || tiny_test) && !(flags_ & (4 | 64)) && nranks_ == 1 && n < B200_WV_ROW_MASK;
+	const bool enabled = (env_u32("B200_WAVES", 1) != 0 || tiny_test) && !(flags_ & (4 | 64)) && n < B200_WV_ROW_MASK;
 	std::vector<int> rc_host(n, -1);
 	long cuts = 0;
 	u64 i = 0;
@@ -1998,8 +2122,24 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 			wave_ensure_scratch(facet0 + (u32)n + 1, std::max<u32>(1u << 17, WD_.cap_pairs), std::max<u64>(k4_words(wl_ub, 2048, wl_ub * 64), WD_.cap_bits));
 		}
 		if (wave_rc_cap_ < n) { wave_fresh(WD_.rc, n); wave_rc_cap_ = n; }
+		// several ranks: the look-ahead passes over large polytopes are sharded, exchanged over peer-mapped memory
+		WD_.nranks = (u32)nranks_;
+		WD_.rank = (u32)rank_;
+		WD_.shard_min_rows = tiny_test ? 0u : env_u32("B200_SHARD_MIN_ROWS_WAVE", 1500000);
+		if (nranks_ > 1) {
+#ifndef B200_EMULATE
+			xarea_setup(STREAM);
+#else
+			xarea_setup();
+#endif
+			if (g_x.ok) {
+				WD_.xsend = g_x.send; WD_.xrecv = g_x.recv; WD_.xflag = g_x.flag;
+				for (int g = 0; g < B200_X_MAXRANKS; g++) { WD_.xpeer_recv[g] = g_x.peer_recv[g]; WD_.xpeer_flag[g] = g_x.peer_flag[g]; }
+			}
+		}
 		WaveCtl wc;
 		memset(&wc, 0, sizeof wc);
+		wc.xseq = g_x.seq;
 		wc.n_total = (u32)n;
 		wc.facet0 = facet0;
 		wc.batch_first = batch_first;
@@ -2065,6 +2205,11 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 			} else if (wc.halt & WH_COMPACT) {
 				compact();
 				wc.reclassify = 1;
+			} else if (wc.halt & WH_XFAIL) {
+				fail("bensolve_b200: a peer rank's look-ahead record did not arrive (rank died or lost its device)");
+			} else if (wc.halt & WH_XOVER) {       // (on every rank alike) rebuild the lists of this pass unsharded
+				wc.noshard_once = 1;
+				wc.reclassify = 1;
 			}
 			if (wc.done_hs >= wc.n_total) break;
 			wave_ensure_scratch(WD_.cap_facets, WD_.cap_pairs, WD_.cap_bits);   // the mark array follows the row capacity
@@ -2072,6 +2217,7 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 			wave_upload_ctl(wc);
 		}
 		wave_epoch_ = wc.epoch + 1;
+		g_x.seq = wc.xseq;
 		// results and statistics of the wave run
 		std::vector<int> rc_dev(n);
 		d2h(rc_dev.data(), WD_.rc, n * sizeof(int));
@@ -2081,7 +2227,7 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 		stats_.cuts += wc.st_cuts; stats_.redundant += wc.st_redundant; stats_.vertex_evals += wc.st_evals; stats_.rows_scanned += wc.st_rows_scanned;
 		stats_.minus += wc.st_minus; stats_.zero += wc.st_zero; stats_.edge_vertices += wc.st_edge; stats_.copies += wc.st_copies;
 		stats_.pair_tests += wc.st_pair_tests; stats_.new_adjacent_pairs += wc.st_pairs; stats_.algorithmic_bytes += wc.st_bytes;
-		stats_.waves += wc.st_waves; stats_.wave_cuts += wc.st_cuts + wc.st_redundant; stats_.la_passes += wc.st_la_passes; stats_.wave_deferred += wc.st_deferred;
+		stats_.waves += wc.st_waves; stats_.wave_cuts += wc.st_cuts + wc.st_redundant; stats_.la_passes += wc.st_la_passes; stats_.wave_deferred += wc.st_deferred; stats_.sharded_passes += wc.st_sharded;
 		small_dirty_ = true;
 		expect_vis_ = expect_m_ = 0;
 		if (WD_.trace) {            // start of each kernel of the last iterations, relative to the iteration's first kernel

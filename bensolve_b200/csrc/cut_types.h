@@ -175,8 +175,20 @@ enum : u32 {                     // WaveCtl::halt
 	WH_GROW = 4u,                // rows / incidence pool too small for the next wave: halt_rows / halt_inc say how much is needed
 	WH_GROW_ADJ = 8u,            // adjacency pool too small: grow, then redo only the adjacency build of this wave
 	WH_COMPACT = 16u,            // dead rows outnumber live ones: compact, rebuild the look-ahead lists
-	WH_GROW_PAIRS = 32u          // pair buffers of a wave position too small: grow, then redo the pair test and the adjacency build
+	WH_GROW_PAIRS = 32u,         // pair buffers of a wave position too small: grow, then redo the pair test and the adjacency build
+	WH_XOVER = 64u,              // a rank's exchange record overflowed: the lists of this pass are rebuilt unsharded
+	WH_XFAIL = 128u              // a peer's record did not arrive (the host reports the failure)
 };
+
+// Multi-GPU look-ahead (state replicated, one process per GPU): a pass over >= shard_min_rows rows is split by row
+// group across the ranks; each rank collects its list entries in a send record, stores the record into every
+// peer's receive area over NVLink (peer-mapped memory, cudaIpc) and publishes the pass number in the peer's flag
+// word; the merge kernel of each rank waits for the flags and appends all records to its own lists.  No host
+// involvement and no collective launch: every rank's scheduler takes the same decisions from the same state.
+#define B200_X_CAP 16382u        // entries (u64: slot << 32 | list entry) per record
+#define B200_X_WORDS (B200_X_CAP + 2u)   // u64 words per record: [0] = entry count (may exceed the capacity = overflow), [1] = pass number
+#define B200_X_MAXRANKS 8
+#define B200_WV_GROUP 512u         // rows per group of the look-ahead kernel (2 per thread of a 256-thread block): the unit of the rank split
 #define ST_WAVE_DEFER 2048u      // (CutCtl::status, wave path) this cut goes back to the pending list untouched
 
 struct WaveCtl {
@@ -205,11 +217,13 @@ struct WaveCtl {
 	u32 iter;                    // completed wave iterations
 	u32 halt, halt_hs, halt_rows, halt_inc, halt_adj, halt_pairs;
 	u32 la_new;                  // bit k: entry k of `la` is a halfspace that just received its slot (parameters to be built)
-	u32 pad0;
+	u32 shard;                   // this look-ahead pass is sharded across the ranks (row groups by rank, exchange over peer memory)
 	u64 halt_bits;
+	u32 xseq;                    // sequence number of the latest sharded pass (process-wide, identical on every rank)
+	u32 noshard_once;            // the next pass runs unsharded (an exchange record overflowed)
 	// ---- statistics (same meaning as EngineStats)
 	u64 st_cuts, st_redundant, st_evals, st_rows_scanned, st_minus, st_zero, st_edge, st_copies, st_pair_tests, st_pairs, st_bytes;
-	u64 st_waves, st_la_passes, st_deferred;
+	u64 st_waves, st_la_passes, st_deferred, st_sharded;
 	u64 t_first, t_last;         // %globaltimer of the first and the latest commit (diagnostics)
 };
 // The kernels stage WaveCtl in shared memory, let one thread work on the copy and write it back with all threads
@@ -244,4 +258,11 @@ struct WaveDev {                 // device pointers of the wave path (kernel arg
 	u32 cap_new, cap_pairs, cap_facets;   // per wave position
 	u64 cap_bits;
 	u32 cap_he;
+	// multi-GPU look-ahead exchange (null / 0 on one GPU)
+	u32 nranks, rank, shard_min_rows;
+	unsigned long long *xsend;                 // [B200_X_WORDS] this rank's record of the current pass
+	unsigned long long *xrecv;                 // [nranks][2][B200_X_WORDS] records stored by the peers (double-buffered by pass parity)
+	u32 *xflag;                                // [nranks * 32] pass number published by each peer (one 128-byte line each)
+	unsigned long long *xpeer_recv[B200_X_MAXRANKS];   // peer-mapped xrecv of every other rank
+	u32 *xpeer_flag[B200_X_MAXRANKS];          // peer-mapped xflag of every other rank
 };

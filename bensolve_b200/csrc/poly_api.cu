@@ -853,6 +853,8 @@ extern "C" int b200_poly_get_stats(poly_args *a, b200_stats *out)
 	out->kernel_launches = s.kernel_launches; out->compactions = s.compactions;
 	out->live_vertices = h->engine->live_vertices(); out->slots = h->engine->slots(); out->facets = a->dual.cnt;
 	out->classify_ms = s.classify_ms; out->cut_ms = s.cut_ms;
+	out->waves = s.waves; out->wave_cuts = s.wave_cuts; out->lookahead_passes = s.la_passes; out->sharded_passes = s.sharded_passes;
+	out->sharded_cuts = s.sharded_cuts;
 	return 0;
 }
 

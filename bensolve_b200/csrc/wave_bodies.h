@@ -77,8 +77,14 @@ B200_HD void wave_list_append(const WaveDev &W, u32 slot, u32 row, u32 code)
 	const u32 pos = B200_ATOMIC_ADD(&W.ctl[slot].n_list, 1u);
 	if (pos < B200_WAVE_LIST) W.list[(size_t)slot * B200_WAVE_LIST + pos] = row | (code << B200_WV_ROW_BITS);
 }
+// (sharded pass) the entry goes to this rank's exchange record instead
+B200_HD void wave_send_append(const WaveDev &W, u32 slot, u32 row, u32 code)
+{
+	const u32 pos = B200_ATOMIC_ADD((u32 *)W.xsend, 1u);        // low word of xsend[0] (little endian): the entry count
+	if (pos < B200_X_CAP) W.xsend[2 + pos] = ((unsigned long long)slot << 32) | (row | (code << B200_WV_ROW_BITS));
+}
 // one live row against the halfspace of one slot (rows a cut creates; the look-ahead kernel has a vectorised form)
-B200_HD void wave_classify_row(const DevState &S, const WaveDev &W, u32 slot, u32 r)
+B200_HD void wave_classify_row(const DevState &S, const WaveDev &W, u32 slot, u32 r, bool to_send = false)
 {
 	const CutParams &P = W.cur[slot];
 	const int id = bit_test(S.ideal, r) ? 1 : 0;
@@ -89,7 +95,9 @@ B200_HD void wave_classify_row(const DevState &S, const WaveDev &W, u32 slot, u3
 		xinf = a > xinf ? a : xinf;
 	}
 	const u32 code = wave_code(t, id, P, xinf);
-	if (code != 0xFFu) wave_list_append(W, slot, r, code);
+	if (code == 0xFFu) return;
+	if (to_send) wave_send_append(W, slot, r, code);
+	else wave_list_append(W, slot, r, code);
 }
 
 B200_HD void wave_reset_slot(CutCtl *c)
@@ -153,6 +161,32 @@ B200_HD void wave_la_plan(WaveCtl &w, u32 nrows)
 		w.st_la_passes++;
 		w.st_rows_scanned += nrows;
 	}
+}
+// Is the pass just planned split across the ranks?  Every rank decides the same from the same numbers.
+B200_HD void wave_shard_plan(WaveCtl &w, const WaveDev &W, u32 nrows)
+{
+	w.shard = 0;
+	if (w.halt || !w.n_la) return;
+	if (W.nranks > 1 && W.xsend && nrows >= W.shard_min_rows && !w.noshard_once) {
+		w.shard = 1;
+		w.xseq++;
+		w.st_sharded++;
+	}
+	w.noshard_once = 0;
+}
+// this rank's share of the `ngroups` row groups of a sharded pass (ranges ascend with the rank)
+B200_HD void wave_shard_range(const WaveDev &W, u32 ngroups, u32 &lo, u32 &hi)
+{
+	const u32 per = (ngroups + W.nranks - 1) / W.nranks;
+	lo = per * W.rank < ngroups ? per * W.rank : ngroups;
+	hi = lo + per < ngroups ? lo + per : ngroups;
+}
+// entry e of a received (or the own) record goes to the list of its slot
+B200_HD void wave_merge_entry(const WaveDev &W, unsigned long long e)
+{
+	const u32 slot = (u32)(e >> 32), ent = (u32)e;
+	const u32 pos = B200_ATOMIC_ADD(&W.ctl[slot].n_list, 1u);
+	if (pos < B200_WAVE_LIST) W.list[(size_t)slot * B200_WAVE_LIST + pos] = ent;
 }
 // entry k of the pass: empty list; a halfspace that just received its slot also gets its parameters and its facet
 B200_HD void wave_la_init(const DevState &S, const WaveDev &W, const WaveCtl &w, u32 k, const double *vals, const unsigned char *ideal)

@@ -21,6 +21,7 @@
 #define WV_TRACE(k) do { if (W.trace && blockIdx.x == 0 && threadIdx.x == 0) W.trace[((W.wc->iter & 255u) << 6) + (k)] = b200_globaltimer(); } while (0)
 // phase stamps inside a kernel (block 0 = CTA 0 of the first cluster)
 #define WV_TP(k) do { if (W.trace && blockIdx.x == 0 && threadIdx.x == 0) W.trace[((w_iter & 255u) << 6) + (k)] = b200_globaltimer(); } while (0)
+static_assert(B200_WV_GROUP == 2 * K_THREADS, "look-ahead row group");
 #define WAVE_NC 8              // CTAs per cluster of the per-cut kernels: 16 clusters of 8 are co-resident on 148 SMs
 
 // all threads of the block copy `bytes` (a multiple of 4) -- the caller synchronises
@@ -171,6 +172,10 @@ __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const 
 		}
 		__syncwarp();
 		wave_la_plan_warp(w, mctl.nrows);
+		if (threadIdx.x == 0) {
+			wave_shard_plan(w, W, mctl.nrows);
+			if (w.shard) { W.xsend[0] = 0; W.xsend[1] = w.xseq; }
+		}
 	}
 	__syncthreads();
 	if (tr) tr[43] = b200_globaltimer();
@@ -214,7 +219,10 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_classify(DevState S, WaveDev
 	__syncthreads();
 	const size_t cap = S.cap_rows;
 	const u32 nrows = w->la_rows, ngroups = (nrows + 2 * K_THREADS - 1) / (2 * K_THREADS);
-	for (u32 g = blockIdx.x; g < ngroups; g += gridDim.x) {
+	const bool shard = w->shard != 0;        // several GPUs: this rank's row groups only, entries into the exchange record
+	u32 g_lo = 0, g_hi = ngroups;
+	if (shard) wave_shard_range(W, ngroups, g_lo, g_hi);
+	for (u32 g = g_lo + blockIdx.x; g < g_hi; g += gridDim.x) {
 		const u32 r = g * 2 * K_THREADS + 2 * threadIdx.x;
 		const u32 lw = S.live[r >> 5] >> (r & 31), iw = S.ideal[r >> 5] >> (r & 31);
 		double2 x[DD];
@@ -244,10 +252,76 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_classify(DevState S, WaveDev
 				if (t[s] > s_thr[k][id] + g2) continue;                                   // safely PLUS
 				u32 code = t[s] > s_thr[k][id] ? CLS_PLUS : t[s] > s_thr[k][2 + id] ? CLS_ZP : t[s] > s_thr[k][4 + id] ? CLS_ZERO : CLS_MINUS;
 				if (t[s] < s_thr[k][4 + id]) code |= B200_WV_STRICT;
-				wave_list_append(W, s_slot[k], r + s, code);
+				if (shard) wave_send_append(W, s_slot[k], r + s, code);
+				else wave_list_append(W, s_slot[k], r + s, code);
 			}
 		}
 	}
+}
+
+// ---------------------------------------------------------------- multi-GPU exchange of a sharded look-ahead pass
+__device__ __forceinline__ u32 wv_ld_acquire_sys(const u32 *p)
+{
+	u32 v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void wv_st_release_sys(u32 *p, u32 v)
+{
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// block p stores this rank's record into rank p's receive area (peer-mapped memory: the stores travel over NVLink)
+// and then publishes the pass number in p's flag word for this rank
+__global__ void __launch_bounds__(K_THREADS) k_wave_xpush(DevState S, WaveDev W)
+{
+	cudaGridDependencySynchronize();
+	const WaveCtl *w = W.wc;
+	if (w->halt || !w->shard) return;
+	const u32 p = blockIdx.x;
+	if (p >= W.nranks || p == W.rank) return;
+	const u32 seq = w->xseq;
+	const unsigned long long cnt = W.xsend[0];
+	const u32 n = (u32)(cnt < B200_X_CAP ? cnt : B200_X_CAP) + 2;
+	unsigned long long *dst = W.xpeer_recv[p] + ((size_t)W.rank * 2 + (seq & 1u)) * B200_X_WORDS;
+	for (u32 x = threadIdx.x; x < n; x += K_THREADS) dst[x] = W.xsend[x];
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) wv_st_release_sys(W.xpeer_flag[p] + W.rank * 32, seq);
+}
+// blocks (src, part): wait for rank src's record of this pass, append its entries to the lists of their slots
+__global__ void __launch_bounds__(K_THREADS) k_wave_xmerge(DevState S, WaveDev W)
+{
+	__shared__ u32 s_ok;
+	cudaGridDependencySynchronize();
+	WaveCtl *w = W.wc;
+	if (w->halt || !w->shard) return;
+	const u32 src = blockIdx.x % W.nranks, part = blockIdx.x / W.nranks, nparts = gridDim.x / W.nranks;
+	if (part >= nparts) return;
+	const u32 seq = w->xseq;
+	const unsigned long long *rec = W.xsend;
+	if (src != W.rank) {
+		if (threadIdx.x == 0) {
+			const u64 t0 = b200_globaltimer();
+			u32 ok = 1;
+			while ((int)(wv_ld_acquire_sys(W.xflag + src * 32) - seq) < 0) {
+				if (b200_globaltimer() - t0 > 4000000000ull) { ok = 0; break; }      // 4 s: the peer is gone
+				__nanosleep(100);
+			}
+			s_ok = ok;
+		}
+		__syncthreads();
+		if (!s_ok) {
+			if (threadIdx.x == 0) { const u32 h = atomicOr(&w->halt, (u32)WH_XFAIL) | WH_XFAIL; W.progress->halt = h; }
+			return;
+		}
+		rec = W.xrecv + ((size_t)src * 2 + (seq & 1u)) * B200_X_WORDS;
+	}
+	const unsigned long long cnt = __ldcg(rec);
+	if (cnt > B200_X_CAP) {                 // every rank sees the same count and halts the same way
+		if (part == 0 && threadIdx.x == 0) { const u32 h = atomicOr(&w->halt, (u32)WH_XOVER) | WH_XOVER; W.progress->halt = h; }
+		return;
+	}
+	for (u32 x = part * K_THREADS + threadIdx.x; x < (u32)cnt; x += nparts * K_THREADS) wave_merge_entry(W, __ldcg(rec + 2 + x));
 }
 
 // ---------------------------------------------------------------- wave formation (two grid-wide kernels)

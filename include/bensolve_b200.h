@@ -145,6 +145,10 @@ typedef struct {
 	uint64_t live_vertices, slots, facets; /* current */
 	double classify_ms;        /* sum of CUDA-event times of K1 when timing is enabled */
 	double cut_ms;             /* sum of CUDA-event times of whole cuts when timing is enabled */
+	/* device-resident batches (wave path): waves run, cuts they carried out, look-ahead passes over the coordinates,
+	 * and how many of those passes were split across the ranks (several GPUs) */
+	uint64_t waves, wave_cuts, lookahead_passes, sharded_passes;
+	uint64_t sharded_cuts;     /* per-call path: cuts whose K1 was split across the ranks */
 } b200_stats;
 int b200_poly_get_stats(poly_args *, b200_stats *out);
 /* flags: bit0 = time every K1 launch and every cut with CUDA events (adds two syncs per cut);

@@ -8,6 +8,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
+os.environ.setdefault("B200_SHARD_MIN_ROWS", "0")        # shard K1 of every cut, however small the polytope
+os.environ.setdefault("B200_SHARD_MIN_ROWS_WAVE", "0")   # and every look-ahead pass of the wave path
+
 import torch.distributed as dist  # noqa: E402
 
 from bensolve_b200 import build, capi, dist as bdist, polytopes as P  # noqa: E402
@@ -27,10 +30,24 @@ def main():
         ra, rb = P.replay(a, tr), P.replay(b, tr)
         assert ra == rb, tr.name
         capi.compare_states(a.state(), b.state(), exact_coords=True)
+        assert b.stats()["sharded_cuts"] > 0
         a.kill(); b.kill()
+    # wave path (device-resident batches): look-ahead passes split by row group, records exchanged through the callback
+    n_wave = 0
+    for tr, chunk in [(P.tangent_polytope(5, 120, 7), 0), (P.tangent_polytope(4, 500, 3), 0), (P.lattice_polytope(4, 60, 3), 7),
+                      (P.mixed_polyhedron(4, 80, 5), 0), (P.cube_zero_plus(4), 0)]:
+        a = capi.PolyEngine(oracle, tr.dim)
+        b = capi.PolyEngine(emul, tr.dim, flags=32)           # waves from the first halfspace on
+        ra, rb = P.replay(a, tr), P.replay_batched(b, tr, chunk)
+        assert ra == rb, tr.name
+        capi.compare_states(a.state(), b.state(), exact_coords=True)
+        st = b.stats()
+        a.kill(); b.kill()
+        assert st["sharded_passes"] > 0 and st["sharded_passes"] == st["lookahead_passes"], st
+        n_wave += 1
     bdist.finalize_comm(emul)
     dist.barrier()
-    print(f"rank {rank}: {len(traces)} traces OK", flush=True)
+    print(f"rank {rank}: {len(traces)} traces OK, {n_wave} wave traces OK", flush=True)
     dist.destroy_process_group()
 
 

@@ -7,6 +7,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
+os.environ.setdefault("B200_SHARD_MIN_ROWS", "0")        # shard K1 of every cut, however small the polytope
+os.environ.setdefault("B200_SHARD_MIN_ROWS_WAVE", "0")   # and every look-ahead pass of the wave path
+
 import ctypes as C  # noqa: E402
 
 import torch  # noqa: E402
@@ -40,6 +43,16 @@ def main():
     assert ra == rb
     capi.compare_states(a.state(), b.state(), exact_coords=True)
     a.kill(); b.kill()
+    # wave path with the look-ahead passes sharded and exchanged over peer-mapped memory (waves from the first halfspace on)
+    for tr in [P.tangent_polytope(5, 400, 3), P.tangent_polytope(6, 300, 88), P.tangent_polytope(4, 3000, 21), P.lattice_polytope(4, 60, 3),
+               P.mixed_polyhedron(4, 80, 5)]:
+        a, b = capi.PolyEngine(oracle, tr.dim), capi.PolyEngine(lib, tr.dim, flags=32)
+        ra, rb = P.replay(a, tr), P.replay_batched(b, tr, 0)
+        assert ra == rb, tr.name
+        capi.compare_states(a.state(), b.state(), exact_coords=True)
+        st = b.stats()
+        assert st["sharded_passes"] > 0, st
+        a.kill(); b.kill()
     torch.cuda.synchronize()
     dist.barrier()
     bdist.finalize_comm(lib)
