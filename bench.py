@@ -326,13 +326,17 @@ def run_b200(a, trace):
     failure = None
     try:
         # (1) full sequence, both paths: properties of a simple polytope + the two paths give the same polytope
-        snap_b, snap_e = INV.Snapshot(eng), INV.Snapshot(eng_e2e)
-        inv_b = INV.check_simple_polytope(snap_b)
-        inv_e = INV.check_simple_polytope(snap_e)
-        dg_b, dg_e = INV.digest(snap_b), INV.digest(snap_e)
+        import gc
+        snap = INV.Snapshot(eng)             # (one snapshot at a time: ~10 GB of host arrays at 10^7 vertices, per rank)
+        inv_b, dg_b = INV.check_polytope(snap), INV.digest(snap)
+        del snap
+        gc.collect()
+        snap = INV.Snapshot(eng_e2e)
+        inv_e, dg_e = INV.check_polytope(snap), INV.digest(snap)
+        del snap
+        gc.collect()
         assert dg_b == dg_e, "device-resident batch path and per-call path end in different polytopes"
         assert inv_b["facets"] == n, "a tangent halfspace was lost"
-        del snap_b, snap_e
         # (2) the prefix the CPU reference can do: bit-exact comparison with the unmodified bslv_poly.c, both paths
         eb, _, _ = step_value(count=prefix, keep=True)
         ee, _, _ = step_e2e(count=prefix, keep=True)
@@ -358,7 +362,7 @@ def run_b200(a, trace):
                        "live_vertices": ref_live, "batch_path": "identical (structure after canonical sorting, coordinates bit-exact)",
                        "per_call_path": "identical (structure after canonical sorting, coordinates bit-exact)"},
             "full_sequence": {"batch_path": inv_b, "per_call_path": inv_e, "batch_vs_per_call": "identical", "sha256": dg_b,
-                              "properties": "every vertex on exactly d facets with d neighbours; adjacency symmetric; adjacent vertices share exactly d-1 facets; "
+                              "properties": "every vertex on >= d facets with >= d neighbours (equality except the counted non_simple_vertices, copies of vertices within 1e-9 of a later hyperplane); adjacency symmetric; adjacent vertices share d-1 facets; "
                                             "facet sets unique; facet lists = transpose of incidence lists; E = V*d/2; every vertex tight on its facets (1e-7), "
                                             "sampled vertices feasible for every halfspace and tight on no other"},
             "ranks_identical": ranks_identical,
