@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--ref-prefix", type=int, default=300, help="halfspaces of the trace the CPU reference is timed on")
     ap.add_argument("--classify-iters", type=int, default=30)
+    ap.add_argument("--solve-time", default="ex10", help="reference example (oracle/_ref/ex/NAME.vlp) whose end-to-end solve time is measured with both engines (1 GPU only; empty = skip)")
     ap.add_argument("--shapes", default="3:200000,5:12000", help="dim:halfspaces of the extra vertex-eval shapes (1 GPU only; empty = skip)")
     return ap.parse_args()
 
@@ -433,6 +434,15 @@ def run_b200(a, trace):
                                "note": "all three on the first %d halfspaces of the trace (identical inputs, identical result: parity.prefix)" % prefix}
         if a.shapes and world == 1:
             line["shapes"] = run_shapes(lib, a, peak)
+        ex = os.path.join(REPO, "oracle", "_ref", "ex", a.solve_time + ".vlp")
+        if a.solve_time and world == 1 and os.path.exists(ex) and os.path.exists(os.path.join(REPO, "oracle", "_ref", "libbensolve_host.so")):
+            # third component of the metric: bensolve's own "CPU time" for a whole solve, reference engine vs B200 engine
+            sys.path.insert(0, os.path.join(REPO, "tools"))
+            import solve_time
+            try:
+                line["solve_time"] = solve_time.compare(ex)
+            except Exception as exc:      # (the LP stand-in needs scipy; never let it take the bench line down)
+                line["solve_time"] = {"error": str(exc)[-300:]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -161,6 +161,34 @@ B200_HD u32 isect_count(const u32 *a, u32 na, const u32 *b, u32 nb)
 	return n;
 }
 
+// On-plane vertex whose incidence list is longer than the shared-facet mask (B200_MAXINC positions): does facet x of
+// inc(v) also lie on one of v's PLUS neighbours (bslv_poly.c:637-652)?  The mask-free form: a binary search in each
+// PLUS neighbour's sorted list.  Rare and slow by design -- it is what keeps a recession direction of an upper image
+// (on thousands of facets after thousands of Benson cuts) from being an error.
+B200_HD bool zero_keeps_facet(const DevState &S, u32 v, u32 x)
+{
+	for (u32 q = 0, off = S.adj_off[v], n = S.adj_len[v]; q < n; q++) {
+		const u32 k = S.adj_pool[off + q];
+		if (S.cls[k] != CLS_PLUS) continue;
+		const u32 *ik = S.inc_pool + S.inc_off[k];
+		u32 lo = 0, hi = S.inc_len[k];
+		while (lo < hi) {
+			const u32 mid = (lo + hi) >> 1;
+			if (ik[mid] < x) lo = mid + 1;
+			else hi = mid;
+		}
+		if (lo < S.inc_len[k] && ik[lo] == x) return true;
+	}
+	return false;
+}
+B200_HD u32 zero_long_count(const DevState &S, u32 v)
+{
+	const u32 *iv = S.inc_pool + S.inc_off[v];
+	u32 n = 0;
+	for (u32 a = 0, niv = S.inc_len[v]; a < niv; a++) n += zero_keeps_facet(S, v, iv[a]) ? 1u : 0u;
+	return n;
+}
+
 // K3a: how many new rows / incidence entries / PLUS neighbours visited entry i produces
 // (sizes of what bslv_poly.c:573-588 and :597-665 append)
 B200_HD void count_outputs(const DevState &S, u32 i)
@@ -172,7 +200,7 @@ B200_HD void count_outputs(const DevState &S, u32 i)
 		const u32 *iv = S.inc_pool + S.inc_off[v];
 		const u32 niv = S.inc_len[v];
 		u64 mask[B200_MAXINC / 64] = {0};
-		if (c == CLS_ZERO && niv > B200_MAXINC) B200_ATOMIC_OR(&S.ctl->status, (u32)ST_ERR_DEGENERATE);
+		const bool zlong = c == CLS_ZERO && niv > B200_MAXINC;       // longer than the mask: counted without it below
 		for (u32 q = 0, off = S.adj_off[v], n = S.adj_len[v]; q < n; q++) {
 			u32 k = S.adj_pool[off + q];
 			if (S.cls[k] != CLS_PLUS) continue;
@@ -181,7 +209,7 @@ B200_HD void count_outputs(const DevState &S, u32 i)
 			const u32 nik = S.inc_len[k];
 			if (c == CLS_MINUS)
 				inc_sz += 1 + isect_count(iv, niv, ik, nik);
-			else {
+			else if (!zlong) {
 				u32 a = 0, b = 0;
 				while (a < niv && a < B200_MAXINC && b < nik) {
 					u32 x = iv[a], y = ik[b];
@@ -194,10 +222,12 @@ B200_HD void count_outputs(const DevState &S, u32 i)
 		if (c == CLS_ZERO) {
 			n_out = 1;
 			inc_sz = 1;
-			for (int w = 0; w < B200_MAXINC / 64; w++) {
-				u64 m = mask[w];
-				while (m) { m &= m - 1; inc_sz++; }
-			}
+			if (zlong) inc_sz += zero_long_count(S, v);
+			else
+				for (int w = 0; w < B200_MAXINC / 64; w++) {
+					u64 m = mask[w];
+					while (m) { m &= m - 1; inc_sz++; }
+				}
 		} else
 			n_out = nplus;
 	}
@@ -425,8 +455,9 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 	const u32 niv = S.inc_len[v];
 	u32 w = ipos;
 	bool placed = false;                      // f keeps the list sorted (see emit_edge_inc)
-	for (u32 a = 0; a < niv && a < B200_MAXINC; a++)
-		if ((mask[a >> 6] >> (a & 63)) & 1) {
+	const bool zlong = niv > B200_MAXINC;     // (then the mask was not built: each facet is tested directly)
+	for (u32 a = 0; a < niv; a++)
+		if (zlong ? zero_keeps_facet(S, v, iv[a]) : (bool)((mask[a >> 6] >> (a & 63)) & 1)) {
 			if (!placed && iv[a] > f) { S.inc_pool[w++] = f; placed = true; }
 			S.inc_pool[w++] = iv[a];
 			B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
@@ -477,7 +508,7 @@ B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
 			if (S.cls[k] != CLS_PLUS) continue;
 			S.padj[ppos + np++] = k;
 			rewire(S, k, v, nw);
-			shared_facet_mask(S, v, k, mask);
+			if (S.inc_len[v] <= B200_MAXINC) shared_facet_mask(S, v, k, mask);
 		}
 		emit_copy_row(S, P, v, jrow, ipos, ppos, np, mask);
 		B200_ATOMIC_ADD(&ctl->n_zero, 1u);
@@ -514,7 +545,7 @@ B200_HD void he_eval_at(const DevState &S, u32 e, u32 i, u32 v, u32 off_i)
 	if (plus) {
 		if (cv == CLS_MINUS) {
 			inc = 1 + isect_count(S.inc_pool + iov, niv, S.inc_pool + iok, nik);
-		} else {
+		} else if (niv <= B200_MAXINC) {
 			u64 mask[B200_MAXINC / 64] = {0};
 			shared_facet_mask(S, v, k, mask);
 			const int nw = (int)((niv + 63) / 64) < B200_MAXINC / 64 ? (int)((niv + 63) / 64) : B200_MAXINC / 64;
@@ -528,7 +559,7 @@ B200_HD void he_eval_at(const DevState &S, u32 e, u32 i, u32 v, u32 off_i)
 }
 // sizes of what visited entry i (row v, class c, half-edges [e0, e1)) produces: out[0] new rows, out[1]
 // incidence entries, out[2] PLUS neighbours; also each half-edge's position among the PLUS ones.
-// Returns false when an on-plane vertex lies on more facets than the mask holds.
+// (Always true now: on-plane vertices with lists longer than the mask are counted without it.)
 B200_HD bool he_count_core(const DevState &S, u32 i, u32 v, u8 c, u32 e0, u32 e1, u32 out[3])
 {
 	u32 n_out = 0, inc_sz = 0, nplus = 0;
@@ -563,11 +594,13 @@ B200_HD bool he_count_core(const DevState &S, u32 i, u32 v, u8 c, u32 e0, u32 e1
 		}
 	if (is_visited_class(c)) {
 		if (c == CLS_ZERO) {
-			if (S.inc_len[v] > B200_MAXINC) ok = false;
 			n_out = 1;
 			inc_sz = 1;
-			const int nw = (int)((S.inc_len[v] + 63) / 64) < B200_MAXINC / 64 ? (int)((S.inc_len[v] + 63) / 64) : B200_MAXINC / 64;
-			for (int w = 0; w < nw; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
+			if (S.inc_len[v] > B200_MAXINC) inc_sz += zero_long_count(S, v);
+			else {
+				const int nw = (int)((S.inc_len[v] + 63) / 64);
+				for (int w = 0; w < nw; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
+			}
 		} else
 			n_out = nplus;
 	} else

@@ -30,16 +30,40 @@ RUNS = {
     "ex07": ["-e", "0.05", "-l", "primal_simplex"],
     "ex05_dual": ["-A", "dual", "-a", "dual"],
     "ex11_dual": ["-A", "dual", "-a", "dual"],
+    # BASELINE config 2: the flags ex/example09.m:9-24 prescribes (61 s of LP time with the HiGHS stand-in)
+    "ex09": ["-e", "1e-2", "-L", "primal_simplex", "-l", "primal_simplex"],
+}
+# BASELINE configs 3-4 (synthetic random VLPs, bensolve_b200/vlpgen.py), scaled to what the LP stand-in finishes in
+# minutes: every image vertex costs one LP through scipy, so q=3, m=2000, n=1000 (hours of LP time) is out of reach
+# here -- the cut path sees the same kind of trace, only shorter.  name -> (q, m, n, seed)
+SYNTHETIC = {
+    "syn_q3_m120_n60": (3, 120, 60, 1),
+    "syn_q5_m40_n20": (5, 40, 20, 1),
 }
 
 
 def main():
-    for name, flags in RUNS.items():
+    import time
+    only = set(sys.argv[1:])
+    todo = {**RUNS, **{k: [] for k in SYNTHETIC}}
+    for name, flags in todo.items():
+        if only and name not in only:
+            continue
         ex = name.split("_")[0]
         with tempfile.TemporaryDirectory() as tmp:
             trace = os.path.join(tmp, "trace.jsonl")
+            vlp = os.path.join(EX, ex + ".vlp")
+            if name in SYNTHETIC:
+                sys.path.insert(0, REPO)
+                from bensolve_b200 import vlpgen
+                q, m, n, seed = SYNTHETIC[name]
+                os.makedirs(os.path.join(tmp, "in"), exist_ok=True)
+                vlp = os.path.join(tmp, "in", name + ".vlp")
+                vlpgen.write_vlp(vlp, *vlpgen.random_vlp(q, m, n, seed=seed))
+            t0 = time.time()
             res = subprocess.run([sys.executable, os.path.join(REPO, "tools", "run_bensolve.py"), "--engine", "ref", "--record", trace,
-                                  "--workdir", tmp, os.path.join(EX, ex + ".vlp")] + flags, capture_output=True, text=True)
+                                  "--workdir", tmp, vlp] + flags, capture_output=True, text=True)
+            print(name, "reference run: %.1f s" % (time.time() - t0), [l for l in res.stdout.splitlines() if "LPs" in l][-1:], flush=True)
             if not os.path.exists(trace):
                 print(name, "FAILED", res.stdout[-500:], res.stderr[-500:])
                 continue

@@ -58,9 +58,22 @@ class Prob(C.Structure):   # mirrors struct glp_prob in tools/lpshim/glpk_shim.c
 FR, LO, UP, DB, FX = 1, 2, 3, 4, 5
 UNDEF, FEAS, INFEAS, NOFEAS, OPT, UNBND = 1, 2, 3, 4, 5, 6
 N_LP = [0]
+T_LP = [0.0]     # seconds inside the LP stand-in (the share of "CPU time" that is not the caller's or the engine's)
 
 
 def solve(pp, meth):
+    import numpy as np
+    from scipy.optimize import linprog
+    from scipy.sparse import csr_matrix
+    import time as _time
+    _t0 = _time.perf_counter()
+    try:
+        return _solve(pp, meth)
+    finally:
+        T_LP[0] += _time.perf_counter() - _t0
+
+
+def _solve(pp, meth):
     import numpy as np
     from scipy.optimize import linprog
     from scipy.sparse import csr_matrix
@@ -163,7 +176,7 @@ def main():
     host.bensolve_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     rc = host.bensolve_main(len(argv), arr)
     sys.stdout.flush()
-    print(f"[run_bensolve] engine={a.engine} rc={rc} LPs={N_LP[0]}", flush=True)
+    print(f"[run_bensolve] engine={a.engine} rc={rc} LPs={N_LP[0]} lp_seconds={T_LP[0]:.3f}", flush=True)
     os._exit(rc)       # the host frees GLPK state at exit; skip interpreter teardown ordering issues
 
 
