@@ -189,6 +189,25 @@ B200_HD u32 zero_long_count(const DevState &S, u32 v)
 	return n;
 }
 
+// The fast form of the same: visited entry i owns row i of a facet bitmap (DevState::zlong) that the PLUS neighbours'
+// lists are OR-ed into -- linear in the list lengths and parallel over the neighbours.  Available when the bitmap
+// covers every facet id and the entry has a row; the copy stage clears the row again.
+B200_HD bool zlong_usable(const DevState &S, u32 i) { return S.zlong && i < B200_VIS_MAX && S.cur->facet < S.zlong_words * 64u; }
+B200_HD void zlong_add_list(const DevState &S, u32 i, u32 k)
+{
+	u64 *row = S.zlong + (size_t)i * S.zlong_words;
+	const u32 *ik = S.inc_pool + S.inc_off[k];
+	for (u32 b = 0, nik = S.inc_len[k]; b < nik; b++) B200_ATOMIC_OR64(&row[ik[b] >> 6], (u64)1 << (ik[b] & 63));
+}
+B200_HD bool zlong_test(const DevState &S, u32 i, u32 x) { return (S.zlong[(size_t)i * S.zlong_words + (x >> 6)] >> (x & 63)) & 1; }
+B200_HD u32 zlong_count(const DevState &S, u32 i, u32 v)
+{
+	const u32 *iv = S.inc_pool + S.inc_off[v];
+	u32 n = 0;
+	for (u32 a = 0, niv = S.inc_len[v]; a < niv; a++) n += zlong_test(S, i, iv[a]) ? 1u : 0u;
+	return n;
+}
+
 // K3a: how many new rows / incidence entries / PLUS neighbours visited entry i produces
 // (sizes of what bslv_poly.c:573-588 and :597-665 append)
 B200_HD void count_outputs(const DevState &S, u32 i)
@@ -209,7 +228,9 @@ B200_HD void count_outputs(const DevState &S, u32 i)
 			const u32 nik = S.inc_len[k];
 			if (c == CLS_MINUS)
 				inc_sz += 1 + isect_count(iv, niv, ik, nik);
-			else if (!zlong) {
+			else if (zlong) {
+				if (zlong_usable(S, i)) zlong_add_list(S, i, k);
+			} else {
 				u32 a = 0, b = 0;
 				while (a < niv && a < B200_MAXINC && b < nik) {
 					u32 x = iv[a], y = ik[b];
@@ -222,7 +243,7 @@ B200_HD void count_outputs(const DevState &S, u32 i)
 		if (c == CLS_ZERO) {
 			n_out = 1;
 			inc_sz = 1;
-			if (zlong) inc_sz += zero_long_count(S, v);
+			if (zlong) inc_sz += zlong_usable(S, i) ? zlong_count(S, i, v) : zero_long_count(S, v);
 			else
 				for (int w = 0; w < B200_MAXINC / 64; w++) {
 					u64 m = mask[w];
@@ -434,7 +455,7 @@ B200_HD void shared_facet_mask(const DevState &S, u32 v, u32 k, u64 mask[B200_MA
 
 // the copy of an on-plane vertex v (bslv_poly.c:573-588): same coordinates, incidence = the masked
 // part of inc(v) plus the new facet; its PLUS neighbours were attached separately.
-B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, u32 ipos, u32 pslot, u32 nplus,
+B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 i, u32 v, u32 j, u32 ipos, u32 pslot, u32 nplus,
                            const u64 mask[B200_MAXINC / 64])
 {
 	const CutCtl *ctl = S.ctl;
@@ -455,9 +476,10 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 	const u32 niv = S.inc_len[v];
 	u32 w = ipos;
 	bool placed = false;                      // f keeps the list sorted (see emit_edge_inc)
-	const bool zlong = niv > B200_MAXINC;     // (then the mask was not built: each facet is tested directly)
+	const bool zlong = niv > B200_MAXINC;     // (then the mask was not built: the facet bitmap of entry i, or a direct test)
+	const bool zbits = zlong && zlong_usable(S, i);
 	for (u32 a = 0; a < niv; a++)
-		if (zlong ? zero_keeps_facet(S, v, iv[a]) : (bool)((mask[a >> 6] >> (a & 63)) & 1)) {
+		if (zbits ? zlong_test(S, i, iv[a]) : zlong ? zero_keeps_facet(S, v, iv[a]) : (bool)((mask[a >> 6] >> (a & 63)) & 1)) {
 			if (!placed && iv[a] > f) { S.inc_pool[w++] = f; placed = true; }
 			S.inc_pool[w++] = iv[a];
 			B200_ATOMIC_ADD(&S.facet_cnt[iv[a]], 1u);
@@ -466,6 +488,10 @@ B200_HD void emit_copy_row(const DevState &S, const CutParams &P, u32 v, u32 j, 
 	if (!placed) S.inc_pool[w++] = f;         // facet_cnt[f] is set once to n_new by the plan stage
 	S.inc_off[nw] = ipos;
 	S.inc_len[nw] = w - ipos;
+	if (zbits) {                              // the bitmap row reads zero again between cuts
+		u64 *row = S.zlong + (size_t)i * S.zlong_words;
+		for (u32 x = 0; x < S.zlong_words; x++) row[x] = 0;
+	}
 }
 
 // retire visited row v (bslv_poly.c:568, 679-688, 697-705): its facets lose one vertex
@@ -510,7 +536,7 @@ B200_HD void emit_outputs(const DevState &S, const CutParams &P, u32 i)
 			rewire(S, k, v, nw);
 			if (S.inc_len[v] <= B200_MAXINC) shared_facet_mask(S, v, k, mask);
 		}
-		emit_copy_row(S, P, v, jrow, ipos, ppos, np, mask);
+		emit_copy_row(S, P, i, v, jrow, ipos, ppos, np, mask);
 		B200_ATOMIC_ADD(&ctl->n_zero, 1u);
 	} else {
 		for (u32 q = 0; q < an; q++) {
@@ -545,7 +571,9 @@ B200_HD void he_eval_at(const DevState &S, u32 e, u32 i, u32 v, u32 off_i)
 	if (plus) {
 		if (cv == CLS_MINUS) {
 			inc = 1 + isect_count(S.inc_pool + iov, niv, S.inc_pool + iok, nik);
-		} else if (niv <= B200_MAXINC) {
+		} else if (niv > B200_MAXINC) {
+			if (zlong_usable(S, i)) zlong_add_list(S, i, k);
+		} else {
 			u64 mask[B200_MAXINC / 64] = {0};
 			shared_facet_mask(S, v, k, mask);
 			const int nw = (int)((niv + 63) / 64) < B200_MAXINC / 64 ? (int)((niv + 63) / 64) : B200_MAXINC / 64;
@@ -596,7 +624,7 @@ B200_HD bool he_count_core(const DevState &S, u32 i, u32 v, u8 c, u32 e0, u32 e1
 		if (c == CLS_ZERO) {
 			n_out = 1;
 			inc_sz = 1;
-			if (S.inc_len[v] > B200_MAXINC) inc_sz += zero_long_count(S, v);
+			if (S.inc_len[v] > B200_MAXINC) inc_sz += zlong_usable(S, i) ? zlong_count(S, i, v) : zero_long_count(S, v);
 			else {
 				const int nw = (int)((S.inc_len[v] + 63) / 64);
 				for (int w = 0; w < nw; w++) inc_sz += popc64(S.zmask[(size_t)i * (B200_MAXINC / 64) + w]);
@@ -646,7 +674,7 @@ B200_HD void he_finish_vertex(const DevState &S, const CutParams &P, u32 i)
 	const u8 c = S.cls[v];
 	if (!is_visited_class(c)) { S.dead_slots[i] = B200_NONE; return; }
 	if (c == CLS_ZERO) {
-		emit_copy_row(S, P, v, S.base3[3 * (size_t)i + 0], S.ctl->inc_used + S.base3[3 * (size_t)i + 1], S.base3[3 * (size_t)i + 2],
+		emit_copy_row(S, P, i, v, S.base3[3 * (size_t)i + 0], S.ctl->inc_used + S.base3[3 * (size_t)i + 1], S.base3[3 * (size_t)i + 2],
 		              S.cnt3[3 * (size_t)i + 2], &S.zmask[(size_t)i * (B200_MAXINC / 64)]);
 	}
 	retire_row(S, v, i);                      // n_minus / n_zero were counted by the plan stage

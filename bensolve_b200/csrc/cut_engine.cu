@@ -433,7 +433,7 @@ CutEngine::~CutEngine()
 #ifdef B200_EMULATE
 	                S_.stage,
 #endif
-	                S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.dead_facets, S_.ctl, S_.cur};
+	                S_.nplist, S_.dbg, S_.xchg_send, S_.xchg_recv, S_.he_off, S_.he_own, S_.he_inc, S_.he_k, S_.he_rank, S_.he_incpre, S_.he_flag, S_.zmask, S_.zlong, S_.dead_facets, S_.ctl, S_.cur};
 	for (void *p : ptrs) dfree(p);
 	dfree(gc_totals_);
 	drop_shadow();
@@ -585,6 +585,17 @@ void CutEngine::ensure_facets(u32 need)
 	regrow(S_.facet_local, cap, S_.cap_facets);
 	regrow(S_.dead_facets, cap, 0);
 	S_.cap_facets = cap;
+	// facet bitmaps for on-plane vertices on more than B200_MAXINC facets (only polytopes with that many facets can
+	// have them): one row per visited entry, as long as that stays within 256 MB -- beyond, the direct test is used
+	const u32 words = (cap + 63) / 64;
+	if (cap > B200_MAXINC && (u64)words * B200_VIS_MAX * 8 <= (256ull << 20)) {
+		regrow(S_.zlong, (size_t)words * B200_VIS_MAX, 0);
+		S_.zlong_words = words;
+	} else {
+		dfree(S_.zlong);
+		S_.zlong = nullptr;
+		S_.zlong_words = 0;
+	}
 }
 
 // ------------------------------------------------------------------ initial state
@@ -1932,7 +1943,9 @@ static void emu_wave_tailA(const DevState &S0, const WaveDev &W)
 			for (u32 x = 0; x < (S.inc_len[r] + 63) / 64 && x < B200_MAXINC / 64; x++) S.zmask[(size_t)i * (B200_MAXINC / 64) + x] = 0;
 		}
 		S.he_off[c->n_vis] = H;
-		if (H > S.cap_he) { c->status |= ST_NEED_BIG; continue; }
+		bool long_zero = false;             // an on-plane vertex on more facets than the mask holds: the cut runs alone
+		for (u32 i = 0; i < c->n_vis; i++) long_zero |= S.cls[S.vis[i]] == CLS_ZERO && S.inc_len[S.vis[i]] > B200_MAXINC;
+		if (H > S.cap_he || long_zero) { c->status |= ST_NEED_BIG; continue; }
 		for (u32 i = 0; i < c->n_vis; i++) he_owner_fill(S, i);
 		for (u32 e = 0; e < H; e++) he_eval(S, e);
 		u32 carry[3] = {0, 0, 0};

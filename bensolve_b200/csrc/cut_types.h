@@ -129,6 +129,9 @@ struct DevState {
 	u32 *he_k, *he_rank, *he_incpre; // [B200_HE_CAP] neighbour row; rank / incidence offset among the vertex's PLUS half-edges
 	u8 *he_flag;         // [B200_HE_CAP]
 	u64 *zmask;          // [B200_VIS_MAX * B200_MAXINC/64] shared-facet masks of ZERO vertices
+	u64 *zlong;          // [B200_VIS_MAX * zlong_words] (or null) facet bitmaps of ZERO vertices whose lists are longer than the mask:
+	                     // bit f of row i <=> facet f lies on a PLUS neighbour of visited entry i.  All zero between cuts.
+	u32 zlong_words;     // words per row = facets the bitmap covers / 64
 	u32 *dead_facets;    // [cap_facets]
 	unsigned char *stage; // [cap_stage] packed per-cut delta: header | coords AoS | parent | ideal | dead slots | dead facets.
 	                      // Device alias of MAPPED PINNED HOST memory: the kernels write the record straight to the host.

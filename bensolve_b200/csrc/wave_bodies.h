@@ -37,6 +37,8 @@ B200_HD DevState wave_view(const DevState &S, const WaveDev &W, u32 slot, u32 wp
 	V.he_incpre = W.he_incpre + (size_t)wpos * W.cap_he;
 	V.he_flag = W.he_flag + (size_t)wpos * W.cap_he;
 	V.zmask = W.zmask + (size_t)wpos * L * (B200_MAXINC / 64);
+	V.zlong = nullptr;                 // (cuts with such vertices leave the wave: ST_NEED_BIG in k_wave_tailA)
+	V.zlong_words = 0;
 	V.padj = W.padj + (size_t)wpos * W.cap_new;
 	V.new_padj_off = W.new_padj_off + (size_t)wpos * W.cap_new;
 	V.new_padj_len = W.new_padj_len + (size_t)wpos * W.cap_new;

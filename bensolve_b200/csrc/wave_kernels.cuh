@@ -473,7 +473,11 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	u32 H = 0;
 	for (u32 base = 0; base < n_vis; base += TAIL_THREADS) {
 		u32 i = base + threadIdx.x, v = 0, tot;
-		if (i < n_vis) v = S.adj_len[slist[i]];
+		if (i < n_vis) {
+			v = S.adj_len[slist[i]];
+			// an on-plane vertex on more facets than the shared-facet mask holds: this cut runs alone (classic path)
+			if (S.inc_len[slist[i]] > B200_MAXINC && S.cls[slist[i]] == CLS_ZERO) s_nstrict = B200_NONE;
+		}
 		u32 e = block_excl_scan(v, ws, tot);
 		if (i < n_vis) {
 			soff[i] = H + e;
@@ -486,7 +490,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 		if (rank == 0) S.he_off[n_vis] = H;
 	}
 	__syncthreads();
-	if (H > S.cap_he) {                          // too large for the scratch of a wave position: runs alone
+	if (H > S.cap_he || s_nstrict == B200_NONE) {   // too large for the scratch of a wave position: runs alone
 		if (ctid == 0) c->status |= ST_NEED_BIG;
 		return;
 	}
