@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <stdexcept>
 
 #ifndef B200_EMULATE
@@ -1356,6 +1357,7 @@ void CutEngine::reserve(u64 rows, u64 inc_entries, u64 adj_entries)
 	ensure_rows((u32)rows);
 	ensure_inc((u32)inc_entries);
 	ensure_adj((u32)adj_entries);
+	ensure_facets((u32)std::min<u64>(rows, 1u << 16));     // (a few MB: the facet-indexed arrays do not grow mid-run either)
 	ensure_shadow();        // the compaction's second set of arrays belongs to "no allocation after reserve" too
 }
 
@@ -1697,8 +1699,72 @@ template <class T> static void wave_fresh(T *&p, size_t n)
 	p = (T *)dalloc(n * sizeof(T));
 }
 
+// The wave scratch (~250 MB in ~45 arrays) of a killed polytope is parked and adopted by the next polytope of the process
+// that starts a device-resident batch on the same device: allocating it costs 45 cudaMalloc calls (12 ms on a good day,
+// 100+ ms on a bad one) at the start of the first batch, and freeing it as much at poly__kill.  What is adopted is the
+// state the previous owner left, which is what the same engine would find at its next batch: the footprint marks carry
+// epochs (monotone, the counter travels with the scratch), everything else is written before it is read -- except the
+// K4 column tags, which are facet ids and restart at 0 with a new polytope: those are cleared.  B200_WAVE_PARK=0: off.
+#ifdef B200_EMULATE
+static const int g_device = 0;
+#endif
+struct WavePark {
+	bool full = false;
+	int device = -1;
+	WaveDev wd;
+	WaveProgress *progress = nullptr;
+	u32 rows = 0, epoch = 1;
+	u64 rc_cap = 0;
+};
+static WavePark g_wave_park;
+static std::mutex g_wave_park_mu;
+static void dzero(void *p, size_t bytes)
+{
+#ifndef B200_EMULATE
+	if (p && bytes) CK(cudaMemset(p, 0, bytes));
+#else
+	if (p && bytes) memset(p, 0, bytes);
+#endif
+}
+bool CutEngine::wave_adopt()
+{
+	static const bool on = env_u32_early("B200_WAVE_PARK", 1) != 0;
+	if (!on) return false;
+	std::lock_guard<std::mutex> lk(g_wave_park_mu);
+	WavePark &k = g_wave_park;
+	if (!k.full || k.device != g_device || k.wd.cap_he != S_.cap_he || (getenv("B200_WAVE_TRACE") != nullptr) != (k.wd.trace != nullptr)) return false;
+	WD_ = k.wd;
+	wave_progress_ = k.progress;
+	wave_rows_ = k.rows;
+	wave_rc_cap_ = k.rc_cap;
+	wave_epoch_ = k.epoch;
+	k.full = false;
+	WD_.nranks = WD_.rank = WD_.shard_min_rows = 0;
+	WD_.xsend = WD_.xrecv = nullptr;
+	WD_.xflag = nullptr;
+	dzero(WD_.facet_epoch, (size_t)B200_WAVE_MAXW * WD_.cap_facets * 4);
+	dzero(WD_.fin_ctr, 16);
+	return true;
+}
+
 void CutEngine::wave_free()
 {
+	if (WD_.wc && env_u32_early("B200_WAVE_PARK", 1) != 0) {
+		std::lock_guard<std::mutex> lk(g_wave_park_mu);
+		WavePark &k = g_wave_park;
+		if (!k.full) {
+			k.full = true;
+			k.device = g_device;
+			k.wd = WD_;
+			k.progress = wave_progress_;
+			k.rows = wave_rows_;
+			k.rc_cap = wave_rc_cap_;
+			k.epoch = wave_epoch_;
+			wave_progress_ = nullptr;
+			memset(&WD_, 0, sizeof WD_);
+			return;
+		}
+	}
 	void *ptrs[] = {WD_.wc, WD_.ctl, WD_.cur, WD_.list, WD_.wflag, WD_.fin_ctr, WD_.trace, WD_.mark, WD_.rc, WD_.vis, WD_.cnt3, WD_.base3, WD_.dead_slots, WD_.he_off, WD_.he_own, WD_.he_inc,
 	                WD_.he_k, WD_.he_rank, WD_.he_incpre, WD_.he_flag, WD_.zmask, WD_.padj, WD_.new_padj_off, WD_.new_padj_len, WD_.new_parent, WD_.deg,
 	                WD_.adj_fill, WD_.adj_base, WD_.pair_a, WD_.pair_b, WD_.surv_a, WD_.surv_b, WD_.facet_epoch, WD_.facet_local, WD_.dead_facets, WD_.bits};
@@ -1716,6 +1782,7 @@ void CutEngine::wave_free()
 void CutEngine::wave_ensure_scratch(u32 n_facets, u32 pairs_per_pos, u64 bits_per_pos)
 {
 	const size_t L = B200_WAVE_LIST, NP = B200_WAVE_MAXW, NS = B200_WAVE_SLOTS;
+	if (!WD_.wc) wave_adopt();
 	if (!WD_.wc) {
 		WD_.wc = (WaveCtl *)dalloc(sizeof(WaveCtl));
 		WD_.ctl = (CutCtl *)dalloc(NS * sizeof(CutCtl));

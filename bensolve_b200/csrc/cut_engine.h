@@ -123,6 +123,7 @@ private:
 	// wave path
 	void wave_ensure_scratch(u32 n_facets, u32 pairs_per_pos, u64 bits_per_pos);
 	void wave_free();
+	bool wave_adopt();                      // take over the parked wave scratch of a killed polytope, if any
 	void wave_enqueue(int from_stage, const double *d_vals, const unsigned char *d_ideal);
 	void wave_sync_ctl(WaveCtl &wc);        // stream idle; host copies of the wave and the main control block
 	void wave_upload_ctl(const WaveCtl &wc);

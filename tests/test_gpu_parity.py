@@ -338,3 +338,30 @@ def test_gpu_wave_path_bench_shape_matches_reference(product_lib, checker, dim, 
     assert ra == rb
     capi.compare_states(sa, sb, exact_coords=True)
     assert st["rows_scanned"] < st["vertex_evals"]
+
+
+# ---------------------------------------------------------------- size-independent properties at scale (the bench's gate as a test)
+@pytest.mark.parametrize("dim,n", [(6, 2000), (5, 6000), (3, 60000)])
+def test_gpu_full_size_properties_and_path_equality(product_lib, dim, n):
+    """10^5..3*10^5 vertices, far beyond what the CPU reference replays in test time: every property a correct result
+    has (bensolve_b200/invariants.py), on the device-resident path and on the per-call path, and equality of the two
+    (SHA-256 of the canonical form, coordinates by bit pattern)."""
+    from bensolve_b200 import invariants as INV
+    tr = P.tangent_polytope(dim, n, 20261018)
+    digests, counts = [], []
+    for batch in (True, False):
+        e = capi.PolyEngine(product_lib, dim)
+        for i in range(dim):
+            e.add(tr.vals[i], 0)
+        assert e.init_approx() == 0
+        rcs = e.add_batch(tr.vals[dim:]) if batch else e.add_each(tr.vals[dim:])
+        assert sum(rcs) == 0                       # tangent halfspaces: none redundant
+        snap = INV.Snapshot(e)
+        counts.append(INV.check_polytope(snap))
+        digests.append(INV.digest(snap))
+        st = e.stats()
+        e.kill()
+        if batch:
+            assert st["waves"] > 0 and st["rows_scanned"] < st["vertex_evals"]
+    assert digests[0] == digests[1]
+    assert counts[0]["facets"] == n and counts[0]["vertices"] > 10 * n
