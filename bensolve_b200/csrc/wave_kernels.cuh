@@ -134,6 +134,55 @@ __device__ __forceinline__ void wave_la_plan_warp(WaveCtl &w, u32 nrows)
 	__syncwarp();
 }
 
+// wave_plan (wave_bodies.h) by the lanes of one warp: lane q owns wave position q, the bases are prefix sums
+__device__ __forceinline__ u32 wv_excl_scan(u32 v, u32 lane)
+{
+	u32 inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= (u32)o) inc += t;
+	}
+	return inc - v;
+}
+__device__ __forceinline__ void wave_plan_warp(const WaveCtl &w, const WaveCut *cut, u32 nrows, u32 inc_used, u32 n_live, u32 cap_rows, u32 cap_inc, u64 cap_bits, WavePlan &pl)
+{
+	const u32 lane = threadIdx.x & 31, n_wave = w.n_wave;
+	WaveCut c;
+	c.status = ST_REDUNDANT; c.n_new = c.inc_new = c.n_minus = c.n_zero = c.facet = 0; c.hs = B200_NONE;
+	if (lane < n_wave) c = cut[lane];
+	const bool red = (c.status & ST_REDUNDANT) != 0;
+	const u32 a_rows = red ? 0u : c.n_new, a_inc = red ? 0u : c.inc_new, a_gone = red ? 0u : c.n_minus + c.n_zero;
+	const u32 rows = nrows + wv_excl_scan(a_rows, lane), inc = inc_used + wv_excl_scan(a_inc, lane);
+	const u32 live = n_live + wv_excl_scan(a_rows, lane) - wv_excl_scan(a_gone, lane);
+	const u32 mpad = (c.n_new + 63) & ~63u, wl_ub = (c.facet + 64) / 64;
+	const u64 bits_ub = k4_words(wl_ub, mpad, wl_ub * 64);
+	u32 bad = 0;
+	if (lane < n_wave && !red) {
+		if (c.status & (ST_NEED_BIG | ST_ERR_DEGENERATE | ST_OVF_PADJ)) bad = WH_SERIAL;
+		else if ((u64)rows + c.n_new > cap_rows || (u64)rows + c.n_new > B200_WV_ROW_MASK || (u64)inc + c.inc_new > cap_inc || bits_ub > cap_bits) bad = WH_GROW;
+	}
+	const u32 bad_mask = __ballot_sync(0xffffffffu, bad != 0);
+	const u32 first_bad = bad_mask ? (u32)__ffs(bad_mask) - 1u : n_wave;
+	if (lane < n_wave) { pl.rows_base[lane] = rows; pl.inc_base[lane] = inc; pl.live_before[lane] = live; }
+	if (lane == 0) {
+		pl.n_commit = first_bad;
+		pl.halt = 0;
+		pl.halt_hs = B200_NONE;
+		pl.need_rows = pl.need_inc = 0;
+		pl.need_bits = 0;
+	}
+	__syncwarp();
+	if (lane == 0 && first_bad == 0 && bad_mask) {       // not even the first cut of the wave fits: the host has to act
+		pl.halt = bad;
+		pl.halt_hs = c.hs;
+		pl.need_rows = rows + c.n_new;
+		pl.need_inc = inc + c.inc_new;
+		pl.need_bits = bits_ub;
+	}
+	__syncwarp();
+}
+
 __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const double *vals, const unsigned char *ideal)
 {
 	__shared__ WaveCtl w;
@@ -192,14 +241,24 @@ __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const 
 
 // Look-ahead K1.  Thread t of a block owns rows 2t, 2t+1 of a 512-row group (one double2 load per coordinate, a
 // contiguous 512-byte run per warp); the coordinates stay in registers while the halfspaces of the pass, staged in
-// shared memory, are evaluated against them one after the other -- strict left-to-right sums of separately rounded
-// products, as bslv_poly.c:123-125 computes them.  Rows inside the guard band are appended to the slot's list.
+// shared memory, are evaluated against them one after the other.
+//
+// All but a few hundred of the 10^6 rows are far on the PLUS side of every halfspace, and saying so does not need the
+// reference's arithmetic: an FP32 dot product (6 FFMA on the FP32 pipe, twice as wide as the FP64 pipe and otherwise
+// idle here) with a rigorous error bound decides them.  |t32 - t| <= (d + 3) 2^-24 * sum|h_j||x_j| <= 7e-7 * ||h||_1 ||x||_inf
+// for d <= 8 (inputs rounded to float, products and sums fused); a row is skipped when
+//     t32 > hi + 2.5e-6 * (|thr| + ||h||_1 ||x||_inf)          (right-hand side rounded up in every step),
+// which implies t > hi + 1e-7 * (|thr| + ||h||_1 ||x||_inf), the guard-band test of wave_code().  Every other row is
+// evaluated exactly as before -- strict left-to-right sums of separately rounded FP64 products, as bslv_poly.c:123-125
+// computes them -- so the lists are the same sets with or without the filter.  The pass was FP64-pipe-bound
+// (30 FP64 instructions per row and halfspace); it is now bound by reading the coordinates.
 template <int D>
 __global__ void __launch_bounds__(K_THREADS) k_wave_classify(DevState S, WaveDev W)
 {
 	constexpr int DD = D > 0 ? D : B200_MAXD;
 	__shared__ double sh[B200_WAVE_SLOTS][DD];
 	__shared__ double s_alpha[B200_WAVE_SLOTS], s_h1[B200_WAVE_SLOTS], s_thr[B200_WAVE_SLOTS][6];
+	__shared__ float sh32[B200_WAVE_SLOTS][DD], s_a32[B200_WAVE_SLOTS][2], s_c32[B200_WAVE_SLOTS];
 	__shared__ u32 s_slot[B200_WAVE_SLOTS];
 	cudaGridDependencySynchronize();
 	WV_TRACE(1);
@@ -211,10 +270,15 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_classify(DevState S, WaveDev
 		const u32 slot = w->la[x];
 		const CutParams &P = W.cur[slot];
 		s_slot[x] = slot;
-		for (int j = 0; j < d; j++) sh[x][j] = P.h[j];
+		for (int j = 0; j < d; j++) { sh[x][j] = P.h[j]; sh32[x][j] = __double2float_rn(P.h[j]); }
 		s_alpha[x] = P.alpha;
 		s_h1[x] = P.h1;
 		s_thr[x][0] = P.hi[0]; s_thr[x][1] = P.hi[1]; s_thr[x][2] = P.mid[0]; s_thr[x][3] = P.mid[1]; s_thr[x][4] = P.lo[0]; s_thr[x][5] = P.lo[1];
+		// FP32 filter: skip when t32 > a32[id] + c32 * xinf32, every constant rounded up
+		const float slack = 2.5e-6f;
+		s_c32[x] = __fmul_ru(slack, __double2float_ru(P.h1));
+		s_a32[x][0] = __fadd_ru(__double2float_ru(P.hi[0]), __fmul_ru(slack, __double2float_ru(fabs(P.alpha))));
+		s_a32[x][1] = __double2float_ru(P.hi[1]);
 	}
 	__syncthreads();
 	const size_t cap = S.cap_rows;
@@ -231,10 +295,24 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_classify(DevState S, WaveDev
 			if (j < d) x[j] = *reinterpret_cast<const double2 *>(S.coord + j * cap + r);
 		if (!(lw & 3u)) continue;
 		double xi0 = 0, xi1 = 0;
+		float x32a[DD], x32b[DD];
 #pragma unroll
 		for (int j = 0; j < DD; j++)
-			if (j < d) { xi0 = fmax(xi0, fabs(x[j].x)); xi1 = fmax(xi1, fabs(x[j].y)); }
+			if (j < d) {
+				xi0 = fmax(xi0, fabs(x[j].x)); xi1 = fmax(xi1, fabs(x[j].y));
+				x32a[j] = __double2float_rn(x[j].x); x32b[j] = __double2float_rn(x[j].y);
+			}
+		const float xf0 = __double2float_ru(xi0), xf1 = __double2float_ru(xi1);
+		const u32 id0 = iw & 1u, id1 = (iw >> 1) & 1u;
 		for (u32 k = 0; k < n_la; k++) {
+			float f0 = sh32[k][0] * x32a[0], f1 = sh32[k][0] * x32b[0];
+#pragma unroll
+			for (int j = 1; j < DD; j++)
+				if (j < d) { f0 = fmaf(sh32[k][j], x32a[j], f0); f1 = fmaf(sh32[k][j], x32b[j], f1); }
+			// (a dead row of the pair counts as decided; NaN or inf compares false and takes the exact path)
+			const bool far0 = !(lw & 1u) || f0 > __fmaf_ru(s_c32[k], xf0, s_a32[k][id0]);
+			const bool far1 = !(lw & 2u) || f1 > __fmaf_ru(s_c32[k], xf1, s_a32[k][id1]);
+			if (far0 && far1) continue;
 			double t0 = __dmul_rn(sh[k][0], x[0].x), t1 = __dmul_rn(sh[k][0], x[0].y);
 #pragma unroll
 			for (int j = 1; j < DD; j++)
@@ -578,7 +656,7 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	if (threadIdx.x < w.n_wave) wave_gather_cut(W, w, threadIdx.x, cut[threadIdx.x]);
 	if (threadIdx.x == 32) n_tgt = 0;
 	__syncthreads();
-	if (threadIdx.x == 0) wave_plan(w, cut, S0.ctl->nrows, S0.ctl->inc_used, S0.ctl->n_live, S0.cap_rows, S0.cap_inc, W.cap_bits, pl);
+	if (threadIdx.x < 32) wave_plan_warp(w, cut, S0.ctl->nrows, S0.ctl->inc_used, S0.ctl->n_live, S0.cap_rows, S0.cap_inc, W.cap_bits, pl);
 	__syncthreads();
 	// look-ahead lists the new rows of this cut are classified into: every pending slot this wave does not carry out
 	if (threadIdx.x < w.n_pending) {
