@@ -94,7 +94,7 @@ class Stats(C.Structure):  # b200_stats, include/bensolve_b200.h
         "cuts", "redundant", "vertex_evals", "rows_scanned", "minus", "zero", "zero_plus_projected", "edge_vertices",
         "copies", "pair_tests", "new_adjacent_pairs", "algorithmic_bytes", "kernel_launches", "compactions",
         "live_vertices", "slots", "facets")] + [("classify_ms", C.c_double), ("cut_ms", C.c_double)] + [(n, C.c_uint64) for n in (
-        "waves", "wave_cuts", "lookahead_passes", "sharded_passes", "sharded_cuts")]
+        "waves", "wave_cuts", "lookahead_passes", "sharded_passes", "sharded_cuts", "sharded_pair_tests")]
 
 
 assert C.sizeof(PolyList) == 24 and C.sizeof(Polytope) == 112 and C.sizeof(PolyArgs) == 392

@@ -258,6 +258,12 @@ struct XArea {
 	unsigned long long *peer_recv[B200_X_MAXRANKS] = {nullptr};
 	u32 *peer_flag[B200_X_MAXRANKS] = {nullptr};
 	u32 seq = 0;
+	// the same set for the adjacent pairs of a sharded pair test
+	unsigned long long *ksend = nullptr, *krecv = nullptr;
+	u32 *kflag = nullptr;
+	unsigned long long *kpeer_recv[B200_X_MAXRANKS] = {nullptr};
+	u32 *kpeer_flag[B200_X_MAXRANKS] = {nullptr};
+	u32 seq_k = 0;
 };
 static XArea g_x;
 #ifndef B200_EMULATE
@@ -269,17 +275,23 @@ static void xarea_setup(cudaStream_t st)
 	if (G < 2 || G > B200_X_MAXRANKS || !g_comm.nccl_comm) return;
 	if (const char *e = getenv("B200_WAVE_SHARD")) if (atoi(e) == 0) return;
 	// every rank must take part in the all-gather below whatever happens locally: collect the local verdict first
-	struct Rec { cudaIpcMemHandle_t recv, flag; int ok; int pad[15]; } mine, *all = nullptr;
-	static_assert(sizeof(Rec) == 192, "exchange record");
+	struct Rec { cudaIpcMemHandle_t recv, flag, krecv, kflag; int ok; int pad[15]; } mine, *all = nullptr;
+	static_assert(sizeof(Rec) == 320, "exchange record");
 	memset(&mine, 0, sizeof mine);
-	const size_t recv_bytes = (size_t)G * 2 * B200_X_WORDS * 8;
+	const size_t recv_bytes = (size_t)G * 2 * B200_X_WORDS * 8, krecv_bytes = (size_t)G * 2 * B200_XK_WORDS * 8;
 	bool ok = cudaMalloc((void **)&g_x.recv, recv_bytes) == cudaSuccess && cudaMalloc((void **)&g_x.flag, (size_t)G * 128) == cudaSuccess &&
-	          cudaMalloc((void **)&g_x.send, (size_t)B200_X_WORDS * 8) == cudaSuccess;
+	          cudaMalloc((void **)&g_x.send, (size_t)B200_X_WORDS * 8) == cudaSuccess &&
+	          cudaMalloc((void **)&g_x.krecv, krecv_bytes) == cudaSuccess && cudaMalloc((void **)&g_x.kflag, (size_t)G * 128) == cudaSuccess &&
+	          cudaMalloc((void **)&g_x.ksend, (size_t)B200_XK_WORDS * 8) == cudaSuccess;
 	if (ok) {
 		cudaMemset(g_x.recv, 0, recv_bytes);
 		cudaMemset(g_x.flag, 0, (size_t)G * 128);
 		cudaMemset(g_x.send, 0, (size_t)B200_X_WORDS * 8);
-		ok = cudaIpcGetMemHandle(&mine.recv, g_x.recv) == cudaSuccess && cudaIpcGetMemHandle(&mine.flag, g_x.flag) == cudaSuccess;
+		cudaMemset(g_x.krecv, 0, krecv_bytes);
+		cudaMemset(g_x.kflag, 0, (size_t)G * 128);
+		cudaMemset(g_x.ksend, 0, (size_t)B200_XK_WORDS * 8);
+		ok = cudaIpcGetMemHandle(&mine.recv, g_x.recv) == cudaSuccess && cudaIpcGetMemHandle(&mine.flag, g_x.flag) == cudaSuccess &&
+		     cudaIpcGetMemHandle(&mine.krecv, g_x.krecv) == cudaSuccess && cudaIpcGetMemHandle(&mine.kflag, g_x.kflag) == cudaSuccess;
 	}
 	(void)cudaGetLastError();
 	mine.ok = ok ? 1 : 0;
@@ -296,11 +308,15 @@ static void xarea_setup(cudaStream_t st)
 	if (ok) {
 		for (int g = 0; g < G && ok; g++) {
 			if (g == me) continue;
-			void *a = nullptr, *b = nullptr;
+			void *a = nullptr, *b = nullptr, *c = nullptr, *e = nullptr;
 			ok = cudaIpcOpenMemHandle(&a, all[g].recv, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
-			     cudaIpcOpenMemHandle(&b, all[g].flag, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+			     cudaIpcOpenMemHandle(&b, all[g].flag, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+			     cudaIpcOpenMemHandle(&c, all[g].krecv, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+			     cudaIpcOpenMemHandle(&e, all[g].kflag, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
 			g_x.peer_recv[g] = (unsigned long long *)a;
 			g_x.peer_flag[g] = (u32 *)b;
+			g_x.kpeer_recv[g] = (unsigned long long *)c;
+			g_x.kpeer_flag[g] = (u32 *)e;
 		}
 		(void)cudaGetLastError();
 	}
@@ -325,6 +341,8 @@ static void xarea_setup()
 	if (G < 2 || G > B200_X_MAXRANKS || !g_comm.callback) return;
 	g_x.send = (unsigned long long *)calloc(B200_X_WORDS, 8);
 	g_x.recv = (unsigned long long *)calloc((size_t)G * B200_X_WORDS, 8);
+	g_x.ksend = (unsigned long long *)calloc(B200_XK_WORDS, 8);
+	g_x.krecv = (unsigned long long *)calloc((size_t)G * B200_XK_WORDS, 8);
 	g_x.ok = true;
 }
 #endif
@@ -1740,8 +1758,8 @@ bool CutEngine::wave_adopt()
 	wave_epoch_ = k.epoch;
 	k.full = false;
 	WD_.nranks = WD_.rank = WD_.shard_min_rows = 0;
-	WD_.xsend = WD_.xrecv = nullptr;
-	WD_.xflag = nullptr;
+	WD_.xsend = WD_.xrecv = WD_.xksend = WD_.xkrecv = nullptr;
+	WD_.xflag = WD_.xkflag = nullptr;
 	dzero(WD_.facet_epoch, (size_t)B200_WAVE_MAXW * WD_.cap_facets * 4);
 	dzero(WD_.fin_ctr, 16);
 	return true;
@@ -1925,6 +1943,11 @@ void CutEngine::wave_enqueue(int from_stage, const double *d_vals, const unsigne
 		launch_dependent(k_wave_k4_filter, gk4, K_THREADS, STREAM, S_, WD_);
 		launch_dependent(k_wave_k4_contain, num_sms_ * 8, K_THREADS, STREAM, S_, WD_);
 		stats_.kernel_launches += 2;
+		if (WD_.xksend) {                   // several GPUs: the adjacent pairs each rank found, to every rank
+			launch_dependent(k_wave_k4_xpush, (int)WD_.nranks, K_THREADS, STREAM, S_, WD_);
+			launch_dependent(k_wave_k4_xmerge, (int)WD_.nranks * 8, K_THREADS, STREAM, S_, WD_);
+			stats_.kernel_launches += 2;
+		}
 	}
 	launch_clusters(k_wave_tail2<WAVE_NC>, nclu, WAVE_NC, STREAM, S_, WD_);
 	stats_.kernel_launches++;
@@ -2081,8 +2104,10 @@ static void emu_wave_tailB(const DevState &S0, const WaveDev &W)
 }
 static void emu_wave_k4(const DevState &S0, const WaveDev &W, bool reset)
 {
-	const WaveCtl *w = W.wc;
+	WaveCtl *w = W.wc;
 	if (w->halt) return;
+	const bool shk = w->shard_k4 != 0;
+	if (shk && reset) wave_k4_record_reset(W, w->xseq_k);
 	for (u32 q = 0; q < w->n_commit; q++) {
 		const DevState S = wave_view(S0, W, w->wave[q], q);
 		CutCtl *c = S.ctl;
@@ -2090,12 +2115,36 @@ static void emu_wave_k4(const DevState &S0, const WaveDev &W, bool reset)
 		if (reset) { c->n_surv = c->n_pairs = 0; for (u32 j = 0; j < c->n_new; j++) S.deg[j] = 0; }
 		const u32 M = c->n_new;
 		for (u32 a = 0; a < M; a++)
-			for (u32 b = a + 1; b < M; b++) k4_filter_pair(S, a, b);
-		if (c->n_surv > S.cap_pairs) continue;
+			for (u32 b = a + 1; b < M; b++)
+				if (!shk || (a + b) % W.nranks == W.rank) k4_filter_pair(S, a, b);      // (sharded: this rank's share of the pair space)
+		if (c->n_surv > S.cap_pairs) {
+			if (shk) { W.xksend[2] |= 1u; if (W.xksend[3] < c->n_surv) W.xksend[3] = c->n_surv; }
+			continue;
+		}
 		for (u32 sv = 0; sv < c->n_surv; sv++) {
 			const u32 a = S.surv_a[sv], b = S.surv_b[sv];
-			if (k4_adjacent_by_columns(S, a, b, c->n_new, c->wl, c->mpad)) { wave_flag_adjacent(S, sv, a, b); c->n_pairs++; }
+			if (!k4_adjacent_by_columns(S, a, b, c->n_new, c->wl, c->mpad)) continue;
+			if (shk) wave_k4_send_pair(W, q, a, b);
+			else { wave_flag_adjacent(S, sv, a, b); c->n_pairs++; }
 		}
+	}
+	if (!shk) return;
+	// exchange of the adjacent pairs (all-gather through the host callback), then every pair under its cut
+	g_comm.callback(W.xksend, W.xkrecv, (size_t)B200_XK_WORDS * 8);
+	u32 need = 0;
+	bool over_rec = false, over_surv = false;
+	for (u32 g = 0; g < W.nranks; g++) {
+		const unsigned long long *rec = W.xkrecv + (size_t)g * B200_XK_WORDS;
+		if (rec[1] != w->xseq_k) fail("multi-rank test double: pair record of another exchange");
+		if ((u32)rec[0] > B200_XK_CAP) over_rec = true;
+		if (rec[2] & 1u) { over_surv = true; need = std::max<u32>(need, (u32)rec[3]); }
+	}
+	if (over_surv) { w->halt |= WH_GROW_PAIRS; w->halt_pairs = std::max(w->halt_pairs, need); }
+	else if (over_rec) w->halt |= WH_XOVER_K4;
+	if (w->halt) { wave_publish(W, *w, S0.ctl->nrows, S0.ctl->n_live); return; }
+	for (u32 g = 0; g < W.nranks; g++) {
+		const unsigned long long *rec = W.xkrecv + (size_t)g * B200_XK_WORDS;
+		for (u32 x = 0; x < (u32)rec[0]; x++) wave_k4_merge_pair(S0, W, *w, rec[4 + x]);
 	}
 }
 static void emu_wave_tail2(const DevState &S0, const WaveDev &W)
@@ -2117,7 +2166,8 @@ static void emu_wave_tail2(const DevState &S0, const WaveDev &W)
 		for (u32 j = 0; j < c->n_new; j++) { S.adj_base[j] = carry; carry += S.new_padj_len[j] + S.deg[j]; }
 		if (carry != c->adj_new) fail("wave adjacency plan disagrees with the scan");
 		for (u32 j = 0; j < c->n_new; j++) adj_place(S, j);
-		for (u32 sv = 0; sv < c->n_surv; sv++) adj_pair_fill_surv(S, sv);
+		if (w.shard_k4) for (u32 pp = 0; pp < c->n_pairs; pp++) adj_pair_fill(S, pp);
+		else for (u32 sv = 0; sv < c->n_surv; sv++) adj_pair_fill_surv(S, sv);
 		for (u32 j = 0; j < c->n_new; j++) adj_sort(S, j);
 	}
 }
@@ -2140,6 +2190,7 @@ static void emu_wave_begin(const DevState &S, const WaveDev &W, const double *va
 		wave_la_plan(w, S.ctl->nrows);
 		wave_shard_plan(w, W, S.ctl->nrows);
 		if (w.shard) { W.xsend[0] = 0; W.xsend[1] = w.xseq; }
+		if (w.shard_k4) { wave_k4_record_reset(W, ++w.xseq_k); w.st_sharded_k4++; }
 		for (u32 k = 0; k < w.n_la; k++) wave_la_init(S, W, w, k, vals, ideal);
 	}
 	wave_publish(W, w, S.ctl->nrows, S.ctl->n_live);
@@ -2214,12 +2265,18 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 #endif
 			if (g_x.ok) {
 				WD_.xsend = g_x.send; WD_.xrecv = g_x.recv; WD_.xflag = g_x.flag;
-				for (int g = 0; g < B200_X_MAXRANKS; g++) { WD_.xpeer_recv[g] = g_x.peer_recv[g]; WD_.xpeer_flag[g] = g_x.peer_flag[g]; }
+				WD_.xksend = g_x.ksend; WD_.xkrecv = g_x.krecv; WD_.xkflag = g_x.kflag;
+				for (int g = 0; g < B200_X_MAXRANKS; g++) {
+					WD_.xpeer_recv[g] = g_x.peer_recv[g]; WD_.xpeer_flag[g] = g_x.peer_flag[g];
+					WD_.xkpeer_recv[g] = g_x.kpeer_recv[g]; WD_.xkpeer_flag[g] = g_x.kpeer_flag[g];
+				}
 			}
 		}
 		WaveCtl wc;
 		memset(&wc, 0, sizeof wc);
 		wc.xseq = g_x.seq;
+		wc.xseq_k = g_x.seq_k;
+		wc.shard_k4 = (WD_.xksend && env_u32("B200_K4_SHARD", 1) != 0) ? 1u : 0u;
 		wc.n_total = (u32)n;
 		wc.facet0 = facet0;
 		wc.batch_first = batch_first;
@@ -2282,6 +2339,10 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 			} else if (wc.halt & WH_GROW_PAIRS) {
 				wave_ensure_scratch(WD_.cap_facets, wc.halt_pairs + wc.halt_pairs / 2, WD_.cap_bits);
 				stage = 1;
+				if (wc.shard_k4) wc.xseq_k++;           // the redone pair test is a new exchange
+			} else if (wc.halt & WH_XOVER_K4) {         // (on every rank alike) this batch goes on with the pair test replicated
+				wc.shard_k4 = 0;
+				stage = 1;
 			} else if (wc.halt & WH_COMPACT) {
 				compact();
 				wc.reclassify = 1;
@@ -2298,6 +2359,7 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 		}
 		wave_epoch_ = wc.epoch + 1;
 		g_x.seq = wc.xseq;
+		g_x.seq_k = wc.xseq_k;
 		// results and statistics of the wave run
 		std::vector<int> rc_dev(n);
 		d2h(rc_dev.data(), WD_.rc, n * sizeof(int));
@@ -2307,7 +2369,7 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 		stats_.cuts += wc.st_cuts; stats_.redundant += wc.st_redundant; stats_.vertex_evals += wc.st_evals; stats_.rows_scanned += wc.st_rows_scanned;
 		stats_.minus += wc.st_minus; stats_.zero += wc.st_zero; stats_.edge_vertices += wc.st_edge; stats_.copies += wc.st_copies;
 		stats_.pair_tests += wc.st_pair_tests; stats_.new_adjacent_pairs += wc.st_pairs; stats_.algorithmic_bytes += wc.st_bytes;
-		stats_.waves += wc.st_waves; stats_.wave_cuts += wc.st_cuts + wc.st_redundant; stats_.la_passes += wc.st_la_passes; stats_.wave_deferred += wc.st_deferred; stats_.sharded_passes += wc.st_sharded;
+		stats_.waves += wc.st_waves; stats_.wave_cuts += wc.st_cuts + wc.st_redundant; stats_.la_passes += wc.st_la_passes; stats_.wave_deferred += wc.st_deferred; stats_.sharded_passes += wc.st_sharded; stats_.sharded_pair_tests += wc.st_sharded_k4;
 		small_dirty_ = true;
 		expect_vis_ = expect_m_ = 0;
 		if (WD_.trace) {            // start of each kernel of the last iterations, relative to the iteration's first kernel

@@ -45,7 +45,7 @@ struct EngineStats {
 	double host_us[12] = {0};     // [8] device growth (ensure_*), [9] growth events
 	u64 redo_loops = 0;
 	u64 waves = 0, wave_cuts = 0, la_passes = 0, wave_deferred = 0, wave_serial = 0, wave_halts = 0;   // wave path
-	u64 sharded_passes = 0, sharded_cuts = 0;      // several ranks: look-ahead passes / per-call cuts split across them
+	u64 sharded_passes = 0, sharded_cuts = 0, sharded_pair_tests = 0;      // several ranks: look-ahead passes / per-call cuts split across them
 };
 
 class CutEngine {

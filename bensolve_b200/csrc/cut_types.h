@@ -180,7 +180,8 @@ enum : u32 {                     // WaveCtl::halt
 	WH_COMPACT = 16u,            // dead rows outnumber live ones: compact, rebuild the look-ahead lists
 	WH_GROW_PAIRS = 32u,         // pair buffers of a wave position too small: grow, then redo the pair test and the adjacency build
 	WH_XOVER = 64u,              // a rank's exchange record overflowed: the lists of this pass are rebuilt unsharded
-	WH_XFAIL = 128u              // a peer's record did not arrive (the host reports the failure)
+	WH_XFAIL = 128u,             // a peer's record did not arrive (the host reports the failure)
+	WH_XOVER_K4 = 256u           // a rank's record of adjacent pairs overflowed: the pair test of this wave is redone unsharded
 };
 
 // Multi-GPU look-ahead (state replicated, one process per GPU): a pass over >= shard_min_rows rows is split by row
@@ -190,6 +191,11 @@ enum : u32 {                     // WaveCtl::halt
 // involvement and no collective launch: every rank's scheduler takes the same decisions from the same state.
 #define B200_X_CAP 16382u        // entries (u64: slot << 32 | list entry) per record
 #define B200_X_WORDS (B200_X_CAP + 2u)   // u64 words per record: [0] = entry count (may exceed the capacity = overflow), [1] = pass number
+// The pair test of a wave is split the same way (tile pairs of all cuts dealt round-robin over ranks x blocks): each rank
+// tests its share, collects the ADJACENT pairs it finds (wave position << 56 | a << 28 | b) and exchanges them like the
+// look-ahead records; the merge kernel files every pair under its cut, so the adjacency build sees the complete list.
+#define B200_XK_CAP 65532u       // adjacent pairs per record
+#define B200_XK_WORDS (B200_XK_CAP + 4u)  // [0] count, [1] exchange number, [2] bit0: a local survivor list overflowed, [3] survivors it needs
 #define B200_X_MAXRANKS 8
 #define B200_WV_GROUP 512u         // rows per group of the look-ahead kernel (2 per thread of a 256-thread block): the unit of the rank split
 #define ST_WAVE_DEFER 2048u      // (CutCtl::status, wave path) this cut goes back to the pending list untouched
@@ -224,9 +230,11 @@ struct WaveCtl {
 	u64 halt_bits;
 	u32 xseq;                    // sequence number of the latest sharded pass (process-wide, identical on every rank)
 	u32 noshard_once;            // the next pass runs unsharded (an exchange record overflowed)
+	u32 shard_k4;                // the pair test of every wave is split across the ranks (host-set, the same on every rank)
+	u32 xseq_k;                  // number of the latest pair-test exchange (process-wide, identical on every rank)
 	// ---- statistics (same meaning as EngineStats)
 	u64 st_cuts, st_redundant, st_evals, st_rows_scanned, st_minus, st_zero, st_edge, st_copies, st_pair_tests, st_pairs, st_bytes;
-	u64 st_waves, st_la_passes, st_deferred, st_sharded;
+	u64 st_waves, st_la_passes, st_deferred, st_sharded, st_sharded_k4;
 	u64 t_first, t_last;         // %globaltimer of the first and the latest commit (diagnostics)
 };
 // The kernels stage WaveCtl in shared memory, let one thread work on the copy and write it back with all threads
@@ -268,4 +276,8 @@ struct WaveDev {                 // device pointers of the wave path (kernel arg
 	u32 *xflag;                                // [nranks * 32] pass number published by each peer (one 128-byte line each)
 	unsigned long long *xpeer_recv[B200_X_MAXRANKS];   // peer-mapped xrecv of every other rank
 	u32 *xpeer_flag[B200_X_MAXRANKS];          // peer-mapped xflag of every other rank
+	unsigned long long *xksend, *xkrecv;       // [B200_XK_WORDS], [nranks][2][B200_XK_WORDS]: the same for the adjacent pairs of a wave
+	u32 *xkflag;
+	unsigned long long *xkpeer_recv[B200_X_MAXRANKS];
+	u32 *xkpeer_flag[B200_X_MAXRANKS];
 };

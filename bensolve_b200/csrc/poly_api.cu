@@ -855,6 +855,7 @@ extern "C" int b200_poly_get_stats(poly_args *a, b200_stats *out)
 	out->classify_ms = s.classify_ms; out->cut_ms = s.cut_ms;
 	out->waves = s.waves; out->wave_cuts = s.wave_cuts; out->lookahead_passes = s.la_passes; out->sharded_passes = s.sharded_passes;
 	out->sharded_cuts = s.sharded_cuts;
+	out->sharded_pair_tests = s.sharded_pair_tests;
 	return 0;
 }
 
@@ -896,7 +897,7 @@ static void rebuild_mirror(poly_args *a, Handle *h, size_t first_slot)
 		}
 	};
 	unsigned nt = std::thread::hardware_concurrency();
-	nt = nt ? std::min(nt, 16u) : 1u;
+	nt = nt ? std::min(nt, (unsigned)std::max(1, atoi(getenv("B200_MIRROR_THREADS") ? getenv("B200_MIRROR_THREADS") : "16"))) : 1u;
 	nt = std::max(1u, nt / (unsigned)std::max(1, b200_comm_size()));      // one process per GPU: the ranks share the host's cores
 	if (n < 65536) nt = 1;
 	std::vector<u32> cutp(nt + 1, n);

@@ -321,6 +321,26 @@ B200_HD void wave_flag_adjacent(const DevState &S, u32 s, u32 a, u32 b)
 	B200_ATOMIC_ADD(&S.deg[a], 1u);
 	B200_ATOMIC_ADD(&S.deg[b], 1u);
 }
+// sharded pair test: an adjacent pair found by this rank goes to its exchange record ...
+B200_HD void wave_k4_send_pair(const WaveDev &W, u32 q, u32 a, u32 b)
+{
+	const u32 pos = B200_ATOMIC_ADD((u32 *)W.xksend, 1u);
+	if (pos < B200_XK_CAP) W.xksend[4 + pos] = ((unsigned long long)q << 56) | ((unsigned long long)a << 28) | b;
+}
+// ... and every pair of every record is filed under its cut (pair list of the wave position, degrees, count)
+B200_HD void wave_k4_merge_pair(const DevState &S0, const WaveDev &W, const WaveCtl &w, unsigned long long e)
+{
+	const u32 q = (u32)(e >> 56), a = (u32)(e >> 28) & 0x0FFFFFFFu, b = (u32)e & 0x0FFFFFFFu;
+	const DevState S = wave_view(S0, W, w.wave[q], q);
+	const u32 pos = B200_ATOMIC_ADD(&S.ctl->n_pairs, 1u);
+	if (pos < S.cap_pairs) { S.pair_a[pos] = a; S.pair_b[pos] = b; }
+	B200_ATOMIC_ADD(&S.deg[a], 1u);
+	B200_ATOMIC_ADD(&S.deg[b], 1u);
+}
+B200_HD void wave_k4_record_reset(const WaveDev &W, u32 seq)
+{	// header: count, exchange number, overflow flag, survivors needed
+	W.xksend[0] = 0; W.xksend[1] = seq; W.xksend[2] = 0; W.xksend[3] = 0;
+}
 B200_HD void adj_pair_fill_surv(const DevState &S, u32 s)
 {
 	u32 a = S.surv_a[s];
@@ -393,6 +413,7 @@ B200_HD u32 wave_adj_plan(const WaveCut *cut, u32 n_commit, u32 adj_used, u32 ca
 		adj_new[q] = 0;
 		if (cut[q].status & ST_REDUNDANT) continue;
 		if (cut[q].n_surv > cap_pairs) over = over > cut[q].n_surv ? over : cut[q].n_surv;
+		if (cut[q].n_pairs > cap_pairs) over = over > cut[q].n_pairs ? over : cut[q].n_pairs;   // (sharded pair test: the merged pair list)
 		adj_new[q] = cut[q].padj_new + 2 * cut[q].n_pairs;
 		base += adj_new[q];
 	}

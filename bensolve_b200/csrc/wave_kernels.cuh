@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const 
 		if (threadIdx.x == 0) {
 			wave_shard_plan(w, W, mctl.nrows);
 			if (w.shard) { W.xsend[0] = 0; W.xsend[1] = w.xseq; }
+			if (w.shard_k4 && !w.halt) { wave_k4_record_reset(W, ++w.xseq_k); w.st_sharded_k4++; }    // one pair-test exchange per iteration, empty or not
 		}
 	}
 	__syncthreads();
@@ -751,11 +752,14 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_k4_filter(DevState S0, WaveD
 		s_mpad[threadIdx.x] = c->mpad;
 	}
 	__syncthreads();
+	const bool shk = w->shard_k4 != 0;
+	const u32 vg = shk ? gridDim.x * W.nranks : gridDim.x, vb = shk ? blockIdx.x * W.nranks + W.rank : blockIdx.x;
 	u32 base = 0;
 	for (u32 q = 0; q < s_n; q++) {
 		if (!s_M[q]) continue;
 		const DevState S = wave_view(S0, W, s_slot[q], q);
-		k4_filter_body(S, k4_threshold(S, true), s_M[q], s_wl[q], s_mpad[q], (blockIdx.x + gridDim.x - base % gridDim.x) % gridDim.x, gridDim.x);
+		// tile pairs of all cuts are dealt round-robin over the blocks -- of every rank when the pair test is sharded
+		k4_filter_body(S, k4_threshold(S, true), s_M[q], s_wl[q], s_mpad[q], (vb + vg - base % vg) % vg, vg);
 		base += k4_tile_pairs(s_M[q]);
 	}
 }
@@ -776,6 +780,14 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_k4_contain(DevState S0, Wave
 		s_mpad[threadIdx.x] = c->mpad;
 	}
 	__syncthreads();
+	const bool shk = w->shard_k4 != 0;
+	if (shk && blockIdx.x == 0 && threadIdx.x < s_n) {       // a local survivor list overflowed: every rank must learn it
+		const CutCtl *c = W.ctl + s_slot[threadIdx.x];
+		if (!(c->status & ST_SKIP_B) && c->n_surv > W.cap_pairs) {
+			atomicOr((u32 *)(W.xksend + 2), 1u);
+			atomicMax((u32 *)(W.xksend + 3), c->n_surv);
+		}
+	}
 	if (threadIdx.x == 0) {
 		u32 t = 0;
 		for (u32 q = 0; q < s_n; q++) { s_off[q] = t; t += s_ns[q]; }
@@ -789,23 +801,86 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_k4_contain(DevState S0, Wave
 		u32 q = 0;
 		while (s_off[q + 1] <= g) q++;
 		if (q != cur_q) {                            // (warp-uniform) pair count of the cut this warp is leaving
-			if (cur_q != B200_NONE && found && lane == 0) atomicAdd(&W.ctl[s_slot[cur_q]].n_pairs, found);
+			if (!shk && cur_q != B200_NONE && found && lane == 0) atomicAdd(&W.ctl[s_slot[cur_q]].n_pairs, found);
 			cur_q = q;
 			found = 0;
 		}
 		const DevState S = wave_view(S0, W, s_slot[q], q);
 		const u32 sv = g - s_off[q], a = S.surv_a[sv], b = S.surv_b[sv];
 		if (k4_columns_verdict(S, a, b, lane, s_M[q], s_wl[q], s_mpad[q])) {
-			if (lane == 0) wave_flag_adjacent(S, sv, a, b);
+			if (lane == 0) {
+				if (shk) wave_k4_send_pair(W, q, a, b);   // counted and filed when the records of all ranks are merged
+				else wave_flag_adjacent(S, sv, a, b);
+			}
 			found++;
 		}
 	}
-	if (cur_q != B200_NONE && found && lane == 0) atomicAdd(&W.ctl[s_slot[cur_q]].n_pairs, found);
+	if (!shk && cur_q != B200_NONE && found && lane == 0) atomicAdd(&W.ctl[s_slot[cur_q]].n_pairs, found);
+}
+// exchange of the adjacent pairs (sharded pair test): same protocol as k_wave_xpush / k_wave_xmerge
+__global__ void __launch_bounds__(K_THREADS) k_wave_k4_xpush(DevState S, WaveDev W)
+{
+	cudaGridDependencySynchronize();
+	const WaveCtl *w = W.wc;
+	if (w->halt || !w->shard_k4) return;
+	const u32 p = blockIdx.x;
+	if (p >= W.nranks || p == W.rank) return;
+	const u32 seq = w->xseq_k;
+	const unsigned long long cnt = W.xksend[0] & 0xFFFFFFFFull;
+	const u32 n = (u32)(cnt < B200_XK_CAP ? cnt : B200_XK_CAP) + 4;
+	unsigned long long *dst = W.xkpeer_recv[p] + ((size_t)W.rank * 2 + (seq & 1u)) * B200_XK_WORDS;
+	for (u32 x = threadIdx.x; x < n; x += K_THREADS) dst[x] = W.xksend[x];
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) wv_st_release_sys(W.xkpeer_flag[p] + W.rank * 32, seq);
+}
+__global__ void __launch_bounds__(K_THREADS) k_wave_k4_xmerge(DevState S, WaveDev W)
+{
+	__shared__ u32 s_ok;
+	__shared__ WaveCtl sw;
+	cudaGridDependencySynchronize();
+	WaveCtl *w = W.wc;
+	if (w->halt || !w->shard_k4) return;
+	const u32 src = blockIdx.x % W.nranks, part = blockIdx.x / W.nranks, nparts = gridDim.x / W.nranks;
+	if (part >= nparts) return;
+	const u32 seq = w->xseq_k;
+	const unsigned long long *rec = W.xksend;
+	if (src != W.rank) {
+		if (threadIdx.x == 0) {
+			const u64 t0 = b200_globaltimer();
+			u32 ok = 1;
+			while ((int)(wv_ld_acquire_sys(W.xkflag + src * 32) - seq) < 0) {
+				if (b200_globaltimer() - t0 > 4000000000ull) { ok = 0; break; }
+				__nanosleep(100);
+			}
+			s_ok = ok;
+		}
+		__syncthreads();
+		if (!s_ok) {
+			if (threadIdx.x == 0) { const u32 h = atomicOr(&w->halt, (u32)WH_XFAIL) | WH_XFAIL; W.progress->halt = h; }
+			return;
+		}
+		rec = W.xkrecv + ((size_t)src * 2 + (seq & 1u)) * B200_XK_WORDS;
+	}
+	const u32 cnt = (u32)__ldcg(rec), flags = (u32)__ldcg(rec + 2), need = (u32)__ldcg(rec + 3);
+	if (cnt > B200_XK_CAP || (flags & 1u)) {     // every rank reads the same headers and halts the same way
+		if (part == 0 && threadIdx.x == 0) {
+			const u32 why = (flags & 1u) ? (u32)WH_GROW_PAIRS : (u32)WH_XOVER_K4;
+			if (flags & 1u) atomicMax(&w->halt_pairs, need);
+			const u32 h = atomicOr(&w->halt, why) | why;
+			W.progress->halt = h;
+		}
+		return;
+	}
+	wv_copy_words(&sw, w, sizeof sw);            // (wave positions -> slots)
+	__syncthreads();
+	for (u32 x = part * K_THREADS + threadIdx.x; x < cnt; x += nparts * K_THREADS) wave_k4_merge_pair(S, W, sw, __ldcg(rec + 4 + x));
 }
 // before the pair test is redone with larger buffers
 __global__ void __launch_bounds__(K_THREADS) k_wave_k4_reset(DevState S0, WaveDev W)
 {
 	const WaveCtl *w = W.wc;
+	if (w->shard_k4 && blockIdx.x == 0 && threadIdx.x == 0) wave_k4_record_reset(W, w->xseq_k);   // (the host advanced the exchange number)
 	for (u32 q = 0; q < w->n_commit; q++) {
 		const DevState S = wave_view(S0, W, w->wave[q], q);
 		if (S.ctl->status & ST_SKIP_B) continue;
@@ -865,7 +940,8 @@ template <int NC> __global__ void __launch_bounds__(TAIL_THREADS, 1) k_wave_tail
 	TAIL_SYNC();
 	WV_TP(34);
 	TAIL_SPREAD(j, n) adj_place(S, j);
-	TAIL_SPREAD(sv, cut[q].n_surv) adj_pair_fill_surv(S, sv);
+	if (w.shard_k4) { TAIL_SPREAD(pp, cut[q].n_pairs) adj_pair_fill(S, pp); }      // the merged pair list of all ranks
+	else TAIL_SPREAD(sv, cut[q].n_surv) adj_pair_fill_surv(S, sv);
 	TAIL_SYNC();
 	WV_TP(35);
 	TAIL_SPREAD(j, n) adj_sort(S, j);

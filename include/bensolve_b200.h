@@ -149,6 +149,7 @@ typedef struct {
 	 * and how many of those passes were split across the ranks (several GPUs) */
 	uint64_t waves, wave_cuts, lookahead_passes, sharded_passes;
 	uint64_t sharded_cuts;     /* per-call path: cuts whose K1 was split across the ranks */
+	uint64_t sharded_pair_tests; /* waves whose pair test was split across the ranks */
 } b200_stats;
 int b200_poly_get_stats(poly_args *, b200_stats *out);
 /* flags: bit0 = time every K1 launch and every cut with CUDA events (adds two syncs per cut);

@@ -43,7 +43,7 @@ def main():
         capi.compare_states(a.state(), b.state(), exact_coords=True)
         st = b.stats()
         a.kill(); b.kill()
-        assert st["sharded_passes"] > 0 and st["sharded_passes"] == st["lookahead_passes"], st
+        assert st["sharded_passes"] > 0 and st["sharded_passes"] == st["lookahead_passes"] and st["sharded_pair_tests"] > 0, st
         n_wave += 1
     bdist.finalize_comm(emul)
     dist.barrier()

@@ -51,7 +51,7 @@ def main():
         assert ra == rb, tr.name
         capi.compare_states(a.state(), b.state(), exact_coords=True)
         st = b.stats()
-        assert st["sharded_passes"] > 0, st
+        assert st["sharded_passes"] > 0 and st["sharded_pair_tests"] > 0, st
         a.kill(); b.kill()
     torch.cuda.synchronize()
     dist.barrier()
