@@ -2256,7 +2256,7 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 		// several ranks: the look-ahead passes over large polytopes are sharded, exchanged over peer-mapped memory
 		WD_.nranks = (u32)nranks_;
 		WD_.rank = (u32)rank_;
-		WD_.shard_min_rows = tiny_test ? 0u : env_u32("B200_SHARD_MIN_ROWS_WAVE", 1500000);
+		WD_.shard_min_rows = tiny_test ? 0u : env_u32("B200_SHARD_MIN_ROWS_WAVE", 3000000);
 		if (nranks_ > 1) {
 #ifndef B200_EMULATE
 			xarea_setup(STREAM);
@@ -2276,7 +2276,10 @@ long CutEngine::cut_batch_from_device(const double *d_vals, const unsigned char 
 		memset(&wc, 0, sizeof wc);
 		wc.xseq = g_x.seq;
 		wc.xseq_k = g_x.seq_k;
-		wc.shard_k4 = (WD_.xksend && env_u32("B200_K4_SHARD", 1) != 0) ? 1u : 0u;
+		// (off by default: at the cut sizes of the measured workloads -- ~10^3 new vertices per cut -- the pair test of a
+		// wave is 40 us of latency-bound work and one more cross-rank rendezvous per iteration costs more than 7/8 of it
+		// saves: 46.4 k vs 48.5 k cuts/s on 8 ranks, 48.3 k vs 52.1 k on 2; it is for cuts with 10^4 new vertices)
+		wc.shard_k4 = (WD_.xksend && env_u32("B200_K4_SHARD", 0) != 0) ? 1u : 0u;
 		wc.n_total = (u32)n;
 		wc.facet0 = facet0;
 		wc.batch_first = batch_first;

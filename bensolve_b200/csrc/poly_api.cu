@@ -898,7 +898,7 @@ static void rebuild_mirror(poly_args *a, Handle *h, size_t first_slot)
 	};
 	unsigned nt = std::thread::hardware_concurrency();
 	nt = nt ? std::min(nt, (unsigned)std::max(1, atoi(getenv("B200_MIRROR_THREADS") ? getenv("B200_MIRROR_THREADS") : "16"))) : 1u;
-	nt = std::max(1u, nt / (unsigned)std::max(1, b200_comm_size()));      // one process per GPU: the ranks share the host's cores
+	if (b200_comm_size() > 1) nt = std::max(std::min(nt, 4u), nt / (unsigned)b200_comm_size());   // one process per GPU: the ranks share the host's cores
 	if (n < 65536) nt = 1;
 	std::vector<u32> cutp(nt + 1, n);
 	cutp[0] = 0;

@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 
 os.environ.setdefault("B200_SHARD_MIN_ROWS", "0")        # shard K1 of every cut, however small the polytope
 os.environ.setdefault("B200_SHARD_MIN_ROWS_WAVE", "0")   # and every look-ahead pass of the wave path
+os.environ.setdefault("B200_K4_SHARD", "1")              # and the pair test of every wave (opt-in otherwise)
 
 import ctypes as C  # noqa: E402
 
