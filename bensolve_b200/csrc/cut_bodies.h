@@ -95,10 +95,12 @@ B200_HD bool zp_activate(const DevState &S, const CutParams &P, u32 i)
 	if (!touch) return false;
 	int id = bit_test(S.ideal, v) ? 1 : 0;
 	double thr = id ? 0.0 : P.alpha;
-	double mu = B200_DIV(B200_SUB(row_dot(S, P.h, v), thr), P.hh);
-	for (int j = 0; j < S.d; j++) {
-		double *x = S.coord + (size_t)j * S.cap_rows + v;
-		*x = B200_SUB(*x, B200_MUL(mu, P.h[j]));
+	if (!P.zp_done) {                    // (a rerun after a bail-out finds the row already projected by the first attempt)
+		double mu = B200_DIV(B200_SUB(row_dot(S, P.h, v), thr), P.hh);
+		for (int j = 0; j < S.d; j++) {
+			double *x = S.coord + (size_t)j * S.cap_rows + v;
+			*x = B200_SUB(*x, B200_MUL(mu, P.h[j]));
+		}
 	}
 	double t = row_dot(S, P.h, v);
 	S.cls[v] = (t > P.lo[id]) ? CLS_ZERO : CLS_MINUS;   // re-test of bslv_poly.c:573 after :674

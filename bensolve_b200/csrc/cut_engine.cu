@@ -716,7 +716,7 @@ void CutEngine::launch_part_a(const CutParams &P)
 	const int gmap = num_sms_ * 4;
 	const int gcls = (int)std::max<u32>(1, std::min<u32>(ntiles, (u32)num_sms_ * 8));
 	if (dev_vals_)
-		k_begin_dev<<<1, 32, 0, STREAM>>>(S_, dev_vals_, dev_ideal_, dev_index_, P.facet, P.batch_first, P.seq);
+		k_begin_dev<<<1, 32, 0, STREAM>>>(S_, dev_vals_, dev_ideal_, dev_index_, P.facet, P.batch_first, P.seq, P.zp_done);
 	else
 		k_begin<<<1, 32, 0, STREAM>>>(S_, P);
 	if (flags_ & 1) CK(cudaEventRecord((cudaEvent_t)ev_[0], STREAM));
@@ -1220,6 +1220,7 @@ void CutEngine::run_cut(const CutParams &P, bool header_only)
 	for (int guard = 0; hdr_.status & redo; guard++) {
 		if (guard > 16) fail("bensolve_b200: capacity negotiation did not converge");
 		stats_.redo_loops++;
+		if (hdr_.n_zp_projected) Pq.zp_done = 1;    // the attempt that bailed out projected ZERO+ rows in place: not twice
 		if (hdr_.status & ST_NEED_BIG) {            // nothing was mutated: rerun through the multi-kernel path
 			small = false;
 			prefer_big_ = true;

@@ -94,7 +94,7 @@ __global__ void k_begin(DevState S, CutParams P)
 
 // begin for the device-resident batch path: the halfspace is built on the device from the dual
 // point vals[i] with the default callback's meaning (cone_polar, bslv_poly.c:30-39)
-__global__ void k_begin_dev(DevState S, const double *vals, const unsigned char *ideal, u64 i, u32 facet, u32 batch_first, u32 seq)
+__global__ void k_begin_dev(DevState S, const double *vals, const unsigned char *ideal, u64 i, u32 facet, u32 batch_first, u32 seq, u32 zp_done)
 {
 	if (threadIdx.x || blockIdx.x) return;
 	CutParams P;
@@ -115,7 +115,7 @@ __global__ void k_begin_dev(DevState S, const double *vals, const unsigned char 
 	P.facet = facet;
 	P.batch_first = batch_first;
 	P.seq = seq;
-	P.pad = 0;
+	P.zp_done = zp_done;
 	*S.cur = P;
 	CutCtl *c = S.ctl;
 	c->status = 0;

@@ -58,7 +58,8 @@ struct CutParams {
 	u32 facet;      // id of the new facet = dual slot of this halfspace
 	u32 batch_first; // primal.cnt when the host mirror was last coherent (sltn inheritance roots, bslv_poly.c:583-587)
 	u32 seq;         // sequence number the device publishes in the staged header when the record is complete
-	u32 pad;
+	u32 zp_done;     // 1: rerun of a cut that bailed out (capacity, size) AFTER its ZERO+ closure had projected rows in place
+	                 // (bslv_poly.c:666-674): the closure activates the same rows again but must not project them twice
 	double h1;       // sum |h_j| (wave path only: scale of the guard band of the look-ahead classification)
 };
 

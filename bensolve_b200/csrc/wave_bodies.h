@@ -131,7 +131,7 @@ B200_HD void wave_make_params(const DevState &S, const WaveCtl *w, const double 
 	P.facet = w->facet0 + hs;
 	P.batch_first = w->batch_first;
 	P.seq = 0;
-	P.pad = 0;
+	P.zp_done = 0;
 }
 
 // ---------------------------------------------------------------- start of an iteration

@@ -365,3 +365,10 @@ def test_gpu_full_size_properties_and_path_equality(product_lib, dim, n):
             assert st["waves"] > 0 and st["rows_scanned"] < st["vertex_evals"]
     assert digests[0] == digests[1]
     assert counts[0]["facets"] == n and counts[0]["vertices"] > n
+
+
+@pytest.mark.parametrize("dim", [3, 4, 5])
+@pytest.mark.parametrize("flags", [0, FLAG_MULTI_KERNEL, FLAG_FORCE_WIDE])
+def test_gpu_zero_plus_rows_are_projected_once(product_lib, checker, tiny_caps, dim, flags):
+    """ZERO+ closure followed by a capacity bail-out: the rerun must not project the rows again (CutParams::zp_done)."""
+    run_pair(checker, product_lib, P.cube_zero_plus(dim), stepwise=True, exact=True, flags_b=flags)

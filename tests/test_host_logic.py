@@ -353,3 +353,11 @@ def test_host_logic_wave_statistics(emul_lib):
     e.kill()
     assert st["cuts"] == len(rcs) - sum(rcs) and st["vertex_evals"] > 0 and st["algorithmic_bytes"] > 0
     assert st["rows_scanned"] < st["vertex_evals"]      # one pass over the coordinates serves many halfspaces
+
+
+@pytest.mark.parametrize("dim", [3, 4, 5])
+@pytest.mark.parametrize("flags", [0, 8])
+def test_host_logic_zero_plus_rows_are_projected_once(oracle_lib, emul_lib, tiny_caps, dim, flags):
+    """A cut whose ZERO+ closure has projected rows in place (bslv_poly.c:666-674) and then bails out for capacity is
+    rerun without projecting them a second time (CutParams::zp_done): bit-identical to the reference, which projects once."""
+    run_pair(oracle_lib, emul_lib, P.cube_zero_plus(dim), stepwise=True, exact=True, flags_b=flags)
