@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(64) k_wave_begin(DevState S, WaveDev W, const 
 		wv_copy_words(S.ctl, &mctl, sizeof mctl);
 	}
 	if (!w.halt && threadIdx.x < w.n_la) wave_la_init(S, W, w, threadIdx.x, vals, ideal);
+	if (threadIdx.x < B200_WAVE_SLOTS) W.wflag[threadIdx.x] = 0;       // wave formation flags of this iteration
 	wv_copy_words(W.wc, &w, sizeof w);
 	if (tr) tr[44] = b200_globaltimer();
 	if (threadIdx.x == 0) wave_publish(W, w, mctl.nrows, mctl.n_live);
@@ -428,7 +429,9 @@ __global__ void __launch_bounds__(K_THREADS) k_wave_mark(DevState S, WaveDev W)
 	WV_TRACE(2);
 	const u32 nc = wave_stage_candidates(W, w, off, nl);
 	if (!nc) return;
-	if (blockIdx.x == 0 && threadIdx.x < nc) W.wflag[threadIdx.x] = W.ctl[w.pending[threadIdx.x]].n_list > B200_WAVE_LIST ? 2u : 0u;
+	// (the flags were cleared by k_wave_begin: other blocks of this grid may already be OR-ing bit 1 into them, so a plain
+	// store here could lose one)
+	if (blockIdx.x == 0 && threadIdx.x < nc && W.ctl[w.pending[threadIdx.x]].n_list > B200_WAVE_LIST) atomicOr(W.wflag + threadIdx.x, 2u);
 	const u32 total = off[nc], epoch = w.epoch;
 	for (u32 x = blockIdx.x * K_THREADS + threadIdx.x; x < total; x += gridDim.x * K_THREADS) {
 		u32 p = 0;
