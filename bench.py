@@ -395,7 +395,8 @@ def run_b200(a, trace):
             "workload": f"pure H->V enumeration, random tangent polytope in R^{d}, {n} halfspaces, seed {a.seed}",
             "live_vertices": int(n_live), "slots": int(per_step["slots"]), "facets": int(per_step["facets"]),
             "l2": "step: coordinates (%.0f MB) stay L2-resident across cuts, inherent to the workload; roofline.k1: L2 flushed (read sweep over 256 MB) before every timed K1 launch" % (n_live * 8 * d / 1e6),
-            "multi_gpu": (f"{world} ranks: state replicated, classification sharded by row range, rest of the cut replicated" if world > 1 else "single"),
+            "multi_gpu": (f"{world} ranks, one process per GPU: state replicated; look-ahead passes split by row group and exchanged over peer-mapped memory from 3M rows, "
+                          f"K1 of a per-call cut split + NCCL all-gather from 4M rows, replicated (nothing exchanged) below; rest of the cut replicated" if world > 1 else "single"),
             "timed_region": "first cut after poly__intl_apprx .. last cut returned with a coherent host mirror; polytope creation (poly__initialise, b200_poly_reserve with the warm-up's counts = all device and host allocation, start simplex) and poly__kill lie between steps, untimed; e2e_unchanged_caller is the figure without any of that help",
         },
         "vertex_evals_per_s": evals_per_s,
