@@ -14,7 +14,8 @@ coherent host mirror.
             around poly__add_vrtx is the C caller's (b200_poly_add_each = what bslv_algs.c writes),
             not a Python loop.  e2e_unchanged_caller: the same without b200_poly_reserve and without a
             recycled host block (first polytope of the process); e2e_batch: all halfspaces handed over
-            in one call from host memory (b200_poly_add_batch, an extension)
+            in one call from host memory (b200_poly_add_batch, an extension); e2e_vertenum: the unchanged
+            API used the way bensolve enumerates vertices (queue everything, then poly__intl_apprx)
     roofline : frac = SURVEY 8(d)'s sequence figure, sum over cuts of the algorithmic bytes B_c divided
                by the step time, against MEASURED_PEAKS.json hbm_gbs; roofline.k1 = the classify kernel
                timed alone with CUDA events on its own stream with an L2 flush before each launch
@@ -263,6 +264,20 @@ def run_b200(a, trace):
         e.kill()
         return None, st, dt
 
+    def step_vertenum():
+        """cone_vertenum's call pattern (bslv_algs.c:331-350) through the unchanged API, no b200_* call at all: every halfspace
+        queued with poly__add_vrtx, then poly__intl_apprx (which re-adds them, bslv_poly.c:190-197 -- as one device-resident batch)."""
+        e = capi.PolyEngine(lib, d)
+        barrier()
+        t0 = time.perf_counter()
+        e.add_each(trace.vals)            # (b200_poly_add_each = the caller's loop around poly__add_vrtx; before initialisation it only queues)
+        assert e.init_approx() == 0
+        barrier()
+        dt = time.perf_counter() - t0
+        st = e.stats()
+        e.kill()
+        return st, dt
+
     # ---- what an UNCHANGED caller gets: first large polytope of the process, no b200_poly_reserve (bslv_algs.c never
     # calls it), no recycled host block; only the CUDA context exists (a 3-d polytope of 40 halfspaces ran before,
     # as bensolve's own cone_vertenum does before its main loop)
@@ -298,6 +313,13 @@ def run_b200(a, trace):
             _, st_b, dt = step_e2e(batch=True)
             t_e2e_batch += dt
             cuts_eb += st_b["cuts"]; launches_eb += st_b["kernel_launches"]
+        t_vn = 0.0
+        cuts_vn = launches_vn = 0
+        step_vertenum()
+        for k in range(a.steps):
+            st_v, dt = step_vertenum()
+            t_vn += dt
+            cuts_vn += st_v["cuts"]; launches_vn += st_v["kernel_launches"]
         eng = eng_keep
         # K1 alone on the final polytope of the last value step
         st_final = eng.stats()
@@ -318,9 +340,9 @@ def run_b200(a, trace):
 
     # max over ranks (strong scaling: every rank takes part in every cut)
     if dist is not None:
-        tt = torch.tensor([t_value, t_e2e, t_e2e_batch, t_pv, t_pe, dt_cold], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t_value, t_e2e, t_e2e_batch, t_pv, t_pe, dt_cold, t_vn], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_value, t_e2e, t_e2e_batch, t_pv, t_pe, dt_cold = (float(x) for x in tt)
+        t_value, t_e2e, t_e2e_batch, t_pv, t_pe, dt_cold, t_vn = (float(x) for x in tt)
 
     # ---------------- parity gate (before any number counts)
     parity = {"ok": False}
@@ -408,7 +430,11 @@ def run_b200(a, trace):
         "e2e_batch": {"value": cuts_eb / t_e2e_batch, "unit": "cuts/s", "ms_per_step": 1e3 * t_e2e_batch / a.steps,
                       "h2d_bytes_per_step": (n - d) * 8 * d, "d2h_bytes_per_step": int(per_step["slots"] * (8 * d + 9) + 4 * (n - d)),
                       "call": "b200_poly_add_batch (extension): all halfspaces in one call from host memory, host mirror coherent at return"},
-        "gpu_launches": int(launches_v + launches_e + launches_eb),
+        "e2e_vertenum": {"value": cuts_vn / t_vn, "unit": "cuts/s", "ms_per_step": 1e3 * t_vn / a.steps,
+                         "h2d_bytes_per_step": n * 8 * d, "d2h_bytes_per_step": int(per_step["slots"] * (8 * d + 9) + 4 * n),
+                         "call": "the UNCHANGED API the way bensolve enumerates vertices (cone_vertenum, bslv_algs.c:331-350): every halfspace queued with poly__add_vrtx, then poly__intl_apprx; "
+                                 "no b200_* extension, no reserve; timed from the first poly__add_vrtx to the return of poly__intl_apprx (growth included)"},
+        "gpu_launches": int(launches_v + launches_e + launches_eb + launches_vn),
         "roofline": {"bound": "hbm", "kernel": "whole cut sequence (SURVEY 8(d): sum over cuts of B_c / T_total); dominant kernels by the launch list in profiles/: see roofline.launch_list",
                      "achieved": seq_achieved, "peak": peak, "unit": "GB/s", "frac": seq_achieved / peak,
                      "traffic": None, "peak_source": peak_src,

@@ -521,6 +521,25 @@ extern "C" int poly__intl_apprx(poly_args *a)
 	a->init_data.intlsd = 1;
 	// queued halfspaces that were not chosen are retired and re-added as fresh dual slots (:190-197)
 	for (size_t q = 0; q < Qu->cnt; q++) UNST_BT(a->dual.used, Qu->data[q]);
+	// A caller that enumerates vertices queues ALL its halfspaces before this call (cone_vertenum, bslv_algs.c:331-350) and
+	// reads the result only after it returns: the re-adds are a known sequence, so they go through the device-resident
+	// path (look-ahead + waves, host mirror rebuilt once) -- same slots, same order, same result as the loop below.
+	static const size_t batch_from = [] { const char *e = getenv("B200_INIT_BATCH_MIN"); return (size_t)(e ? atol(e) : 32); }();
+	const bool batch = Qu->cnt >= batch_from && !a->dim_primg_dl && to_hp == default_dual_to_halfspace;
+	if (batch) {
+		std::vector<double> vals(Qu->cnt * d);
+		std::vector<unsigned char> idl(Qu->cnt);
+		for (size_t q = 0; q < Qu->cnt; q++) {
+			const size_t src = Qu->data[q];
+			memcpy(vals.data() + q * d, a->dual.data + src * d, d * sizeof(double));
+			idl[q] = (unsigned char)IS_ELEM(a->dual.ideal, src);
+		}
+		if (b200_poly_add_batch(a, vals.data(), idl.data(), Qu->cnt, NULL) < 0) die("poly__intl_apprx", b200_last_error());
+		if (Qu->cnt) {                  // what the last poly__add_vrtx of the loop would have left in the caller-visible fields
+			memcpy(a->val, vals.data() + (Qu->cnt - 1) * d, d * sizeof(double));
+			a->ideal = idl[Qu->cnt - 1];
+		}
+	} else
 	for (size_t q = 0; q < Qu->cnt; q++) {
 		const size_t src = Qu->data[q];
 		for (size_t j = 0; j < d; j++) a->val[j] = a->dual.data[src * d + j];

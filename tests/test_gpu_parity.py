@@ -372,3 +372,11 @@ def test_gpu_full_size_properties_and_path_equality(product_lib, dim, n):
 def test_gpu_zero_plus_rows_are_projected_once(product_lib, checker, tiny_caps, dim, flags):
     """ZERO+ closure followed by a capacity bail-out: the rerun must not project the rows again (CutParams::zp_done)."""
     run_pair(checker, product_lib, P.cube_zero_plus(dim), stepwise=True, exact=True, flags_b=flags)
+
+
+@pytest.mark.parametrize("tr", [P.tangent_polytope(4, 300, 3), P.tangent_polytope(6, 300, 88), P.tangent_polytope(5, 1500, 88), P.lattice_polytope(4, 60, 2),
+                                P.mixed_polyhedron(4, 80, 5), P.random_cone(5, 40, 2), P.random_offsets(4, 90, 1)], ids=lambda t: t.name)
+def test_gpu_vertex_enumeration_through_intl_apprx(product_lib, checker, tr):
+    """cone_vertenum's call pattern (bslv_algs.c:331-350) with the UNCHANGED API: everything queued, then poly__intl_apprx;
+    inside, the re-adds run as one device-resident batch (look-ahead + waves)."""
+    run_pair(checker, product_lib, P.Trace(tr.dim, tr.vals, tr.ideal, len(tr.vals), tr.name + "_queued"), exact=True)

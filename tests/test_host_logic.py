@@ -361,3 +361,16 @@ def test_host_logic_zero_plus_rows_are_projected_once(oracle_lib, emul_lib, tiny
     """A cut whose ZERO+ closure has projected rows in place (bslv_poly.c:666-674) and then bails out for capacity is
     rerun without projecting them a second time (CutParams::zp_done): bit-identical to the reference, which projects once."""
     run_pair(oracle_lib, emul_lib, P.cube_zero_plus(dim), stepwise=True, exact=True, flags_b=flags)
+
+
+def _queue_all(tr):
+    """The same halfspaces handed over the way cone_vertenum does (bslv_algs.c:331-350): all queued, then poly__intl_apprx."""
+    return P.Trace(tr.dim, tr.vals, tr.ideal, len(tr.vals), tr.name + "_queued")
+
+
+@pytest.mark.parametrize("tr", [P.tangent_polytope(4, 300, 3), P.tangent_polytope(6, 60, 5), P.lattice_polytope(4, 60, 2), P.mixed_polyhedron(4, 80, 5),
+                                P.random_cone(5, 40, 2), P.random_offsets(4, 90, 1), P.cube_zero_plus(4)], ids=lambda t: t.name)
+def test_host_logic_vertex_enumeration_through_intl_apprx(ref_lib, emul_lib, tr):
+    """All halfspaces queued before poly__intl_apprx: the re-adds inside it (bslv_poly.c:190-197) run as one device-resident
+    batch from 32 queued halfspaces on; the result is the reference's, which re-adds them one by one."""
+    run_pair(ref_lib, emul_lib, _queue_all(tr), exact=True)
