@@ -46,6 +46,13 @@ def main():
         a.kill(); b.kill()
         assert st["sharded_passes"] > 0 and st["sharded_passes"] == st["lookahead_passes"] and st["sharded_pair_tests"] > 0, st
         n_wave += 1
+    # cone_vertenum's pattern on several ranks: everything queued, poly__intl_apprx re-adds it as one device-resident batch
+    for tr in (P.tangent_polytope(4, 200, 9), P.random_cone(5, 40, 2)):
+        q = P.Trace(tr.dim, tr.vals, tr.ideal, len(tr.vals), tr.name + "_queued")
+        a, b = capi.PolyEngine(oracle, q.dim), capi.PolyEngine(emul, q.dim)
+        assert P.replay(a, q) == P.replay(b, q)
+        capi.compare_states(a.state(), b.state(), exact_coords=True)
+        a.kill(); b.kill()
     bdist.finalize_comm(emul)
     dist.barrier()
     print(f"rank {rank}: {len(traces)} traces OK, {n_wave} wave traces OK", flush=True)
